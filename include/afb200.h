@@ -1,0 +1,174 @@
+/*
+ * afb200.h — C ABI of libafb200.so, the B200-native (sm_100a) AltFreezing
+ * clip-classification hot path.
+ *
+ * The reference (Mariachiar/Spatiotemporal-Deepfake-Detection-for-Live-Video-Calls)
+ * is pure Python and has no FFI of its own; every entry point below names the
+ * reference interface it stands in for (paths relative to the reference root).
+ * Conventions: plain pointers and sizes only, no C++/torch types; every call
+ * returns an af_status (0 = ok, negative = error) and never throws; the text of
+ * the last error on the calling thread is af_last_error().  Device pointers are
+ * owned by the caller (PyTorch's allocator in the Python host); the engine owns
+ * its weights and workspace.  Calls on one handle are not re-entrant (the
+ * reference's services are single-threaded singletons, altfreezing/TEST2.py:64-70).
+ * `stream` is a cudaStream_t passed as void* (0 = the legacy default stream); all
+ * *_dev entry points are asynchronous on it.
+ */
+#ifndef AFB200_H
+#define AFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFB200_VERSION 100
+
+typedef struct af_engine* af_handle;
+
+typedef enum {
+  AF_OK = 0,
+  AF_ERR_INVALID = -1,      /* bad argument / unsupported shape                     */
+  AF_ERR_CUDA = -2,         /* a CUDA runtime/driver call failed (see af_last_error) */
+  AF_ERR_UNSUPPORTED = -3,  /* no sm_100 device                                      */
+  AF_ERR_NOMEM = -4
+} af_status;
+
+typedef enum { AF_F32 = 0, AF_BF16 = 1, AF_F16 = 2, AF_U8 = 3 } af_dtype;
+
+/* Arithmetic of the trunk. FP32: fp32 activations/weights/accumulate (parity gate
+ * 1e-3 on logits). BF16: bf16 activations/weights, fp32 accumulate on tcgen05
+ * tensor cores (parity gate 2e-2 and same decision at logit 0). */
+typedef enum { AF_PREC_FP32 = 0, AF_PREC_BF16 = 1 } af_precision;
+
+/* One Conv3d with its eval-mode BatchNorm3d already folded by the host
+ * (W' = W*gamma/sqrt(var+eps), b' = beta - mean*gamma/sqrt(var+eps)).
+ * Replaces nn.Conv3d + nn.BatchNorm3d pairs built at
+ * altfreezing/slowfast/models/stem_helper.py:156-171 and resnet_helper.py:255-309,411-423. */
+typedef struct {
+  const float* weight; /* host, [cout][cin][kt][kh][kw] fp32 (PyTorch Conv3d layout) */
+  const float* bias;   /* host, [cout] fp32                                          */
+  int32_t cin, cout;
+  int32_t kt, kh, kw;
+  int32_t st, sh, sw;
+  int32_t pt, ph, pw;
+} af_conv_desc;
+
+/* One bottleneck ResBlock: relu(shortcut + c(b(a(x)))) — resnet_helper.py:438-444,311-326.
+ * Indices into af_weights.convs; branch1 = -1 for identity shortcuts. */
+typedef struct {
+  int32_t branch1, a, b, c;
+  int32_t temporal_pool_before; /* 1: MaxPool3d [2,1,1] on the block input
+                                   (pathway0_pool, video_model_builder.py:474-480,566-568) */
+} af_block_desc;
+
+/* The whole network: stem conv (+BN+ReLU) + MaxPool3d [1,3,3]/[1,2,2]/[0,1,1]
+ * (stem_helper.py:173-178), the blocks, global average pool + Linear(F->1)
+ * (head_helper.py:74-95). */
+typedef struct {
+  int32_t n_convs;
+  const af_conv_desc* convs;
+  int32_t stem;            /* index of the stem conv */
+  int32_t n_blocks;
+  const af_block_desc* blocks;
+  const float* fc_weight;  /* host, [feature_dim] */
+  float fc_bias;
+  int32_t feature_dim;     /* 2048 */
+  int32_t clip_t, clip_s;  /* 32, 224 (cfg.clip_size, cfg.imsize; setting/i3d_ori.yaml:20,60) */
+} af_weights;
+
+/* Per-frame source description for the crop kernel: one decoded RGB (or BGR) u8
+ * frame in device memory and that frame's enlarged face box ("big box",
+ * altfreezing/test_tools/utils.py:13-24), exclusive lower-right corner. */
+typedef struct {
+  const uint8_t* data; /* device pointer to pixel (0,0), 3 interleaved channels */
+  int64_t pitch;       /* bytes per row */
+  int32_t height, width;
+  int32_t box[4];      /* x1, y1, x2, y2 in frame coordinates */
+} af_frame_desc;
+
+/* Per-clip geometry computed on the host by the similarity estimator
+ * (altfreezing/test_tools/warp_for_xray.py:556-560) and the union-box logic of
+ * FasterCropAlignXRay.__call__ (faster_crop_align_xray.py:22-50). */
+typedef struct {
+  double tfm[6];        /* forward 2x3 map canvas -> SxS crop, row-major */
+  int32_t left_top[2];  /* canvas origin in frame coordinates (x, y)     */
+  int32_t canvas_wh[2]; /* canvas size (w, h) = union of the clip's big boxes */
+} af_clip_geom;
+
+const char* af_last_error(void);
+int32_t af_version(void);
+/* Number of the engine's own CUDA kernel launches since creation (bench "gpu_launches"). */
+int64_t af_launch_count(af_handle h);
+
+/* Build an engine on `device`: uploads and re-lays-out the folded weights, allocates
+ * the activation workspace for up to max_batch clips per call.
+ * Replaces `PluginLoader.get_classifier("i3d_ori")().to(device).eval()` + `.load(ckpt)`
+ * (altfreezing/demo.py:403-404; model/_base.py:20-23,39-104) for the device side. */
+af_status af_create(af_handle* out, int32_t device, const af_weights* w, int32_t max_batch,
+                    int32_t precision);
+af_status af_destroy(af_handle h);
+
+/* Tuning knobs (chunk sizes of the batch schedule); name/value pairs, optional. */
+af_status af_set_option(af_handle h, const char* name, int64_t value);
+
+/* clf(x)["final_output"]: x is a normalised clip tensor [B,3,T,S,S] of `dtype` in device
+ * memory with arbitrary element strides (B,C,T,H,W) — contiguous NCTHW, a permuted NTHWC
+ * view (demo.py:317) or channels_last_3d (TEST2.py:155).  Writes fp32 logits [B] (no
+ * activation, head_helper.py:90-94) and, if non-null, the pooled features [B,feature_dim]
+ * (the input of head.projection that altfreezing/feature.py:106-114 hooks).
+ * Replaces ModelBase.forward -> I3D8x8.forward -> ResNet.forward
+ * (model/_base.py:25-26, model/classifier/i3d_ori.py:92-104, video_model_builder.py:561-578). */
+af_status af_forward(af_handle h, const void* clip_dev, int32_t dtype, const int64_t strides[5],
+                     int32_t batch, float* logits_dev, float* features_dev, void* stream);
+
+/* ClassifierSvc.infer_scores (altfreezing/TEST2.py:151-204, test/af_realtime.py:75-96) on
+ * device buffers: u8 aligned clips [B,T,S,S,3] RGB -> (x-255*mean)/(255*std) -> trunk ->
+ * logits [B] (and sigmoid scores [B] if scores_dev != NULL). mean/std are the three
+ * per-channel constants already multiplied by 255 (demo.py:84-87). */
+af_status af_infer_u8(af_handle h, const uint8_t* clips_dev, int32_t batch, const float mean255[3],
+                      const float std255[3], float* logits_dev, float* scores_dev,
+                      float* features_dev, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies the u8 clips to the device,
+ * runs af_infer_u8, copies logits/scores back and synchronises the stream. This is the
+ * end-to-end entry the benchmark's `e2e` number is measured through. */
+af_status af_infer_u8_host(af_handle h, const uint8_t* clips_host, int32_t batch,
+                           const float mean255[3], const float std255[3], float* logits_host,
+                           float* scores_host, void* stream);
+
+/* FasterCropAlignXRay.process_single for a batch of clips, bit-exact with
+ * cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) (faster_crop_align_xray.py:77-88):
+ * gathers straight from the decoded frames (frames[b*T+t]), masks to each frame's big
+ * box, writes u8 [B,T,S,S,3].  `frames_dev` and `geom_dev` are device arrays.
+ * bgr != 0 swaps channels 0 and 2 while reading (decoded BGR -> RGB, demo.py:245-269). */
+af_status af_crop_u8(const af_frame_desc* frames_dev, const af_clip_geom* geom_dev, int32_t batch,
+                     int32_t frames_per_clip, int32_t size, int32_t bgr, uint8_t* out_dev,
+                     void* stream);
+
+/* Fused fast path: the same warp, normalised and written directly into the engine's
+ * internal clip layout, followed by the trunk.  Replaces crop_align_func + the three
+ * torch pack lines + classifier(images_t) of the hot loop (demo.py:309-328). */
+af_status af_crop_infer(af_handle h, const af_frame_desc* frames_dev, const af_clip_geom* geom_dev,
+                        int32_t batch, int32_t bgr, const float mean255[3], const float std255[3],
+                        float* logits_dev, float* scores_dev, float* features_dev, void* stream);
+
+/* Test/diagnostic entry: one conv (+bias, +residual, +ReLU) on NDHWC device tensors of the
+ * engine's precision (fp32 or bf16), through the same kernels the trunk uses.
+ * impl: 0 = engine's choice, 1 = force the SIMT kernel, 2 = force the tcgen05 kernel. */
+af_status af_conv_ndhwc(const void* x_dev, const af_conv_desc* conv_host, const void* residual_dev,
+                        void* y_dev, int32_t batch, int32_t t, int32_t hgt, int32_t wid,
+                        int32_t relu, int32_t precision, int32_t impl, void* stream);
+
+/* Copy intermediate activations of the LAST af_forward/af_infer call out for stage
+ * parity tests: which = 1..5 (s1..s5 outputs) as fp32 NCTHW [B,C,T,H,W] into out_dev.
+ * Requires option "keep_stages" = 1 (costs extra memory). */
+af_status af_get_stage(af_handle h, int32_t which, float* out_dev, int64_t capacity_elems,
+                       int32_t dims_out[5], void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFB200_H */

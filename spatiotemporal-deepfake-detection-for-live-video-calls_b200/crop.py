@@ -1,0 +1,174 @@
+"""Host side of the crop/align step: the per-clip geometry (numpy, fp64) and the
+FasterCropAlignXRay-compatible wrapper around the K1 CUDA kernel.
+
+  get_crop_box                     <- altfreezing/test_tools/utils.py:13-24
+  estimate_clip_transform          <- warp_for_xray.py:556-560 -> :496-529 -> findSimilarity :337-425
+                                      -> findNonreflectiveSimilarity :224-334
+  clip_geometry / CropAlignB200    <- FasterCropAlignXRay.__call__ faster_crop_align_xray.py:21-75
+
+The pixels are produced on the GPU (csrc/crop_pack.cu); only the 4-dof least-squares fit
+(a [2*5T,4] system, ~0.3 ms) and the landmark transforms stay on the host.
+"""
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ._lib import AfClipGeom, AfFrameDesc, check, lib
+
+_STD_317 = np.array([[85.82991, 115.7792], [169.0532, 114.3381], [127.574, 167.0006],
+                     [90.6964, 204.7014], [167.3069, 203.3733]]) + 30.0
+STD_POINTS_256 = _STD_317.copy()
+STD_POINTS_256[:, 0] -= 30.0
+STD_POINTS_256[:, 1] -= 60.0
+
+
+def get_crop_box(shape, box, scale=0.5):
+    """Enlarge a detector box by `scale` of its size on every side, clip to the frame,
+    round to int -> (x1, y1, x2, y2)."""
+    height, width = shape
+    b = np.rint(np.asarray(box, np.float64)).astype(int).reshape(2, 2)
+    half = scale * (b[1] - b[0])
+    nb = b + np.stack([-half, half])
+    nb[:, 0] = np.clip(nb[:, 0], 0, width - 1)
+    nb[:, 1] = np.clip(nb[:, 1], 0, height - 1)
+    return np.rint(nb).astype(int).reshape(-1)
+
+
+def _fit_nonreflective(src, dst):
+    """Least-squares non-reflective similarity: returns the 3x3 `T` with [dst 1] = [src 1] @ T
+    (solves for the inverse map dst->src, then inverts it, as the reference does)."""
+    n = dst.shape[0]
+    x, y = dst[:, 0:1], dst[:, 1:2]
+    one, zero = np.ones((n, 1)), np.zeros((n, 1))
+    X = np.vstack((np.hstack((x, y, one, zero)), np.hstack((y, -x, zero, one))))
+    U = np.vstack((src[:, 0:1], src[:, 1:2]))
+    if np.linalg.matrix_rank(X) < 4:
+        raise ValueError("similarity fit needs at least two distinct points")
+    r = np.squeeze(np.linalg.lstsq(X, U, rcond=-1)[0])
+    T = np.linalg.inv(np.array([[r[0], -r[1], 0.0], [r[1], r[0], 0.0], [r[2], r[3], 1.0]]))
+    T[:, 2] = (0.0, 0.0, 1.0)
+    return T
+
+
+def _apply(T, pts):
+    return (np.hstack((pts, np.ones((pts.shape[0], 1)))) @ T)[:, :2]
+
+
+def estimate_clip_transform(src_pts_t52, tgt_pts_52) -> Tuple[np.ndarray, np.ndarray]:
+    """One similarity for the whole clip from all T x 5 landmark pairs -> (tfm 2x3, trans 3x3).
+
+    Behavioural quirk kept on purpose: the reference reflects its target array IN PLACE
+    before fitting the mirrored candidate (`xyR = xy` is an alias, warp_for_xray.py:404-405),
+    so BOTH residuals are measured against the mirrored targets."""
+    src = np.asarray(src_pts_t52, np.float64).reshape(-1, 2)
+    dst = np.repeat(np.asarray(tgt_pts_52, np.float64)[None], len(src_pts_t52), 0).reshape(-1, 2)
+    direct = _fit_nonreflective(src, dst)
+    dst[:, 0] *= -1.0
+    mirrored = _fit_nonreflective(src, dst) @ np.diag([-1.0, 1.0, 1.0])
+    e_direct = np.linalg.norm(_apply(direct, src) - dst)
+    e_mirrored = np.linalg.norm(_apply(mirrored, src) - dst)
+    trans = direct if e_direct <= e_mirrored else mirrored
+    return trans[:, 0:2].T.copy(), trans
+
+
+def clip_geometry(big_boxes, lm5_rel, size=224):
+    """left_top, canvas (w,h), per-frame offset, tfm, trans for one clip.
+    big_boxes: [T,4] int frame coordinates; lm5_rel: [T,5,2] relative to each frame's big box."""
+    boxes = np.asarray(big_boxes)
+    left_top = boxes[:, :2].min(0)
+    w, h = boxes[:, 2:].max(0) - left_top
+    diff = boxes[:, :2] - left_top[None]
+    lm5 = np.asarray(lm5_rel, np.float64) + diff[:, None, :]
+    tfm, trans = estimate_clip_transform(lm5, STD_POINTS_256 * size / 256.0)
+    return left_top, (int(w), int(h)), diff, tfm, trans
+
+
+def pack_descriptors(frame_tensors: Sequence[torch.Tensor], big_boxes, geoms, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Build the device arrays af_crop_u8 / af_crop_infer take.
+    frame_tensors: B*T u8 CUDA tensors [H,W,3] (may alias one another; may be row-strided views);
+    big_boxes: [B*T,4]; geoms: list of (tfm 2x3, left_top (x,y), canvas (w,h)) per clip."""
+    n = len(frame_tensors)
+    fd = (AfFrameDesc * n)()
+    for i, (ft, bb) in enumerate(zip(frame_tensors, big_boxes)):
+        if isinstance(ft, torch.Tensor):
+            assert ft.dtype == torch.uint8 and ft.dim() == 3 and ft.shape[2] == 3 and ft.stride(2) == 1 and ft.stride(1) == 3
+            ptr, pitch, hh, ww = ft.data_ptr(), ft.stride(0), ft.shape[0], ft.shape[1]
+        else:                       # raw (device pointer, pitch, height, width)
+            ptr, pitch, hh, ww = ft
+        fd[i].data = ptr
+        fd[i].pitch = pitch
+        fd[i].height, fd[i].width = hh, ww
+        for k in range(4):
+            fd[i].box[k] = int(bb[k])
+    cg = (AfClipGeom * len(geoms))()
+    for i, (tfm, lt, wh) in enumerate(geoms):
+        flat = np.asarray(tfm, np.float64).reshape(-1)
+        for k in range(6):
+            cg[i].tfm[k] = float(flat[k])
+        cg[i].left_top[0], cg[i].left_top[1] = int(lt[0]), int(lt[1])
+        cg[i].canvas_wh[0], cg[i].canvas_wh[1] = int(wh[0]), int(wh[1])
+    fd_t = torch.frombuffer(bytearray(bytes(fd)), dtype=torch.uint8).to(device)
+    cg_t = torch.frombuffer(bytearray(bytes(cg)), dtype=torch.uint8).to(device)
+    return fd_t, cg_t
+
+
+def crop_u8(frame_tensors, big_boxes, geoms, frames_per_clip, size=224, bgr=False, device=None) -> torch.Tensor:
+    """GPU warp of B clips -> u8 [B,T,S,S,3] on the device (bit-exact with cv2.warpAffine)."""
+    dev = device if device is not None else frame_tensors[0].device
+    B = len(geoms)
+    fd_t, cg_t = pack_descriptors(frame_tensors, big_boxes, geoms, dev)
+    out = torch.empty((B, frames_per_clip, size, size, 3), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().af_crop_u8(C.c_void_p(fd_t.data_ptr()), C.c_void_p(cg_t.data_ptr()), B, frames_per_clip, size,
+                               int(bgr), C.c_void_p(out.data_ptr()),
+                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "af_crop_u8")
+    return out
+
+
+class CropAlignB200:
+    """Drop-in for FasterCropAlignXRay(size): `(landmarks, images) -> (lm68_T, u8 [T,S,S,3])`.
+    landmarks: list of (box, lm5, lm68, big_box) with lm coordinates relative to the big box;
+    images: list of HxWx3 u8 crops (numpy; views are fine).  The crops are uploaded and warped
+    by the CUDA kernel; results come back as numpy like the reference's."""
+
+    def __init__(self, size=256, return_ldm5=False, device=0):
+        self.image_size = size
+        self.std_points = STD_POINTS_256 * size / 256.0
+        self.return_ldm5 = return_ldm5
+        self.device = torch.device("cuda", device)
+
+    def __call__(self, landmarks, images=None, jitter=False):
+        landmarks = [lm[:4] for lm in landmarks]
+        boxes = np.array([lm[3] for lm in landmarks])
+        lm5 = np.array([lm[1] for lm in landmarks])
+        lm68 = np.array([lm[2] for lm in landmarks])
+        left_top = boxes[:, :2].min(0)
+        w, h = boxes[:, 2:].max(0) - left_top
+        diff = boxes[:, :2] - left_top[None]
+        new5 = lm5 + diff[:, None, :]
+        new68 = lm68 + diff[:, None, :]
+        fit = new5.copy()
+        if jitter:
+            fit += np.random.uniform(-4, 4, fit.shape)
+        tfm, trans = estimate_clip_transform(fit, self.std_points)
+        t68 = np.array([_apply(trans, l) for l in new68])
+        t5 = np.array([_apply(trans, l) for l in new5])
+        if images is None:
+            return (t5, t68) if self.return_ldm5 else t68
+        # Each crop is uploaded as is and addressed in CANVAS coordinates: the descriptor's
+        # base pointer is moved back by the crop's offset d inside the canvas, so canvas pixel
+        # (x,y) resolves to crop pixel (x-d.x, y-d.y); the box mask keeps every read inside the crop.
+        keep, descs, bbs = [], [], []
+        for img, d in zip(images, diff):
+            t = torch.from_numpy(np.ascontiguousarray(img)).to(self.device)
+            keep.append(t)
+            ih, iw = img.shape[:2]
+            pitch = iw * 3
+            descs.append((t.data_ptr() - (int(d[1]) * pitch + int(d[0]) * 3), pitch, int(h), int(w)))
+            bbs.append((int(d[0]), int(d[1]), int(d[0]) + iw, int(d[1]) + ih))
+        out = crop_u8(descs, bbs, [(tfm, (0, 0), (int(w), int(h)))], len(images), self.image_size,
+                      device=self.device)
+        imgs = out[0].cpu().numpy()
+        return (t5, t68, imgs) if self.return_ldm5 else (t68, imgs)

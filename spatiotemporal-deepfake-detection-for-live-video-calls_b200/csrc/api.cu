@@ -1,0 +1,550 @@
+// C-ABI entry points and the engine (weights, workspace, batch schedule) of libafb200.so.
+// Public contract: include/afb200.h.  The schedule restates ResNet.forward
+// (altfreezing/slowfast/models/video_model_builder.py:561-578): stem -> s2 -> temporal
+// max-pool -> s3 -> s4 -> s5 -> head, with every BatchNorm folded into its conv and the
+// residual add + ReLU fused into the `c` conv's epilogue (resnet_helper.py:438-444).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/afb200.h"
+#include "common.cuh"
+
+namespace afb {
+
+static thread_local char g_err[1024] = "";
+thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+struct ConvLayer {
+  int cin, cout, cin_p;
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+  float* w_simt = nullptr;  // [taps][cin_p][cout] fp32 (bf16-rounded values in bf16 precision)
+  bf16* w_umma = nullptr;   // [taps][cout][cin_p] bf16 (bf16 precision only)
+  float* bias = nullptr;    // [cout]
+};
+
+static void free_layer(ConvLayer& L) {
+  if (L.w_simt) cudaFree(L.w_simt);
+  if (L.w_umma) cudaFree(L.w_umma);
+  if (L.bias) cudaFree(L.bias);
+  L.w_simt = nullptr; L.w_umma = nullptr; L.bias = nullptr;
+}
+
+// Re-lay-out one folded conv for the kernels and upload it.
+static int upload_layer(const af_conv_desc& d, bool is_bf16, ConvLayer& L) {
+  L.cin = d.cin; L.cout = d.cout; L.cin_p = (d.cin + 3) / 4 * 4;
+  L.kt = d.kt; L.kh = d.kh; L.kw = d.kw; L.st = d.st; L.sh = d.sh; L.sw = d.sw;
+  L.pt = d.pt; L.ph = d.ph; L.pw = d.pw;
+  const int taps = d.kt * d.kh * d.kw;
+  const size_t n = (size_t)taps * L.cin_p * d.cout;
+  std::vector<float> ws(n, 0.f);
+  std::vector<bf16> wu;
+  if (is_bf16) wu.assign(n, __float2bfloat16_rn(0.f));
+  for (int co = 0; co < d.cout; ++co)
+    for (int ci = 0; ci < d.cin; ++ci)
+      for (int tp = 0; tp < taps; ++tp) {
+        float v = d.weight[((size_t)co * d.cin + ci) * taps + tp];
+        if (is_bf16) {
+          v = bf16_round(v);
+          wu[((size_t)tp * d.cout + co) * L.cin_p + ci] = __float2bfloat16_rn(v);
+        }
+        ws[((size_t)tp * L.cin_p + ci) * d.cout + co] = v;
+      }
+  AFB_CUDA(cudaMalloc(&L.w_simt, n * sizeof(float)));
+  AFB_CUDA(cudaMemcpy(L.w_simt, ws.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  if (is_bf16) {
+    AFB_CUDA(cudaMalloc(&L.w_umma, n * sizeof(bf16)));
+    AFB_CUDA(cudaMemcpy(L.w_umma, wu.data(), n * sizeof(bf16), cudaMemcpyHostToDevice));
+  }
+  AFB_CUDA(cudaMalloc(&L.bias, d.cout * sizeof(float)));
+  AFB_CUDA(cudaMemcpy(L.bias, d.bias, d.cout * sizeof(float), cudaMemcpyHostToDevice));
+  return AF_OK;
+}
+
+struct Dims { int T, H, W, C; long long elems() const { return (long long)T * H * W * C; } };
+
+static Dims conv_out(const ConvLayer& L, Dims in) {
+  Dims o;
+  o.T = (in.T + 2 * L.pt - L.kt) / L.st + 1;
+  o.H = (in.H + 2 * L.ph - L.kh) / L.sh + 1;
+  o.W = (in.W + 2 * L.pw - L.kw) / L.sw + 1;
+  o.C = L.cout;
+  return o;
+}
+
+}  // namespace afb
+
+using namespace afb;
+
+struct af_engine {
+  int device = 0;
+  bool is_bf16 = false;
+  int T = 32, S = 224, max_batch = 1;
+  std::vector<ConvLayer> convs;
+  int stem = 0;
+  std::vector<af_block_desc> blocks;
+  float* fc_w = nullptr;
+  float fc_b = 0.f;
+  int feat_dim = 0;
+  int cb_front = 2, cb_back = 8;
+  int conv_impl = 0;       // 0 auto, 1 force SIMT, 2 force UMMA where supported
+  bool keep_stages = false;
+  long long launches = 0;
+
+  // clip buffer (padded NDHWC4) for max_batch clips
+  void* clip_raw = nullptr;
+  ClipLayout clip;
+  // workspace
+  size_t esz = 4;
+  int split = -1;            // first block of the "back" part (-1: none)
+  long long front_max = 0, back_max = 0, group_elems = 0;
+  void* fbuf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* bbuf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* gbuf = nullptr;      // group input of the back part [cb_back, ...]
+  float* feat_ws = nullptr;  // [max_batch, feat_dim]
+  uint8_t* u8_stage = nullptr;
+  float* out_stage = nullptr;  // [2*max_batch] logits, scores (device staging for *_host calls)
+  // kept stages (fp32 NCTHW) for parity tests
+  float* stage_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  Dims stage_dims[5];
+  int stage_batch = 0;
+};
+
+namespace afb {
+
+static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, long long xsB, long long xsT,
+                    long long xsH, long long xsW, int B, const void* res, void* y, bool relu, cudaStream_t s,
+                    int impl_override = -1) {
+  ConvProblem p;
+  p.x = x; p.bias = L.bias; p.res = res; p.y = y;
+  p.B = B; p.Ti = in.T; p.Hi = in.H; p.Wi = in.W; p.Cin = L.cin_p;
+  p.xsB = xsB; p.xsT = xsT; p.xsH = xsH; p.xsW = xsW;
+  Dims o = conv_out(L, in);
+  p.To = o.T; p.Ho = o.H; p.Wo = o.W; p.Cout = L.cout;
+  p.kt = L.kt; p.kh = L.kh; p.kw = L.kw; p.st = L.st; p.sh = L.sh; p.sw = L.sw;
+  p.pt = L.pt; p.ph = L.ph; p.pw = L.pw;
+  p.relu = relu ? 1 : 0;
+  p.M = (long long)B * o.T * o.H * o.W;
+  const bool is_bf16 = e ? e->is_bf16 : (L.w_umma != nullptr);
+  const int impl = impl_override >= 0 ? impl_override : (e ? e->conv_impl : 0);
+  if (is_bf16 && impl != 1) {
+    p.w = L.w_umma;
+    if (conv_umma_supported(p)) return conv_umma_launch(p, s);
+    if (impl == 2) { set_error("tcgen05 conv kernel does not take this shape"); return AF_ERR_INVALID; }
+  }
+  p.w = L.w_simt;
+  return conv_simt_launch(p, is_bf16, s);
+}
+
+static int dense_conv(af_engine* e, int idx, const void* x, Dims in, int B, const void* res, void* y, bool relu,
+                      cudaStream_t s) {
+  const long long sW = in.C, sH = (long long)in.W * in.C, sT = sH * in.H, sB = sT * in.T;
+  return run_conv(e, e->convs[idx], x, in, sB, sT, sH, sW, B, res, y, relu, s);
+}
+
+static int keep_stage(af_engine* e, int which, const void* x, Dims d, int b0, int B, cudaStream_t s) {
+  if (!e->keep_stages) return AF_OK;
+  float*& buf = e->stage_buf[which];
+  if (!buf) AFB_CUDA(cudaMalloc(&buf, (size_t)e->max_batch * d.elems() * sizeof(float)));
+  e->stage_dims[which] = d;
+  return ndhwc_to_ncthw_f32_launch(x, buf + (long long)b0 * d.elems(), B, d.T, d.H, d.W, d.C, e->is_bf16, s);
+}
+
+static bool is_stage_end(const af_engine* e, int bi) {
+  return bi + 1 == (int)e->blocks.size() || e->blocks[bi + 1].branch1 >= 0;
+}
+
+// Run blocks [b_begin, b_end) on `B` clips whose input is `x` (dense NDHWC, dims `d`), using
+// the 5 scratch buffers `buf`.  Returns the output buffer/dims through x/d.
+static int run_blocks(af_engine* e, int b_begin, int b_end, const void*& x, Dims& d, int B, void* const buf[5],
+                      int clip0, int& stage_no, cudaStream_t s) {
+  for (int bi = b_begin; bi < b_end; ++bi) {
+    const af_block_desc& blk = e->blocks[bi];
+    // scratch buffers that do not alias the block input
+    std::vector<void*> freeb;
+    for (int i = 0; i < 5; ++i)
+      if (buf[i] != x) freeb.push_back(buf[i]);
+    if (blk.temporal_pool_before) {
+      void* pooled = freeb.back();
+      freeb.pop_back();
+      int rc = maxpool_temporal_launch(x, pooled, B, d.T, d.H, d.W, d.C, e->is_bf16, s);
+      if (rc) return rc;
+      for (int i = 0; i < 5; ++i)
+        if (buf[i] == x) freeb.push_back(buf[i]);
+      x = pooled; d.T /= 2;
+    }
+    if (freeb.size() < 4) { set_error("internal: scratch exhausted"); return AF_ERR_INVALID; }
+    void *ya = freeb[0], *yb = freeb[1], *ysc = freeb[2], *yout = freeb[3];
+    const void* shortcut = x;
+    if (blk.branch1 >= 0) {
+      int rc = dense_conv(e, blk.branch1, x, d, B, nullptr, ysc, false, s);
+      if (rc) return rc;
+      shortcut = ysc;
+    }
+    int rc = dense_conv(e, blk.a, x, d, B, nullptr, ya, true, s);
+    if (rc) return rc;
+    Dims da = conv_out(e->convs[blk.a], d);
+    rc = dense_conv(e, blk.b, ya, da, B, nullptr, yb, true, s);
+    if (rc) return rc;
+    Dims db = conv_out(e->convs[blk.b], da);
+    rc = dense_conv(e, blk.c, yb, db, B, shortcut, yout, true, s);
+    if (rc) return rc;
+    d = conv_out(e->convs[blk.c], db);
+    x = yout;
+    if (is_stage_end(e, bi)) {
+      rc = keep_stage(e, stage_no, x, d, clip0, B, s);
+      if (rc) return rc;
+      ++stage_no;
+    }
+  }
+  return AF_OK;
+}
+
+// The trunk on clips [0,B) already packed in e->clip.
+static int run_trunk(af_engine* e, int B, float* logits, float* scores, float* features, cudaStream_t s) {
+  const ConvLayer& stem = e->convs[e->stem];
+  const Dims din = {e->T, e->S, e->S, stem.cin_p};
+  const Dims dpre = conv_out(stem, din);
+  const Dims dpool = {dpre.T, (dpre.H + 2 - 3) / 2 + 1, (dpre.W + 2 - 3) / 2 + 1, dpre.C};
+  const int nblk = (int)e->blocks.size();
+  const int split = e->split < 0 ? nblk : e->split;
+  e->stage_batch = B;
+
+  for (int g0 = 0; g0 < B; g0 += e->cb_back) {
+    const int gB = (B - g0) < e->cb_back ? (B - g0) : e->cb_back;
+    Dims dg = {0, 0, 0, 0};
+    for (int f0 = g0; f0 < g0 + gB; f0 += e->cb_front) {
+      const int fB = (g0 + gB - f0) < e->cb_front ? (g0 + gB - f0) : e->cb_front;
+      const char* xin = (const char*)e->clip.base + (long long)f0 * e->clip.sB * e->esz;
+      int rc = run_conv(e, stem, xin, din, e->clip.sB, e->clip.sT, e->clip.sH, e->clip.sW, fB, nullptr, e->fbuf[0],
+                        true, s);
+      if (rc) return rc;
+      rc = maxpool_spatial_launch(e->fbuf[0], e->fbuf[1], fB, dpre.T, dpre.H, dpre.W, dpre.C, e->is_bf16, s);
+      if (rc) return rc;
+      rc = keep_stage(e, 0, e->fbuf[1], dpool, f0, fB, s);
+      if (rc) return rc;
+      const void* x = e->fbuf[1];
+      Dims d = dpool;
+      int stage_no = 1;
+      rc = run_blocks(e, 0, split, x, d, fB, e->fbuf, f0, stage_no, s);
+      if (rc) return rc;
+      // hand the chunk to the group buffer of the back part
+      dg = d;
+      AFB_CUDA(cudaMemcpyAsync((char*)e->gbuf + (long long)(f0 - g0) * d.elems() * e->esz, x,
+                               (size_t)fB * d.elems() * e->esz, cudaMemcpyDeviceToDevice, s));
+    }
+    const void* x = e->gbuf;
+    Dims d = dg;
+    int stage_no = 1;
+    for (int bi = 0; bi < split; ++bi) stage_no += is_stage_end(e, bi) ? 1 : 0;
+    int rc = run_blocks(e, split, nblk, x, d, gB, e->bbuf, g0, stage_no, s);
+    if (rc) return rc;
+    rc = head_launch(x, gB, d.T * d.H * d.W, d.C, e->is_bf16, e->fc_w, e->fc_b, e->feat_ws + (long long)g0 * e->feat_dim,
+                     features ? features + (long long)g0 * e->feat_dim : nullptr, logits ? logits + g0 : nullptr,
+                     scores ? scores + g0 : nullptr, s);
+    if (rc) return rc;
+  }
+  return AF_OK;
+}
+
+static int plan_workspace(af_engine* e) {
+  // walk the network once for one clip to size the scratch buffers
+  const ConvLayer& stem = e->convs[e->stem];
+  Dims d = conv_out(stem, Dims{e->T, e->S, e->S, stem.cin_p});
+  long long fmax = d.elems();
+  d = Dims{d.T, (d.H + 2 - 3) / 2 + 1, (d.W + 2 - 3) / 2 + 1, d.C};
+  long long bmax = 0;
+  e->split = -1;
+  for (size_t bi = 0; bi < e->blocks.size(); ++bi) {
+    const af_block_desc& blk = e->blocks[bi];
+    long long& mx = (e->split >= 0 || blk.temporal_pool_before) ? bmax : fmax;
+    if (blk.temporal_pool_before && e->split < 0) {
+      e->split = (int)bi;
+      e->group_elems = d.elems();
+    }
+    if (blk.temporal_pool_before) { d.T /= 2; if (d.elems() > mx) mx = d.elems(); }
+    Dims da = conv_out(e->convs[blk.a], d);
+    Dims db = conv_out(e->convs[blk.b], da);
+    Dims dc = conv_out(e->convs[blk.c], db);
+    for (long long v : {d.elems(), da.elems(), db.elems(), dc.elems()})
+      if (v > mx) mx = v;
+    if (dc.C != e->convs[blk.c].cout) { set_error("internal dims"); return AF_ERR_INVALID; }
+    d = dc;
+  }
+  if (e->split < 0) e->group_elems = d.elems();
+  if (d.C != e->feat_dim) { set_error("af_create: trunk ends with %d channels, head expects %d", d.C, e->feat_dim); return AF_ERR_INVALID; }
+  e->front_max = fmax;
+  e->back_max = bmax > 0 ? bmax : 1;
+  return AF_OK;
+}
+
+static int alloc_workspace(af_engine* e) {
+  for (int i = 0; i < 5; ++i) {
+    AFB_CUDA(cudaMalloc(&e->fbuf[i], (size_t)e->cb_front * e->front_max * e->esz));
+    AFB_CUDA(cudaMalloc(&e->bbuf[i], (size_t)e->cb_back * e->back_max * e->esz));
+  }
+  AFB_CUDA(cudaMalloc(&e->gbuf, (size_t)e->cb_back * e->group_elems * e->esz));
+  return AF_OK;
+}
+
+static void free_workspace(af_engine* e) {
+  for (int i = 0; i < 5; ++i) {
+    if (e->fbuf[i]) cudaFree(e->fbuf[i]);
+    if (e->bbuf[i]) cudaFree(e->bbuf[i]);
+    e->fbuf[i] = e->bbuf[i] = nullptr;
+  }
+  if (e->gbuf) cudaFree(e->gbuf);
+  e->gbuf = nullptr;
+}
+
+}  // namespace afb
+
+extern "C" {
+
+const char* af_last_error(void) { return afb::g_err; }
+int32_t af_version(void) { return AFB200_VERSION; }
+int64_t af_launch_count(af_handle h) { return h ? h->launches : 0; }
+
+af_status af_destroy(af_handle h) {
+  if (!h) return AF_OK;
+  cudaSetDevice(h->device);
+  for (auto& L : h->convs) free_layer(L);
+  free_workspace(h);
+  if (h->fc_w) cudaFree(h->fc_w);
+  if (h->clip_raw) cudaFree(h->clip_raw);
+  if (h->feat_ws) cudaFree(h->feat_ws);
+  if (h->u8_stage) cudaFree(h->u8_stage);
+  if (h->out_stage) cudaFree(h->out_stage);
+  for (int i = 0; i < 5; ++i)
+    if (h->stage_buf[i]) cudaFree(h->stage_buf[i]);
+  delete h;
+  return AF_OK;
+}
+
+static af_status create_impl(af_engine* e, const af_weights* w) {
+  AFB_CUDA(cudaSetDevice(e->device));
+  cudaDeviceProp prop;
+  AFB_CUDA(cudaGetDeviceProperties(&prop, e->device));
+  if (prop.major != 10) {
+    set_error("af_create: device %d is sm_%d%d; this library is built for sm_100a only", e->device, prop.major, prop.minor);
+    return AF_ERR_UNSUPPORTED;
+  }
+  if (e->is_bf16) {
+    int rc = conv_umma_init();
+    if (rc) return (af_status)rc;
+  }
+  e->convs.resize(w->n_convs);
+  for (int i = 0; i < w->n_convs; ++i) {
+    int rc = upload_layer(w->convs[i], e->is_bf16, e->convs[i]);
+    if (rc) return (af_status)rc;
+  }
+  e->blocks.assign(w->blocks, w->blocks + w->n_blocks);
+  AFB_CUDA(cudaMalloc(&e->fc_w, w->feature_dim * sizeof(float)));
+  AFB_CUDA(cudaMemcpy(e->fc_w, w->fc_weight, w->feature_dim * sizeof(float), cudaMemcpyHostToDevice));
+  // padded clip buffer: T+4 frames, S+6 rows, S+8 columns, 4 channels; pads stay zero forever
+  const long long Tp = e->T + 4, Hp = e->S + 6, Wp = e->S + 8;
+  const size_t clip_bytes = (size_t)e->max_batch * Tp * Hp * Wp * 4 * e->esz;
+  AFB_CUDA(cudaMalloc(&e->clip_raw, clip_bytes));
+  AFB_CUDA(cudaMemset(e->clip_raw, 0, clip_bytes));
+  e->clip.sW = 4; e->clip.sH = Wp * 4; e->clip.sT = Hp * Wp * 4; e->clip.sB = Tp * Hp * Wp * 4;
+  e->clip.T = e->T; e->clip.S = e->S; e->clip.is_bf16 = e->is_bf16;
+  e->clip.base = (char*)e->clip_raw + (2 * e->clip.sT + 3 * e->clip.sH + 3 * e->clip.sW) * (long long)e->esz;
+  int rc = plan_workspace(e);
+  if (rc) return (af_status)rc;
+  if (e->cb_back > e->max_batch) e->cb_back = e->max_batch;
+  if (e->cb_front > e->cb_back) e->cb_front = e->cb_back;
+  rc = alloc_workspace(e);
+  if (rc) return (af_status)rc;
+  AFB_CUDA(cudaMalloc(&e->feat_ws, (size_t)e->max_batch * e->feat_dim * sizeof(float)));
+  AFB_CUDA(cudaMalloc(&e->out_stage, (size_t)2 * e->max_batch * sizeof(float)));
+  return AF_OK;
+}
+
+af_status af_create(af_handle* out, int32_t device, const af_weights* w, int32_t max_batch, int32_t precision) {
+  if (!out || !w || max_batch <= 0 || w->n_convs <= 0 || w->n_blocks <= 0 || !w->convs || !w->blocks) {
+    set_error("af_create: invalid arguments");
+    return AF_ERR_INVALID;
+  }
+  if (precision != AF_PREC_FP32 && precision != AF_PREC_BF16) {
+    set_error("af_create: unknown precision %d", precision);
+    return AF_ERR_INVALID;
+  }
+  for (int i = 0; i < w->n_convs; ++i) {
+    const af_conv_desc& c = w->convs[i];
+    if (!c.weight || !c.bias || c.cout % 64 != 0 || c.cin <= 0) {
+      set_error("af_create: conv %d unsupported (cin=%d cout=%d)", i, c.cin, c.cout);
+      return AF_ERR_INVALID;
+    }
+  }
+  af_engine* e = new af_engine();
+  e->device = device;
+  e->is_bf16 = precision == AF_PREC_BF16;
+  e->esz = e->is_bf16 ? 2 : 4;
+  e->T = w->clip_t; e->S = w->clip_s; e->max_batch = max_batch;
+  e->stem = w->stem; e->fc_b = w->fc_bias; e->feat_dim = w->feature_dim;
+  af_status rc = create_impl(e, w);
+  if (rc != AF_OK) { af_destroy(e); return rc; }
+  *out = e;
+  return AF_OK;
+}
+
+af_status af_set_option(af_handle h, const char* name, int64_t value) {
+  if (!h || !name) { set_error("af_set_option: null"); return AF_ERR_INVALID; }
+  std::string n(name);
+  if (n == "keep_stages") { h->keep_stages = value != 0; return AF_OK; }
+  if (n == "conv_impl") { h->conv_impl = (int)value; return AF_OK; }
+  if (n == "chunk_front" || n == "chunk_back") {
+    if (value <= 0) { set_error("af_set_option: %s must be positive", name); return AF_ERR_INVALID; }
+    AFB_CUDA(cudaSetDevice(h->device));
+    AFB_CUDA(cudaDeviceSynchronize());
+    free_workspace(h);
+    if (n == "chunk_front") h->cb_front = (int)value; else h->cb_back = (int)value;
+    if (h->cb_back > h->max_batch) h->cb_back = h->max_batch;
+    if (h->cb_front > h->cb_back) h->cb_front = h->cb_back;
+    return (af_status)alloc_workspace(h);
+  }
+  set_error("af_set_option: unknown option '%s'", name);
+  return AF_ERR_INVALID;
+}
+
+static af_status check_batch(af_handle h, int32_t batch, const char* who) {
+  if (!h) { set_error("%s: null handle", who); return AF_ERR_INVALID; }
+  if (batch <= 0 || batch > h->max_batch) {
+    set_error("%s: batch %d outside 1..max_batch=%d", who, batch, h->max_batch);
+    return AF_ERR_INVALID;
+  }
+  return AF_OK;
+}
+
+af_status af_forward(af_handle h, const void* clip_dev, int32_t dtype, const int64_t strides[5], int32_t batch,
+                     float* logits_dev, float* features_dev, void* stream) {
+  af_status rc = check_batch(h, batch, "af_forward");
+  if (rc) return rc;
+  if (!clip_dev || !strides || !logits_dev) { set_error("af_forward: null pointer"); return AF_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  AFB_CUDA(cudaSetDevice(h->device));
+  const long long before = g_launches;
+  long long q[5] = {strides[0], strides[1], strides[2], strides[3], strides[4]};
+  int r = pack_clip_launch(clip_dev, dtype, q, batch, h->clip, s);
+  if (!r) r = run_trunk(h, batch, logits_dev, nullptr, features_dev, s);
+  h->launches += g_launches - before;
+  return (af_status)r;
+}
+
+af_status af_infer_u8(af_handle h, const uint8_t* clips_dev, int32_t batch, const float mean255[3],
+                      const float std255[3], float* logits_dev, float* scores_dev, float* features_dev,
+                      void* stream) {
+  af_status rc = check_batch(h, batch, "af_infer_u8");
+  if (rc) return rc;
+  if (!clips_dev || !mean255 || !std255) { set_error("af_infer_u8: null pointer"); return AF_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  AFB_CUDA(cudaSetDevice(h->device));
+  const long long before = g_launches;
+  int r = pack_u8_launch(clips_dev, batch, mean255, std255, h->clip, s);
+  if (!r) r = run_trunk(h, batch, logits_dev, scores_dev, features_dev, s);
+  h->launches += g_launches - before;
+  return (af_status)r;
+}
+
+af_status af_infer_u8_host(af_handle h, const uint8_t* clips_host, int32_t batch, const float mean255[3],
+                           const float std255[3], float* logits_host, float* scores_host, void* stream) {
+  af_status rc = check_batch(h, batch, "af_infer_u8_host");
+  if (rc) return rc;
+  if (!clips_host) { set_error("af_infer_u8_host: null pointer"); return AF_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  AFB_CUDA(cudaSetDevice(h->device));
+  const size_t clip_bytes = (size_t)h->T * h->S * h->S * 3;
+  if (!h->u8_stage) AFB_CUDA(cudaMalloc(&h->u8_stage, (size_t)h->max_batch * clip_bytes));
+  AFB_CUDA(cudaMemcpyAsync(h->u8_stage, clips_host, (size_t)batch * clip_bytes, cudaMemcpyHostToDevice, s));
+  rc = af_infer_u8(h, h->u8_stage, batch, mean255, std255, h->out_stage, h->out_stage + h->max_batch, nullptr, stream);
+  if (rc) return rc;
+  if (logits_host)
+    AFB_CUDA(cudaMemcpyAsync(logits_host, h->out_stage, batch * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (scores_host)
+    AFB_CUDA(cudaMemcpyAsync(scores_host, h->out_stage + h->max_batch, batch * sizeof(float), cudaMemcpyDeviceToHost, s));
+  AFB_CUDA(cudaStreamSynchronize(s));
+  return AF_OK;
+}
+
+af_status af_crop_u8(const af_frame_desc* frames_dev, const af_clip_geom* geom_dev, int32_t batch,
+                     int32_t frames_per_clip, int32_t size, int32_t bgr, uint8_t* out_dev, void* stream) {
+  if (!frames_dev || !geom_dev || !out_dev || batch <= 0 || frames_per_clip <= 0 || size <= 0) {
+    set_error("af_crop_u8: invalid arguments");
+    return AF_ERR_INVALID;
+  }
+  static_assert(sizeof(af_frame_desc) == sizeof(FrameDesc), "frame desc layout");
+  static_assert(sizeof(af_clip_geom) == sizeof(ClipGeom), "clip geom layout");
+  return (af_status)crop_launch((const FrameDesc*)frames_dev, (const ClipGeom*)geom_dev, batch, frames_per_clip, size,
+                                bgr, out_dev, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+af_status af_crop_infer(af_handle h, const af_frame_desc* frames_dev, const af_clip_geom* geom_dev, int32_t batch,
+                        int32_t bgr, const float mean255[3], const float std255[3], float* logits_dev,
+                        float* scores_dev, float* features_dev, void* stream) {
+  af_status rc = check_batch(h, batch, "af_crop_infer");
+  if (rc) return rc;
+  if (!frames_dev || !geom_dev || !mean255 || !std255) { set_error("af_crop_infer: null pointer"); return AF_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  AFB_CUDA(cudaSetDevice(h->device));
+  const long long before = g_launches;
+  int r = crop_launch((const FrameDesc*)frames_dev, (const ClipGeom*)geom_dev, batch, h->T, h->S, bgr, nullptr, &h->clip,
+                      mean255, std255, s);
+  if (!r) r = run_trunk(h, batch, logits_dev, scores_dev, features_dev, s);
+  h->launches += g_launches - before;
+  return (af_status)r;
+}
+
+af_status af_conv_ndhwc(const void* x_dev, const af_conv_desc* conv_host, const void* residual_dev, void* y_dev,
+                        int32_t batch, int32_t t, int32_t hgt, int32_t wid, int32_t relu, int32_t precision,
+                        int32_t impl, void* stream) {
+  if (!x_dev || !conv_host || !y_dev || batch <= 0) { set_error("af_conv_ndhwc: invalid arguments"); return AF_ERR_INVALID; }
+  if (conv_host->cin % 4 != 0 || conv_host->cout % 64 != 0) {
+    set_error("af_conv_ndhwc: needs cin %% 4 == 0 and cout %% 64 == 0");
+    return AF_ERR_INVALID;
+  }
+  const bool is_bf16 = precision == AF_PREC_BF16;
+  if (is_bf16) { int rc = conv_umma_init(); if (rc) return (af_status)rc; }
+  ConvLayer L;
+  int rc = upload_layer(*conv_host, is_bf16, L);
+  if (!rc) {
+    Dims in = {t, hgt, wid, L.cin_p};
+    const long long sW = in.C, sH = (long long)in.W * in.C, sT = sH * in.H, sB = sT * in.T;
+    rc = run_conv(nullptr, L, x_dev, in, sB, sT, sH, sW, batch, residual_dev, y_dev, relu != 0, (cudaStream_t)stream, impl);
+    if (!rc && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+      set_error("af_conv_ndhwc: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = AF_ERR_CUDA;
+    }
+  }
+  free_layer(L);
+  return (af_status)rc;
+}
+
+af_status af_get_stage(af_handle h, int32_t which, float* out_dev, int64_t capacity_elems, int32_t dims_out[5],
+                       void* stream) {
+  if (!h || which < 1 || which > 5 || !dims_out) { set_error("af_get_stage: invalid arguments"); return AF_ERR_INVALID; }
+  if (!h->keep_stages || !h->stage_buf[which - 1]) {
+    set_error("af_get_stage: stage %d not kept (set option keep_stages=1 before the forward)", which);
+    return AF_ERR_INVALID;
+  }
+  const Dims d = h->stage_dims[which - 1];
+  dims_out[0] = h->stage_batch; dims_out[1] = d.C; dims_out[2] = d.T; dims_out[3] = d.H; dims_out[4] = d.W;
+  const long long n = (long long)h->stage_batch * d.elems();
+  if (out_dev) {
+    if (capacity_elems < n) { set_error("af_get_stage: buffer too small (%lld < %lld)", (long long)capacity_elems, n); return AF_ERR_INVALID; }
+    AFB_CUDA(cudaMemcpyAsync(out_dev, h->stage_buf[which - 1], n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  }
+  return AF_OK;
+}
+
+}  // extern "C"

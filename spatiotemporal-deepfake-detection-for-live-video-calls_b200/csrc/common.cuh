@@ -1,0 +1,74 @@
+// Shared declarations for the afb200 CUDA sources (internal; the public ABI is include/afb200.h).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace afb {
+
+typedef __nv_bfloat16 bf16;
+
+// A convolution expressed on channels-last (NDHWC) activations.
+// Input may be a strided view (the padded clip buffer); output / residual are dense [M, Cout].
+struct ConvProblem {
+  const void* x;
+  const void* w;       // SIMT: float [taps][cin][cout];  UMMA: bf16 [taps][cout][cin]
+  const float* bias;   // [cout]
+  const void* res;     // nullptr or dense [M, cout]
+  void* y;             // dense [M, cout]
+  int B, Ti, Hi, Wi, Cin;
+  long long xsB, xsT, xsH, xsW;   // element strides of the input view (channel stride 1)
+  int To, Ho, Wo, Cout;
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+  int relu;
+  long long M;         // B*To*Ho*Wo
+};
+
+void set_error(const char* fmt, ...);
+extern thread_local long long g_launches;   // kernels launched by this thread (copied into engines)
+
+#define AFB_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (call);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      afb::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                \
+                     cudaGetErrorString(_e));                                            \
+      return AF_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+// conv_simt.cu
+int conv_simt_launch(const ConvProblem& p, bool is_bf16, cudaStream_t s);
+// conv_umma.cu
+bool conv_umma_supported(const ConvProblem& p);
+int conv_umma_launch(const ConvProblem& p, cudaStream_t s);
+int conv_umma_init();
+// pool_head.cu
+int maxpool_spatial_launch(const void* x, void* y, int B, int T, int H, int W, int C, bool is_bf16,
+                           cudaStream_t s);   // k[1,3,3] s[1,2,2] p[0,1,1]
+int maxpool_temporal_launch(const void* x, void* y, int B, int T, int H, int W, int C, bool is_bf16,
+                            cudaStream_t s);  // k[2,1,1] s[2,1,1]
+int head_launch(const void* x, int B, int P, int C, bool is_bf16, const float* fc_w, float fc_b,
+                float* features_ws, float* features_out, float* logits, float* scores,
+                cudaStream_t s);
+int ndhwc_to_ncthw_f32_launch(const void* x, float* y, int B, int T, int H, int W, int C,
+                              bool is_bf16, cudaStream_t s);
+// crop_pack.cu
+struct ClipLayout {     // engine-internal normalised clip: padded NDHWC4
+  void* base;           // points at logical element (b=0,t=0,y=0,x=0,c=0)
+  long long sB, sT, sH, sW;   // element strides
+  int T, S;
+  bool is_bf16;
+};
+int pack_clip_launch(const void* src, int dtype, const long long strides[5], int B,
+                     const ClipLayout& dst, cudaStream_t s);
+int pack_u8_launch(const uint8_t* src, int B, const float mean[3], const float stdv[3],
+                   const ClipLayout& dst, cudaStream_t s);
+struct FrameDesc { const uint8_t* data; long long pitch; int height, width; int box[4]; };
+struct ClipGeom { double tfm[6]; int left_top[2]; int canvas_wh[2]; };
+int crop_launch(const FrameDesc* frames, const ClipGeom* geom, int B, int T, int S, int bgr,
+                uint8_t* out_u8, const ClipLayout* dst, const float mean[3], const float stdv[3],
+                cudaStream_t s);
+
+}  // namespace afb

@@ -1,0 +1,500 @@
+// K2: channels-last Conv3d (+folded-BN bias, +residual, +ReLU) as an implicit GEMM on the
+// 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands staged by TMA.
+//
+// Replaces, for every trunk convolution of the reference (1x3x3, 3x1x1 and 1x1x1, stride 1
+// or [1,2,2]; altfreezing/slowfast/models/resnet_helper.py:255-326,411-444), the chain
+// nn.Conv3d -> BatchNorm3d(eval) [-> + shortcut] [-> ReLU] that PyTorch runs as 2-4 kernels.
+//
+// GEMM view: D[M, N] = sum over taps, channel blocks of A_tap[M, 64] * W_tap[N, 64]^T with
+//   M = B*To*Ho*Wo flattened output pixels (NDHWC order), N = Cout, K = taps*Cin.
+// A tiles: 128 consecutive output pixels x 64 input channels, loaded by ONE im2col-mode TMA
+//   (cp.async.bulk.tensor.5d...im2col): the hardware walks the pixels across rows / frames /
+//   clips, applies the conv stride, adds the filter-tap offset and zero-fills the padding halo.
+//   1x1x1 stride-1 convs use a plain 2-D tiled map over [M, Cin].
+// B tiles: BLOCK_N output channels x 64 input channels of one tap from W[tap][Cout][Cin].
+// Both land in 128B-swizzled K-major shared memory, which is what the UMMA descriptors read.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0   : TMA producer (one lane)        -- STAGES-deep full/empty mbarrier ring
+//   warp 1   : tcgen05.mma issuer (one lane)  -- owns the TMEM allocation (2 accumulators)
+//   warps 2-5: epilogue: tcgen05.ld -> +bias (+residual) -> ReLU -> bf16 -> swizzled smem
+//              -> TMA store; double-buffered against the next tile's main loop through the
+//              tmem_full/tmem_empty barriers.
+#include <cuda.h>
+
+#include "../../include/afb200.h"
+#include "common.cuh"
+
+namespace afb {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;             // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
+constexpr int OUT_STAGE_BYTES = BLOCK_M * 64 * 2;      // one 64-column output chunk, 16 KiB
+
+struct UmmaParams {
+  const float* bias;
+  const bf16* res;
+  long long M;
+  int Cout, Cin;
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+  int To, Ho, Wo;
+  int num_m_tiles, num_n_tiles;
+  int relu;
+  int im2col;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c, int w, int h,
+                                                   int d, int n, uint16_t ow, uint16_t oh, uint16_t od) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+      "%7}], [%2], {%8, %9, %10};" ::"r"(smem_u32(dst)),
+      "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "h"(ow), "h"(oh), "h"(od)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)m),
+               "r"(smem_u32(src)), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void tma_store_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (rows of 128 bytes, 8-row groups
+// 1024 bytes apart). Encoding per the PTX ISA "shared memory descriptor" / CUTLASS
+// cute/arch/mma_sm100_desc.hpp: addr>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BLOCK_N.
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+#define TMEM_LD_32x32b_x32(taddr, r)                                                                               \
+  asm volatile(                                                                                                    \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                    \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                    \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),      \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),     \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                   \
+      : "r"(taddr)                                                                                                 \
+      : "memory")
+
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int BLOCK_N, int STAGES> struct SmemLayout {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BIAS = OFF_OUT + 2 * OUT_STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_BIAS + BLOCK_N * 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+  static constexpr int TOTAL = OFF_TMEM + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;   // slack for the 1024-byte alignment of the base
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const __grid_constant__ CUtensorMap tm_y, const UmmaParams p) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_out = smem + L::OFF_OUT;
+  float* bias_s = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int cblocks = p.Cin / BLOCK_K;
+  const int num_kb = p.kt * p.kh * p.kw * cblocks;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_y);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_THREADS); }
+    fence_barrier_init();
+  } else if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+        const long long m0 = (long long)m_tile * BLOCK_M;
+        const int n0 = n_tile * BLOCK_N;
+        long long r = m0;
+        const int wo = (int)(r % p.Wo); r /= p.Wo;
+        const int ho = (int)(r % p.Ho); r /= p.Ho;
+        const int to = (int)(r % p.To); r /= p.To;
+        const int b = (int)r;
+        const int wb = wo * p.sw - p.pw, hb = ho * p.sh - p.ph, tb = to * p.st - p.pt;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          const int tap = kb / cblocks, cb = kb - tap * cblocks;
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          if (p.im2col) {
+            const int dx = tap % p.kw, q = tap / p.kw, dy = q % p.kh, dt = q / p.kh;
+            tma_load_im2col_5d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, wb, hb, tb, b, (uint16_t)dx, (uint16_t)dy,
+                               (uint16_t)dt);
+          } else {
+            tma_load_2d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, (int)m0);
+          }
+          tma_load_2d(sb, &tm_b, &full_bar[stage], cb * BLOCK_K, tap * p.Cout + n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(a_addr);
+          const uint64_t bdesc = make_smem_desc(a_addr + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the >>4 address field
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);               // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5)
+    const int et = threadIdx.x - 64;               // 0..127
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;              // accumulator row == output pixel within the tile
+    int it = 0;
+    int out_buf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+      const long long m0 = (long long)m_tile * BLOCK_M;
+      const int n0 = n_tile * BLOCK_N;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      for (int i = et; i < BLOCK_N; i += EPI_THREADS) bias_s[i] = __ldg(p.bias + n0 + i);
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const long long m = m0 + row;
+      const bool row_ok = m < p.M;
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk) {
+        uint8_t* sout = smem_out + out_buf * OUT_STAGE_BYTES;
+        if (et == 0) tma_store_wait_read<1>();     // the store that last read this buffer is done
+        epi_bar_sync();                            // (also publishes bias_s)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BLOCK_N + chunk * 64 + half * 32;
+          TMEM_LD_32x32b_x32(taddr, v);
+          tmem_ld_wait();
+          const int cbase = chunk * 64 + half * 32;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_s[cbase + j];
+          if (p.res != nullptr && row_ok) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + m * p.Cout + n0 + cbase);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 t = __ldg(rp + q);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                f[q * 8 + 2 * e] += __low2float(h2[e]);
+                f[q * 8 + 2 * e + 1] += __high2float(h2[e]);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 t;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1]);
+            const int j16 = half * 4 + q;          // 16-byte chunk index within the 128-byte row
+            *reinterpret_cast<uint4*>(sout + row * 128 + ((j16 ^ (row & 7)) << 4)) = t;
+          }
+        }
+        if (chunk == BLOCK_N / 64 - 1) {           // all TMEM reads of this accumulator are done
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[as]);
+        }
+        fence_proxy_async_smem();
+        epi_bar_sync();
+        if (et == 0) {
+          tma_store_2d(&tm_y, sout, n0 + chunk * 64, (int)m0);
+          tma_store_commit();
+        }
+        out_buf ^= 1;
+      }
+    }
+    if (et == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+int g_num_sms = 0;
+int g_driver_version = 0;
+bool g_corner_dhw = false;    // AFB200_IM2COL_CORNERS=dhw flips the corner array order (bring-up knob)
+
+template <int BLOCK_N, int STAGES>
+int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const UmmaParams& up, cudaStream_t s) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  static bool configured = false;
+  auto kern = conv_umma_kernel<BLOCK_N, STAGES>;
+  if (!configured) {
+    AFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    configured = true;
+  }
+  const int tiles = up.num_m_tiles * up.num_n_tiles;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  kern<<<grid, NUM_THREADS, L::DYN_BYTES, s>>>(ta, tb, ty, up);
+  ++g_launches;
+  AFB_CUDA(cudaGetLastError());
+  return AF_OK;
+}
+
+int encode_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, const char* what) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {BLOCK_K, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s: rows=%llu cols=%llu box_rows=%u) failed: %d", what,
+              (unsigned long long)rows, (unsigned long long)cols, box_rows, (int)r);
+    return AF_ERR_CUDA;
+  }
+  return AF_OK;
+}
+
+}  // namespace
+
+int conv_umma_init() {
+  if (g_encode_tiled && g_encode_im2col) return AF_OK;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  AFB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available in this driver"); return AF_ERR_UNSUPPORTED; }
+  g_encode_tiled = (EncodeTiledFn)fn;
+  fn = nullptr;
+  AFB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeIm2col not available in this driver"); return AF_ERR_UNSUPPORTED; }
+  g_encode_im2col = (EncodeIm2colFn)fn;
+  int dev = 0;
+  AFB_CUDA(cudaGetDevice(&dev));
+  AFB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  AFB_CUDA(cudaDriverGetVersion(&g_driver_version));
+  const char* c = getenv("AFB200_IM2COL_CORNERS");
+  g_corner_dhw = c && c[0] == 'd';
+  return AF_OK;
+}
+
+bool conv_umma_supported(const ConvProblem& p) {
+  if (!g_encode_tiled) return false;
+  if (p.Cin % BLOCK_K != 0 || p.Cout % 64 != 0) return false;
+  // dense NDHWC input only
+  if (p.xsW != p.Cin || p.xsH != (long long)p.Wi * p.Cin || p.xsT != (long long)p.Hi * p.Wi * p.Cin ||
+      p.xsB != (long long)p.Ti * p.Hi * p.Wi * p.Cin)
+    return false;
+  if (p.kt > 16 || p.kh > 16 || p.kw > 16) return false;
+  if (p.M >= (1LL << 31)) return false;
+  return true;
+}
+
+int conv_umma_launch(const ConvProblem& p, cudaStream_t s) {
+  UmmaParams up;
+  up.bias = p.bias; up.res = (const bf16*)p.res; up.M = p.M; up.Cout = p.Cout; up.Cin = p.Cin;
+  up.kt = p.kt; up.kh = p.kh; up.kw = p.kw; up.st = p.st; up.sh = p.sh; up.sw = p.sw;
+  up.pt = p.pt; up.ph = p.ph; up.pw = p.pw; up.To = p.To; up.Ho = p.Ho; up.Wo = p.Wo;
+  up.relu = p.relu;
+  const bool pointwise = p.kt == 1 && p.kh == 1 && p.kw == 1 && p.st == 1 && p.sh == 1 && p.sw == 1;
+  const char* force = getenv("AFB200_FORCE_IM2COL");
+  up.im2col = (pointwise && !(force && force[0] == '1')) ? 0 : 1;
+  up.num_m_tiles = (int)((p.M + BLOCK_M - 1) / BLOCK_M);
+
+  // tile width: the widest of 256/128/64 that still gives every SM at least ~2 tiles
+  int bn = 64;
+  for (int cand : {256, 128}) {
+    if (p.Cout % cand == 0 && (long long)up.num_m_tiles * (p.Cout / cand) >= 2LL * g_num_sms) { bn = cand; break; }
+  }
+  const char* fbn = getenv("AFB200_BLOCK_N");
+  if (fbn) { int v = atoi(fbn); if ((v == 64 || v == 128 || v == 256) && p.Cout % v == 0) bn = v; }
+  up.num_n_tiles = p.Cout / bn;
+
+  alignas(64) CUtensorMap ta, tb, ty;
+  if (up.im2col) {
+    cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Ti, (cuuint64_t)p.B};
+    cuuint64_t strides[4] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Wi * p.Cin * 2, (cuuint64_t)p.Hi * p.Wi * p.Cin * 2,
+                             (cuuint64_t)p.Ti * p.Hi * p.Wi * p.Cin * 2};
+    int lower[3] = {-p.pw, -p.ph, -p.pt};
+    int upper[3] = {p.pw - (p.kw - 1), p.ph - (p.kh - 1), p.pt - (p.kt - 1)};
+    if (g_corner_dhw) { int t0 = lower[0]; lower[0] = lower[2]; lower[2] = t0; t0 = upper[0]; upper[0] = upper[2]; upper[2] = t0; }
+    cuuint32_t es[5] = {1, (cuuint32_t)p.sw, (cuuint32_t)p.sh, (cuuint32_t)p.st, 1};
+    CUresult r = g_encode_im2col(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(p.x), dims, strides, lower,
+                                 upper, BLOCK_K, BLOCK_M, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeIm2col failed: %d (C=%d W=%d H=%d T=%d B=%d k=%dx%dx%d)", (int)r, p.Cin, p.Wi, p.Hi,
+                p.Ti, p.B, p.kt, p.kh, p.kw);
+      return AF_ERR_CUDA;
+    }
+    // CUTLASS (copy_traits_sm90_im2col.hpp) clears bit 21 of descriptor word 1 for tensors
+    // smaller than 128 KiB on drivers <= 13.1 to work around a driver encoding issue.
+    const unsigned long long bytes = (unsigned long long)p.B * p.Ti * p.Hi * p.Wi * p.Cin * 2ULL;
+    if (g_driver_version <= 13010 && bytes < 131072ULL) reinterpret_cast<uint64_t*>(&ta)[1] &= ~(1ULL << 21);
+  } else {
+    int rc = encode_2d(&ta, p.x, (uint64_t)p.M, (uint64_t)p.Cin, BLOCK_M, "A");
+    if (rc) return rc;
+  }
+  const int taps = p.kt * p.kh * p.kw;
+  int rc = encode_2d(&tb, p.w, (uint64_t)taps * p.Cout, (uint64_t)p.Cin, (uint32_t)bn, "W");
+  if (rc) return rc;
+  rc = encode_2d(&ty, p.y, (uint64_t)p.M, (uint64_t)p.Cout, BLOCK_M, "Y");
+  if (rc) return rc;
+
+  switch (bn) {
+    case 256: return launch_t<256, 4>(ta, tb, ty, up, s);
+    case 128: return launch_t<128, 5>(ta, tb, ty, up, s);
+    default: return launch_t<64, 6>(ta, tb, ty, up, s);
+  }
+}
+
+}  // namespace afb

@@ -1,0 +1,51 @@
+"""Batching services on top of the engine, shaped like the streaming callers' singletons.
+
+  ClassifierSvc.infer_scores  <- altfreezing/TEST2.py:138-204, test/af_realtime.py:64-96
+  CropAlignSvc.__call__       <- altfreezing/TEST2.py:207-212
+"""
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .crop import CropAlignB200
+from .engine import Engine, mean_std_255
+
+
+class ClassifierSvc:
+    """`infer_scores(u8[B,T,H,W,3]) -> np.float32[B]` (sigmoid of the logit).
+
+    The reference converts to fp32 on the device, permutes to NCTHW, normalises and runs the
+    model; here the u8 batch is uploaded once and K-packed, normalised and classified by the
+    C library (af_infer_u8_host)."""
+
+    def __init__(self, state_dict, device: int = 0, precision: str = "bf16", max_batch: int = 32,
+                 clip_size: int = 32, imsize: int = 224):
+        self.engine = Engine(state_dict, device=device, max_batch=max_batch, precision=precision,
+                             clip_t=clip_size, clip_s=imsize)
+        # TEST2.py:147-148 builds mean/std as float32(mean)*255 on the device
+        self.engine.mean255, self.engine.std255 = mean_std_255("svc")
+        self.clip_size, self.imsize = clip_size, imsize
+        self._last_scores: Optional[np.ndarray] = None
+        self._last_logits: Optional[np.ndarray] = None
+
+    def infer_scores(self, aligned_batch_bthwc) -> np.ndarray:
+        arr = np.asarray(aligned_batch_bthwc)
+        if arr.ndim != 5 or arr.shape[1:] != (self.clip_size, self.imsize, self.imsize, 3):
+            raise ValueError("infer_scores expects u8 [B,%d,%d,%d,3], got %s" %
+                             (self.clip_size, self.imsize, self.imsize, arr.shape))
+        if arr.dtype != np.uint8:
+            # the reference casts whatever it gets to fp32; aligned crops are always u8
+            arr = np.clip(np.rint(arr), 0, 255).astype(np.uint8)
+        scores, logits = self.engine.infer_scores_u8_host(arr, return_logits=True)
+        self._last_scores, self._last_logits = scores.copy(), logits
+        return scores
+
+
+class CropAlignSvc:
+    def __init__(self, imsize: int = 224, device: int = 0):
+        self.fn = CropAlignB200(imsize, device=device)
+
+    def __call__(self, infos, imgs):
+        _, aligned = self.fn(infos, imgs)
+        return aligned
