@@ -111,6 +111,14 @@ af_status af_create(af_handle* out, int32_t device, const af_weights* w, int32_t
                     int32_t precision);
 af_status af_destroy(af_handle h);
 
+/* Counters for the benchmark's roofline line.  With option "profile_events" = 1 every
+ * conv launch is bracketed by CUDA events on its stream (no synchronisation); the getters
+ * below synchronise the device and aggregate them since the last "reset_stats" option call:
+ *   "conv_umma_ms" / "conv_umma_launches" / "conv_umma_flops"   tcgen05 conv kernel
+ *   "conv_simt_ms" / "conv_simt_launches" / "conv_simt_flops"   CUDA-core conv kernel
+ *   "conv_bytes"                                                algorithmic activation+weight bytes of all convs */
+af_status af_get_stat(af_handle h, const char* name, double* value);
+
 /* Tuning knobs (chunk sizes of the batch schedule); name/value pairs, optional. */
 af_status af_set_option(af_handle h, const char* name, int64_t value);
 

@@ -5,6 +5,7 @@
 // residual add + ReLU fused into the `c` conv's epilogue (resnet_helper.py:438-444).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -22,6 +23,26 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool OpTrace::enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("AFB200_TRACE"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
+OpTrace::OpTrace(cudaStream_t st) : s(st) {
+  if (!enabled()) return;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, s);
+}
+void OpTrace::done(const char* what, double flops, double bytes) {
+  if (!enabled()) return;
+  cudaEventRecord(e1, s);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  fprintf(stderr, "[afb200] %-46s %8.3f ms  %8.1f TFLOP/s  %8.1f GB/s\n", what, ms, flops / (ms * 1e9), bytes / (ms * 1e6));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
 }
 
 static inline float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
@@ -72,6 +93,38 @@ static int upload_layer(const af_conv_desc& d, bool is_bf16, ConvLayer& L) {
   return AF_OK;
 }
 
+// bf16 engine: the stem conv re-expressed on the x/row-pair-unfolded clip (crop_pack.cu,
+// stem_unfold_kernel): 64 "channels" k = dyy*28 + dx*4 + c, taps (dt, p) with input row
+// dy = 2p + dyy.  W'[dt][p][cout][k] = W[cout][c][dt][2p+dyy][dx].
+static int upload_stem_unfolded(const af_conv_desc& d, ConvLayer& L) {
+  if (d.kt != 5 || d.kh != 7 || d.kw != 7 || d.cin != 3 || d.st != 1 || d.sh != 2 || d.sw != 2 || d.pt != 2 ||
+      d.ph != 3 || d.pw != 3)
+    return AF_ERR_INVALID;
+  L.cin = 64; L.cin_p = 64; L.cout = d.cout;
+  L.kt = 5; L.kh = 4; L.kw = 1; L.st = 1; L.sh = 1; L.sw = 1; L.pt = 2; L.ph = 0; L.pw = 0;
+  const int taps = 20;
+  const size_t n = (size_t)taps * d.cout * 64;
+  std::vector<bf16> wu(n, __float2bfloat16_rn(0.f));
+  std::vector<float> ws(n, 0.f);
+  for (int co = 0; co < d.cout; ++co)
+    for (int c = 0; c < 3; ++c)
+      for (int dt = 0; dt < 5; ++dt)
+        for (int dy = 0; dy < 7; ++dy)
+          for (int dx = 0; dx < 7; ++dx) {
+            const float v = bf16_round(d.weight[((((size_t)co * 3 + c) * 5 + dt) * 7 + dy) * 7 + dx]);
+            const int pr = dy / 2, dyy = dy % 2, k = dyy * 28 + dx * 4 + c, tap = dt * 4 + pr;
+            wu[((size_t)tap * d.cout + co) * 64 + k] = __float2bfloat16_rn(v);
+            ws[((size_t)tap * 64 + k) * d.cout + co] = v;
+          }
+  AFB_CUDA(cudaMalloc(&L.w_umma, n * sizeof(bf16)));
+  AFB_CUDA(cudaMemcpy(L.w_umma, wu.data(), n * sizeof(bf16), cudaMemcpyHostToDevice));
+  AFB_CUDA(cudaMalloc(&L.w_simt, n * sizeof(float)));
+  AFB_CUDA(cudaMemcpy(L.w_simt, ws.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  AFB_CUDA(cudaMalloc(&L.bias, d.cout * sizeof(float)));
+  AFB_CUDA(cudaMemcpy(L.bias, d.bias, d.cout * sizeof(float), cudaMemcpyHostToDevice));
+  return AF_OK;
+}
+
 struct Dims { int T, H, W, C; long long elems() const { return (long long)T * H * W * C; } };
 
 static Dims conv_out(const ConvLayer& L, Dims in) {
@@ -92,6 +145,8 @@ struct af_engine {
   bool is_bf16 = false;
   int T = 32, S = 224, max_batch = 1;
   std::vector<ConvLayer> convs;
+  ConvLayer stem_u;          // unfolded stem (bf16 engine), valid if has_stem_u
+  bool has_stem_u = false;
   int stem = 0;
   std::vector<af_block_desc> blocks;
   float* fc_w = nullptr;
@@ -115,6 +170,12 @@ struct af_engine {
   float* feat_ws = nullptr;  // [max_batch, feat_dim]
   uint8_t* u8_stage = nullptr;
   float* out_stage = nullptr;  // [2*max_batch] logits, scores (device staging for *_host calls)
+  // event-based conv timing (option profile_events)
+  bool profile_events = false;
+  struct EvRec { cudaEvent_t e0, e1; int kind; double flops, bytes; };
+  std::vector<EvRec> ev_recs;
+  std::vector<cudaEvent_t> ev_pool;
+  double stat_ms[2] = {0, 0}, stat_flops[2] = {0, 0}, stat_launches[2] = {0, 0}, stat_bytes = 0;
   // kept stages (fp32 NCTHW) for parity tests
   float* stage_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   Dims stage_dims[5];
@@ -138,13 +199,42 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
   p.M = (long long)B * o.T * o.H * o.W;
   const bool is_bf16 = e ? e->is_bf16 : (L.w_umma != nullptr);
   const int impl = impl_override >= 0 ? impl_override : (e ? e->conv_impl : 0);
-  if (is_bf16 && impl != 1) {
-    p.w = L.w_umma;
-    if (conv_umma_supported(p)) return conv_umma_launch(p, s);
-    if (impl == 2) { set_error("tcgen05 conv kernel does not take this shape"); return AF_ERR_INVALID; }
+  OpTrace tr(s);
+  int rc;
+  const char* which = "simt";
+  const double Kd = (double)L.kt * L.kh * L.kw * L.cin_p;
+  const double conv_flops = 2.0 * (double)p.M * L.cout * Kd;
+  const double conv_bytes = ((double)B * in.elems() + (double)p.M * L.cout * (res ? 2 : 1) + Kd * L.cout) * (is_bf16 ? 2.0 : 4.0);
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  const bool prof = e && e->profile_events;
+  if (prof) {
+    for (cudaEvent_t* pe : {&ev0, &ev1}) {
+      if (e->ev_pool.empty()) { cudaEventCreate(pe); } else { *pe = e->ev_pool.back(); e->ev_pool.pop_back(); }
+    }
+    cudaEventRecord(ev0, s);
   }
-  p.w = L.w_simt;
-  return conv_simt_launch(p, is_bf16, s);
+  p.w = L.w_umma;
+  if (is_bf16 && impl != 1 && conv_umma_supported(p)) {
+    rc = conv_umma_launch(p, s);
+    which = "umma";
+  } else if (is_bf16 && impl == 2) {
+    set_error("tcgen05 conv kernel does not take this shape");
+    return AF_ERR_INVALID;
+  } else {
+    p.w = L.w_simt;
+    rc = conv_simt_launch(p, is_bf16, s);
+  }
+  if (prof) {
+    cudaEventRecord(ev1, s);
+    e->ev_recs.push_back({ev0, ev1, which[0] == 'u' ? 0 : 1, conv_flops, conv_bytes});
+  }
+  if (OpTrace::enabled()) {
+    char nm[128];
+    snprintf(nm, sizeof(nm), "conv %s k%dx%dx%d s%d M=%lld N=%d K=%d%s", which, L.kt, L.kh, L.kw, L.sh, p.M, L.cout,
+             (int)Kd, res ? " +res" : "");
+    tr.done(nm, conv_flops, conv_bytes);
+  }
+  return rc;
 }
 
 static int dense_conv(af_engine* e, int idx, const void* x, Dims in, int B, const void* res, void* y, bool relu,
@@ -178,8 +268,10 @@ static int run_blocks(af_engine* e, int b_begin, int b_end, const void*& x, Dims
     if (blk.temporal_pool_before) {
       void* pooled = freeb.back();
       freeb.pop_back();
+      OpTrace tr(s);
       int rc = maxpool_temporal_launch(x, pooled, B, d.T, d.H, d.W, d.C, e->is_bf16, s);
       if (rc) return rc;
+      tr.done("temporal maxpool 2x1x1", 0.0, (double)B * d.elems() * 1.5 * e->esz);
       for (int i = 0; i < 5; ++i)
         if (buf[i] == x) freeb.push_back(buf[i]);
       x = pooled; d.T /= 2;
@@ -227,11 +319,25 @@ static int run_trunk(af_engine* e, int B, float* logits, float* scores, float* f
     for (int f0 = g0; f0 < g0 + gB; f0 += e->cb_front) {
       const int fB = (g0 + gB - f0) < e->cb_front ? (g0 + gB - f0) : e->cb_front;
       const char* xin = (const char*)e->clip.base + (long long)f0 * e->clip.sB * e->esz;
-      int rc = run_conv(e, stem, xin, din, e->clip.sB, e->clip.sT, e->clip.sH, e->clip.sW, fB, nullptr, e->fbuf[0],
-                        true, s);
+      int rc;
+      if (e->has_stem_u && e->conv_impl != 1) {
+        OpTrace tr(s);
+        rc = stem_unfold_launch(e->clip, f0, fB, e->fbuf[2], s);
+        if (rc) return rc;
+        const Dims du = {e->T, e->S / 2 + 3, e->S / 2, 64};
+        tr.done("stem unfold", 0.0, (double)fB * (du.elems() + (double)e->T * e->S * e->S * 4) * 2.0);
+        const long long sW = 64, sH = (long long)du.W * 64, sT = sH * du.H, sB = sT * du.T;
+        rc = run_conv(e, e->stem_u, e->fbuf[2], du, sB, sT, sH, sW, fB, nullptr, e->fbuf[0], true, s);
+      } else {
+        rc = run_conv(e, stem, xin, din, e->clip.sB, e->clip.sT, e->clip.sH, e->clip.sW, fB, nullptr, e->fbuf[0], true, s);
+      }
       if (rc) return rc;
-      rc = maxpool_spatial_launch(e->fbuf[0], e->fbuf[1], fB, dpre.T, dpre.H, dpre.W, dpre.C, e->is_bf16, s);
-      if (rc) return rc;
+      {
+        OpTrace tr(s);
+        rc = maxpool_spatial_launch(e->fbuf[0], e->fbuf[1], fB, dpre.T, dpre.H, dpre.W, dpre.C, e->is_bf16, s);
+        if (rc) return rc;
+        tr.done("stem maxpool 1x3x3", 0.0, (double)fB * (dpre.elems() + dpool.elems()) * e->esz);
+      }
       rc = keep_stage(e, 0, e->fbuf[1], dpool, f0, fB, s);
       if (rc) return rc;
       const void* x = e->fbuf[1];
@@ -250,10 +356,12 @@ static int run_trunk(af_engine* e, int B, float* logits, float* scores, float* f
     for (int bi = 0; bi < split; ++bi) stage_no += is_stage_end(e, bi) ? 1 : 0;
     int rc = run_blocks(e, split, nblk, x, d, gB, e->bbuf, g0, stage_no, s);
     if (rc) return rc;
+    OpTrace trh(s);
     rc = head_launch(x, gB, d.T * d.H * d.W, d.C, e->is_bf16, e->fc_w, e->fc_b, e->feat_ws + (long long)g0 * e->feat_dim,
                      features ? features + (long long)g0 * e->feat_dim : nullptr, logits ? logits + g0 : nullptr,
                      scores ? scores + g0 : nullptr, s);
     if (rc) return rc;
+    trh.done("head avgpool+fc", 0.0, (double)gB * d.elems() * e->esz);
   }
   return AF_OK;
 }
@@ -263,6 +371,10 @@ static int plan_workspace(af_engine* e) {
   const ConvLayer& stem = e->convs[e->stem];
   Dims d = conv_out(stem, Dims{e->T, e->S, e->S, stem.cin_p});
   long long fmax = d.elems();
+  if (e->has_stem_u) {
+    const long long u = (long long)e->T * (e->S / 2 + 3) * (e->S / 2) * 64;
+    if (u > fmax) fmax = u;
+  }
   d = Dims{d.T, (d.H + 2 - 3) / 2 + 1, (d.W + 2 - 3) / 2 + 1, d.C};
   long long bmax = 0;
   e->split = -1;
@@ -320,6 +432,7 @@ af_status af_destroy(af_handle h) {
   if (!h) return AF_OK;
   cudaSetDevice(h->device);
   for (auto& L : h->convs) free_layer(L);
+  free_layer(h->stem_u);
   free_workspace(h);
   if (h->fc_w) cudaFree(h->fc_w);
   if (h->clip_raw) cudaFree(h->clip_raw);
@@ -328,6 +441,8 @@ af_status af_destroy(af_handle h) {
   if (h->out_stage) cudaFree(h->out_stage);
   for (int i = 0; i < 5; ++i)
     if (h->stage_buf[i]) cudaFree(h->stage_buf[i]);
+  for (auto& r : h->ev_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto ev : h->ev_pool) cudaEventDestroy(ev);
   delete h;
   return AF_OK;
 }
@@ -348,6 +463,11 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
   for (int i = 0; i < w->n_convs; ++i) {
     int rc = upload_layer(w->convs[i], e->is_bf16, e->convs[i]);
     if (rc) return (af_status)rc;
+  }
+  if (e->is_bf16 && (e->S % 2 == 0)) {
+    int rc = upload_stem_unfolded(w->convs[w->stem], e->stem_u);
+    if (rc == AF_OK) e->has_stem_u = true;
+    else if (rc != AF_ERR_INVALID) return (af_status)rc;
   }
   e->blocks.assign(w->blocks, w->blocks + w->n_blocks);
   AFB_CUDA(cudaMalloc(&e->fc_w, w->feature_dim * sizeof(float)));
@@ -404,6 +524,16 @@ af_status af_set_option(af_handle h, const char* name, int64_t value) {
   std::string n(name);
   if (n == "keep_stages") { h->keep_stages = value != 0; return AF_OK; }
   if (n == "conv_impl") { h->conv_impl = (int)value; return AF_OK; }
+  if (n == "profile_events") { h->profile_events = value != 0; return AF_OK; }
+  if (n == "reset_stats") {
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& r : h->ev_recs) { h->ev_pool.push_back(r.e0); h->ev_pool.push_back(r.e1); }
+    h->ev_recs.clear();
+    for (int k = 0; k < 2; ++k) h->stat_ms[k] = h->stat_flops[k] = h->stat_launches[k] = 0;
+    h->stat_bytes = 0;
+    return AF_OK;
+  }
   if (n == "chunk_front" || n == "chunk_back") {
     if (value <= 0) { set_error("af_set_option: %s must be positive", name); return AF_ERR_INVALID; }
     AFB_CUDA(cudaSetDevice(h->device));
@@ -416,6 +546,30 @@ af_status af_set_option(af_handle h, const char* name, int64_t value) {
   }
   set_error("af_set_option: unknown option '%s'", name);
   return AF_ERR_INVALID;
+}
+
+af_status af_get_stat(af_handle h, const char* name, double* value) {
+  if (!h || !name || !value) { set_error("af_get_stat: null"); return AF_ERR_INVALID; }
+  AFB_CUDA(cudaSetDevice(h->device));
+  AFB_CUDA(cudaDeviceSynchronize());
+  for (auto& r : h->ev_recs) {          // fold finished event pairs into the running sums
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      h->stat_ms[r.kind] += ms; h->stat_flops[r.kind] += r.flops; h->stat_launches[r.kind] += 1; h->stat_bytes += r.bytes;
+    }
+    h->ev_pool.push_back(r.e0); h->ev_pool.push_back(r.e1);
+  }
+  h->ev_recs.clear();
+  std::string n(name);
+  if (n == "conv_umma_ms") *value = h->stat_ms[0];
+  else if (n == "conv_umma_flops") *value = h->stat_flops[0];
+  else if (n == "conv_umma_launches") *value = h->stat_launches[0];
+  else if (n == "conv_simt_ms") *value = h->stat_ms[1];
+  else if (n == "conv_simt_flops") *value = h->stat_flops[1];
+  else if (n == "conv_simt_launches") *value = h->stat_launches[1];
+  else if (n == "conv_bytes") *value = h->stat_bytes;
+  else { set_error("af_get_stat: unknown stat '%s'", name); return AF_ERR_INVALID; }
+  return AF_OK;
 }
 
 static af_status check_batch(af_handle h, int32_t batch, const char* who) {

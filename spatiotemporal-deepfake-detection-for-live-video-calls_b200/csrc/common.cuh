@@ -28,6 +28,15 @@ struct ConvProblem {
 void set_error(const char* fmt, ...);
 extern thread_local long long g_launches;   // kernels launched by this thread (copied into engines)
 
+// Per-op timing to stderr when AFB200_TRACE=1 (synchronises; bring-up/profiling aid only).
+struct OpTrace {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t s;
+  static bool enabled();
+  explicit OpTrace(cudaStream_t st);
+  void done(const char* what, double flops, double bytes);
+};
+
 #define AFB_CUDA(call)                                                                   \
   do {                                                                                   \
     cudaError_t _e = (call);                                                             \
@@ -61,6 +70,7 @@ struct ClipLayout {     // engine-internal normalised clip: padded NDHWC4
   int T, S;
   bool is_bf16;
 };
+int stem_unfold_launch(const ClipLayout& clip, int clip0, int B, void* U, cudaStream_t s);
 int pack_clip_launch(const void* src, int dtype, const long long strides[5], int B,
                      const ClipLayout& dst, cudaStream_t s);
 int pack_u8_launch(const uint8_t* src, int B, const float mean[3], const float stdv[3],

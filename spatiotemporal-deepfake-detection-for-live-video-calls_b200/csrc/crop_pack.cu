@@ -150,6 +150,37 @@ __global__ void __launch_bounds__(256) pack_clip_kernel(const TS* __restrict__ s
   }
 }
 
+// Stem unfold (bf16 engine only): U[b][t][r][xo][64] gathers, for output column xo and input
+// row pair r (rows 2r-3, 2r-2), the 2 x 7 x 4 window values X[t][2r-3+dyy][2xo-3+dx][c] at
+// k = dyy*28 + dx*4 + c (k >= 56 zero).  On U the reference's stem conv
+// (k[5,7,7] s[1,2,2] p[2,3,3], altfreezing/slowfast/models/stem_helper.py:156-163) becomes a
+// dense 64-channel conv with kernel [5,4,1], stride 1, pad [2,0,0] that the tcgen05 kernel takes.
+// One thread writes one 16-byte group (two 4-channel pixels).
+__global__ void __launch_bounds__(256) stem_unfold_kernel(const bf16* __restrict__ clip, long long sB, long long sT,
+                                                          long long sH, long long sW, int T_, int Hu, int Wo,
+                                                          bf16* __restrict__ U, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r_ = i;
+    const int j = (int)(r_ & 7); r_ >>= 3;
+    const int xo = (int)(r_ % Wo); r_ /= Wo;
+    const int r = (int)(r_ % Hu); r_ /= Hu;
+    const int t = (int)(r_ % T_); r_ /= T_;
+    const bf16* src = clip + r_ * sB + t * sT;
+    uint2 px[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = 2 * j + h;                 // pixel slot 0..15
+      px[h] = make_uint2(0u, 0u);
+      if (q < 14) {
+        const int dyy = q >= 7 ? 1 : 0, dx = q - 7 * dyy;
+        px[h] = *reinterpret_cast<const uint2*>(src + (long long)(2 * r - 3 + dyy) * sH + (long long)(2 * xo - 3 + dx) * sW);
+      }
+    }
+    *reinterpret_cast<uint4*>(U + i * 8) = make_uint4(px[0].x, px[0].y, px[1].x, px[1].y);
+  }
+}
+
 inline int flat_grid(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -175,6 +206,17 @@ int crop_launch(const FrameDesc* frames, const ClipGeom* geom, int B, int T, int
     crop_kernel<float, true><<<grid, block, 0, s>>>(frames, geom, T, S, bgr, nullptr, (float*)dst->base, dst->sB,
                                                     dst->sT, dst->sH, dst->sW, n);
   }
+  ++g_launches;
+  AFB_CUDA(cudaGetLastError());
+  return AF_OK;
+}
+
+int stem_unfold_launch(const ClipLayout& clip, int clip0, int B, void* U, cudaStream_t s) {
+  const int Wo = clip.S / 2, Hu = clip.S / 2 + 3;
+  const long long total = (long long)B * clip.T * Hu * Wo * 8;
+  const bf16* base = (const bf16*)clip.base + (long long)clip0 * clip.sB;
+  stem_unfold_kernel<<<flat_grid(total, 256), 256, 0, s>>>(base, clip.sB, clip.sT, clip.sH, clip.sW, clip.T, Hu, Wo,
+                                                           (bf16*)U, total);
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;

@@ -63,6 +63,11 @@ class Engine:
     def set_option(self, name: str, value: int):
         check(self._L.af_set_option(self._h, name.encode(), int(value)), "af_set_option(%s)" % name)
 
+    def get_stat(self, name: str) -> float:
+        v = C.c_double()
+        check(self._L.af_get_stat(self._h, name.encode(), C.byref(v)), "af_get_stat(%s)" % name)
+        return float(v.value)
+
     @property
     def launch_count(self) -> int:
         return int(self._L.af_launch_count(self._h))

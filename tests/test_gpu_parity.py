@@ -1,0 +1,275 @@
+"""GPU parity tests (B200): every CUDA kernel, called through the C ABI (ctypes), against the
+CPU oracle on the same seeded inputs and against the committed reference-generated goldens.
+
+Tolerances (BASELINE.json north_star): crop <= 1 LSB (we require 0), fp32 path max|dlogit| <= 1e-3,
+bf16 path <= 2e-2 with the same decision at logit 0 (after re-centring the head bias).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import afb200
+from afb200 import synthetic
+from oracle import crop_oracle, i3d_oracle
+from tests.helpers import crop_case_inputs, sha256_u8, stage_sample_index
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    assert torch.cuda.get_device_capability(0)[0] == 10, "sm_100a required"
+    afb200.lib()                     # fails loudly if libafb200.so is missing
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def clips_u8():
+    return np.stack([synthetic.synthetic_clip_u8(i) for i in range(4)])
+
+
+# ------------------------------------------------------------------ K1 crop / warp / normalise
+@pytest.mark.parametrize("name", ["fixture", "synthetic0", "synthetic1", "synthetic2"])
+def test_crop_kernel_bit_exact(dev, golden_crop, name):
+    lms, imgs, frames, bigs = crop_case_inputs(golden_crop, name, synthetic, afb200.crop)
+    lt, wh, diff, tfm, trans = afb200.clip_geometry(bigs, [l[1] for l in lms], 224)
+    fr = [torch.from_numpy(f).to(dev) for f in frames]
+    out = afb200.crop.crop_u8(fr, bigs, [(tfm, lt, wh)], 32, 224)[0].cpu().numpy()
+    assert np.array_equal(sha256_u8(out), golden_crop[name + "_img_sha256"])        # == cv2.warpAffine in the reference
+    assert np.array_equal(out[:, ::4, ::4, :], golden_crop[name + "_img_sub"])
+    # FasterCropAlignXRay-compatible wrapper on the separate crops
+    t68, out2 = afb200.CropAlignB200(224)(lms, imgs)
+    assert np.array_equal(out2, out)
+    assert np.abs(t68 - golden_crop[name + "_lm68_t"]).max() <= 1e-9
+
+
+def test_crop_kernel_edge_cases(dev):
+    rng = np.random.default_rng(3)
+    H, W = 240, 320
+    frames = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(4)]
+    fr = [torch.from_numpy(f).to(dev) for f in frames]
+    cases = [
+        # heavy rotation + crop partly outside the canvas; boxes touching the frame border; tiny box
+        (np.array([[0.9, -0.6, 40.0], [0.6, 0.9, -70.0]]), [(0, 0, 320, 240)] * 4),
+        (np.array([[2.5, 0.0, -300.0], [0.0, 2.5, -200.0]]), [(100, 60, 220, 170), (90, 50, 230, 180), (100, 60, 220, 170), (110, 70, 210, 160)]),
+        (np.array([[0.3, 0.0, 10.0], [0.0, 0.3, 10.0]]), [(5, 5, 319, 239)] * 4),
+        (np.array([[-1.0, 0.0, 200.0], [0.0, 1.0, 0.0]]), [(150, 100, 153, 102)] * 4),     # reflection, 3x2 box
+    ]
+    for tfm, boxes in cases:
+        bigs = np.array(boxes)
+        lt = bigs[:, :2].min(0)
+        wh = tuple(int(v) for v in (bigs[:, 2:].max(0) - lt))
+        out = afb200.crop.crop_u8(fr, bigs, [(tfm, lt, wh)], 4, 64)[0].cpu().numpy()
+        want = crop_oracle.crop_align_from_frames(frames, bigs, tfm, lt, wh, 64)
+        assert np.array_equal(out, want)
+    # BGR frames: the kernel swaps while reading
+    bigs = np.array([(0, 0, 320, 240)] * 4)
+    tfm = np.array([[0.8, 0.1, 3.0], [-0.1, 0.8, 5.0]])
+    out = afb200.crop.crop_u8(fr, bigs, [(tfm, (0, 0), (320, 240))], 4, 64, bgr=True)[0].cpu().numpy()
+    want = crop_oracle.crop_align_from_frames([f[..., ::-1] for f in frames], bigs, tfm, (0, 0), (320, 240), 64)
+    assert np.array_equal(out, want)
+
+
+# ------------------------------------------------------------------ conv kernels, layer level
+def _conv_ref(x, w, b, stride, pad, relu, res):
+    y = F.conv3d(x.float().cpu().permute(0, 4, 1, 2, 3), w, b, stride, pad)
+    if res is not None:
+        y = y + res.float().cpu().permute(0, 4, 1, 2, 3)
+    return (F.relu(y) if relu else y).permute(0, 2, 3, 4, 1).contiguous()
+
+
+CONV_CASES = [
+    # cin, cout, kernel, stride, pad, B, T, H, W
+    (64, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 4, 16, 16),
+    (256, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 3, 7, 7),         # M = 147: tail tile
+    (64, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), 2, 4, 12, 12),
+    (128, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, 4, 7, 7),
+    (128, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1), 1, 4, 16, 16),
+    (256, 512, (1, 1, 1), (1, 2, 2), (0, 0, 0), 1, 4, 14, 14),
+    (1024, 512, (3, 1, 1), (1, 1, 1), (1, 0, 0), 1, 16, 7, 7),
+    (512, 2048, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 16, 7, 7),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("mode", ["simt_fp32", "simt_bf16", "umma_bf16"])
+def test_conv_kernels_vs_torch_fp32(dev, case, mode):
+    cin, cout, k, s, p, B, T, H, W = case
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    dtype = torch.float32 if mode == "simt_fp32" else torch.bfloat16
+    impl = 2 if mode == "umma_bf16" else 1
+    x = torch.randn(B, T, H, W, cin, generator=g).to(dev, dtype)
+    w = torch.randn(cout, cin, *k, generator=g) * (2.0 / (cin * k[0] * k[1] * k[2])) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    wr = w.to(dtype).float()
+    for res_on in (False, True):
+        y0 = _conv_ref(x, wr, b, s, p, True, None)
+        res = torch.randn(y0.shape, generator=g).to(dev, dtype) if res_on else None
+        want = _conv_ref(x, wr, b, s, p, True, res)
+        got = afb200.conv_ndhwc(x, w, b, s, p, True, res, impl=impl).float().cpu()
+        # fp32: accumulation-order noise only; bf16: one rounding of the output (2^-8 relative)
+        tol = 1e-4 if dtype == torch.float32 else 2.0 ** -8 * max(1.0, want.abs().max().item()) + 1e-3
+        assert (got - want).abs().max().item() <= tol
+
+
+def test_umma_and_simt_bf16_agree_closely(dev):
+    """Same bf16 inputs, both fp32-accumulating: results may differ only by accumulation
+    order, i.e. by at most one bf16 ulp after the final rounding."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 4, 14, 14, 256, generator=g).to(dev, torch.bfloat16)
+    w = torch.randn(256, 256, 1, 3, 3, generator=g) * 0.03
+    b = torch.randn(256, generator=g) * 0.1
+    a = afb200.conv_ndhwc(x, w, b, (1, 1, 1), (0, 1, 1), True, None, impl=1).float()
+    c = afb200.conv_ndhwc(x, w, b, (1, 1, 1), (0, 1, 1), True, None, impl=2).float()
+    d = (a - c).abs()
+    assert d.max().item() <= 2.0 ** -7 * max(1.0, a.abs().max().item())
+    assert (d > 0).float().mean().item() < 0.05
+
+
+# ------------------------------------------------------------------ whole path
+@pytest.fixture(scope="module")
+def oracle_out(state_dict, clips_u8):
+    x = synthetic.normalise_clip(clips_u8)
+    logits, stages = i3d_oracle.forward(state_dict, x, return_stages=True)
+    return x, logits, stages
+
+
+def test_fp32_path_matches_oracle_and_golden(dev, state_dict, clips_u8, oracle_out, golden_model):
+    x, o_logits, o_stages = oracle_out
+    eng = afb200.Engine(state_dict, max_batch=4, precision="fp32")
+    eng.set_option("keep_stages", 1)
+    logits, feats = eng.forward(x.to(dev), return_features=True)
+    assert (logits.cpu() - o_logits).abs().max().item() <= 1e-3
+    assert np.abs(logits.cpu().numpy() - golden_model["logits"]).max() <= 1e-3
+    assert np.abs(feats.cpu().numpy() - golden_model["features"]).max() <= 1e-3
+    for si, name in enumerate(("s1", "s2", "s3", "s4", "s5")):
+        got = eng.get_stage(si + 1).cpu()
+        assert tuple(got.shape) == tuple(golden_model[name + "_shape"])
+        idx = stage_sample_index(got.numel())
+        assert np.abs(got.reshape(-1).numpy()[idx] - golden_model[name + "_samples"]).max() <= 1e-4
+        assert (got - o_stages[si]).abs().max().item() <= 1e-4
+    eng.close()
+
+
+def test_bf16_path_within_tolerance_and_same_decision(dev, state_dict, clips_u8, oracle_out, golden_model):
+    x, o_logits, o_stages = oracle_out
+    # re-centre the head bias so that the four clips straddle the decision threshold
+    sd = dict(state_dict)
+    med = float(o_logits.median())
+    sd["resnet.head.projection.bias"] = state_dict["resnet.head.projection.bias"] - med
+    ref = o_logits - med
+    eng = afb200.Engine(sd, max_batch=4, precision="bf16")
+    eng.set_option("keep_stages", 1)
+    logits = eng.forward(x.to(dev)).cpu()
+    err = (logits - ref).abs().max().item()
+    assert err <= 2e-2, err
+    near_tie = ref.abs() < 2e-2
+    assert torch.equal((logits > 0)[~near_tie], (ref > 0)[~near_tie])
+    assert (ref > 0).any() and (ref < 0).any()
+    for si in range(5):
+        got = eng.get_stage(si + 1).cpu()
+        rel = ((got - o_stages[si]).norm() / o_stages[si].norm()).item()
+        assert rel <= 2e-2, (si, rel)
+    # the launch counter moves: these were our kernels, not a fallback
+    assert eng.launch_count >= 60
+    eng.close()
+
+
+def test_input_layouts_and_dtypes_give_same_logits(dev, state_dict, clips_u8):
+    eng = afb200.Engine(state_dict, max_batch=2, precision="fp32")
+    x = synthetic.normalise_clip(clips_u8[:2]).to(dev)
+    base = eng.forward(x)
+    # permuted NTHWC view (demo.py:317) and channels_last_3d (TEST2.py:155)
+    nthwc = x.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+    assert torch.equal(eng.forward(nthwc), base)
+    assert torch.equal(eng.forward(x.contiguous(memory_format=torch.channels_last_3d)), base)
+    # u8 entry == float entry when the constants agree
+    lg, sc = eng.infer_u8(torch.from_numpy(clips_u8[:2]).to(dev))
+    assert (lg.view(-1) - base.view(-1)).abs().max().item() <= 1e-5
+    assert torch.allclose(sc, torch.sigmoid(lg))
+    # more clips than max_batch are chunked by the host
+    x3 = torch.cat([x, x[:1]])
+    assert torch.equal(eng.forward(x3)[:2], base)
+    with pytest.raises(ValueError):
+        eng.forward(x[:, :, :16])
+    eng.close()
+
+
+def test_crop_infer_equals_crop_then_infer(dev, state_dict):
+    H, W = 720, 1280
+    eng = afb200.Engine(state_dict, max_batch=2, precision="bf16")
+    frames, boxes, geoms, fr_all = [], [], [], []
+    for c in range(2):
+        track = synthetic.synthetic_track(c)
+        fr = [torch.from_numpy(synthetic.synthetic_frame_u8(10 * c + f)).to(dev) for f in range(32)]
+        bigs = np.stack([afb200.get_crop_box((H, W), b, 0.5) for b, _ in track])
+        lm5_rel = [lm - big[:2][None] for (_, lm), big in zip(track, bigs)]
+        lt, wh, diff, tfm, trans = afb200.clip_geometry(bigs, lm5_rel, 224)
+        frames += fr
+        boxes += list(bigs)
+        geoms.append((tfm, lt, wh))
+    u8 = afb200.crop.crop_u8(frames, boxes, geoms, 32, 224)
+    lg_a, sc_a = eng.infer_u8(u8)
+    fd, cg = afb200.crop.pack_descriptors(frames, boxes, geoms, dev)
+    lg_b, sc_b = eng.crop_infer(fd, cg, 2)
+    assert torch.equal(lg_a, lg_b)            # fused path writes the identical normalised clip
+    # host-buffer service call (ClassifierSvc.infer_scores boundary)
+    scores = eng.infer_scores_u8_host(u8.cpu().numpy())
+    assert np.allclose(scores, sc_a.cpu().numpy(), atol=1e-6)
+    eng.close()
+
+
+def test_classifier_plugin_interface_and_feature_hook(dev, state_dict, clips_u8, oracle_out):
+    x, o_logits, o_stages = oracle_out
+    clf = afb200.Classifier(precision="fp32", max_batch=2).to(dev).eval()
+    clf.load_state_dict_tolerant({"state_dict": {"module." + k: v for k, v in state_dict.items()}})
+    with torch.no_grad():
+        out = clf(x[:2].to(dev))
+    assert set(out) == {"final_output"} and tuple(out["final_output"].shape) == (2, 1)
+    assert (out["final_output"].cpu() - o_logits[:2]).abs().max().item() <= 1e-3
+    # feature.py:106-114: hook the LAST nn.Linear and read its input
+    lin = [m for m in clf.modules() if isinstance(m, torch.nn.Linear)][-1]
+    grabbed = {}
+    h = lin.register_forward_hook(lambda m, i, o: grabbed.update(feat=i[0].detach()))
+    with torch.no_grad():
+        out2 = clf(x[:2].to(dev))
+    h.remove()
+    assert grabbed["feat"].reshape(2, -1).shape == (2, 2048)
+    assert (grabbed["feat"].reshape(2, -1).cpu() - o_stages[5][:2]).abs().max().item() <= 1e-3
+    assert (out2["final_output"] - out["final_output"]).abs().max().item() <= 1e-4
+    # reloading other weights re-folds
+    sd2 = synthetic.synthetic_state_dict(1)
+    clf.load_state_dict_tolerant(sd2)
+    with torch.no_grad():
+        out3 = clf(x[:1].to(dev))
+    assert (out3["final_output"] - out["final_output"][:1]).abs().max().item() > 1e-3
+
+
+def test_service_infer_scores(dev, state_dict, clips_u8, oracle_out):
+    x, o_logits, _ = oracle_out
+    svc = afb200.ClassifierSvc(state_dict, precision="bf16", max_batch=2)
+    scores = svc.infer_scores(clips_u8[:3])
+    assert scores.shape == (3,) and scores.dtype == np.float32
+    assert np.abs(scores - torch.sigmoid(o_logits[:3, 0]).numpy()).max() <= 5e-3
+    with pytest.raises(ValueError):
+        svc.infer_scores(clips_u8[:, :8])
+
+
+def test_linearity_property_of_conv_at_full_size(dev):
+    """Size-independent property at a full BASELINE layer size (s2 1x3x3, one clip):
+    conv(x1 + x2) == conv(x1) + conv(x2) without bias/ReLU, up to bf16 rounding."""
+    g = torch.Generator().manual_seed(9)
+    x1 = (torch.randn(1, 32, 56, 56, 64, generator=g) * 0.5).to(dev, torch.bfloat16)
+    x2 = (torch.randn(1, 32, 56, 56, 64, generator=g) * 0.5).to(dev, torch.bfloat16)
+    w = torch.randn(64, 64, 1, 3, 3, generator=g) * 0.05
+    z = torch.zeros(64)
+    xs = (x1.float() + x2.float()).to(torch.bfloat16)
+    xs_err = (xs.float() - (x1.float() + x2.float())).abs().max().item()
+    a = afb200.conv_ndhwc(xs, w, z, (1, 1, 1), (0, 1, 1), False, None, impl=2).float()
+    b = afb200.conv_ndhwc(x1, w, z, (1, 1, 1), (0, 1, 1), False, None, impl=2).float() + \
+        afb200.conv_ndhwc(x2, w, z, (1, 1, 1), (0, 1, 1), False, None, impl=2).float()
+    scale = b.abs().max().item()
+    assert (a - b).abs().max().item() <= 3 * 2.0 ** -8 * scale + 576 * 0.05 * xs_err
