@@ -24,6 +24,7 @@
 
 #include "../../include/afb200.h"
 #include "common.cuh"
+#include "umma_ptx.cuh"
 
 namespace afb {
 
@@ -49,123 +50,14 @@ struct UmmaParams {
   int im2col;
 };
 
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int x, int y) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(x), "r"(y)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_im2col_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c, int w, int h,
-                                                   int d, int n, uint16_t ow, uint16_t oh, uint16_t od) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
-      "%7}], [%2], {%8, %9, %10};" ::"r"(smem_u32(dst)),
-      "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "h"(ow), "h"(oh), "h"(od)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int x, int y) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)m),
-               "r"(smem_u32(src)), "r"(x), "r"(y)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-template <int N> __device__ __forceinline__ void tma_store_wait() {
-  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// K-major, 128B-swizzled shared-memory matrix descriptor (rows of 128 bytes, 8-row groups
-// 1024 bytes apart). Encoding per the PTX ISA "shared memory descriptor" / CUTLASS
-// cute/arch/mma_sm100_desc.hpp: addr>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
-// version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BLOCK_N.
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-#define TMEM_LD_32x32b_x32(taddr, r)                                                                               \
-  asm volatile(                                                                                                    \
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                    \
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                    \
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), \
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),      \
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),     \
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                   \
-      : "r"(taddr)                                                                                                 \
-      : "memory")
-
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 template <int BLOCK_N, int STAGES> struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
-  static constexpr int OFF_BIAS = OFF_OUT + 2 * OUT_STAGE_BYTES;
+  static constexpr int OFF_RES = OFF_OUT + 2 * OUT_STAGE_BYTES;        // residual tiles (TMA-loaded)
+  static constexpr int OFF_BIAS = OFF_RES + 2 * OUT_STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_BIAS + BLOCK_N * 4;
-  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 6;
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;   // slack for the 1024-byte alignment of the base
@@ -174,16 +66,19 @@ template <int BLOCK_N, int STAGES> struct SmemLayout {
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const __grid_constant__ CUtensorMap tm_y, const UmmaParams p) {
+                 const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_r,
+                 const UmmaParams p) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_out = smem + L::OFF_OUT;
+  uint8_t* smem_res = smem + L::OFF_RES;
   float* bias_s = reinterpret_cast<float*>(smem + L::OFF_BIAS);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* res_full = tmem_empty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -197,7 +92,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tma_prefetch_desc(&tm_b);
     tma_prefetch_desc(&tm_y);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_THREADS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_THREADS); mbar_init(&res_full[i], 1); }
+    tma_prefetch_desc(&tm_r);
     fence_barrier_init();
   } else if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
@@ -280,6 +176,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int row = quad * 32 + lane;              // accumulator row == output pixel within the tile
     int it = 0;
     int out_buf = 0;
+    uint32_t res_phase = 0;                        // bit s = parity of the next completion of residual slot s
+    const bool has_res = p.res != nullptr;
+    constexpr int CHUNKS = BLOCK_N / 64;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
       const long long m0 = (long long)m_tile * BLOCK_M;
@@ -287,15 +186,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       for (int i = et; i < BLOCK_N; i += EPI_THREADS) bias_s[i] = __ldg(p.bias + n0 + i);
+      // Residual tiles arrive by TMA into their own 2-deep ring, prefetched ahead of the math.
+      // chunk c of a tile uses ring slot (c & 1): CHUNKS is 1, 2 or 4, so slot use is in order.
+      if (has_res && et == 0) {
+#pragma unroll
+        for (int c = 0; c < (CHUNKS < 2 ? CHUNKS : 2); ++c) {
+          const int slot = CHUNKS == 1 ? (it & 1) : c;
+          mbar_expect_tx(&res_full[slot], OUT_STAGE_BYTES);
+          tma_load_2d(smem_res + slot * OUT_STAGE_BYTES, &tm_r, &res_full[slot], n0 + c * 64, (int)m0);
+        }
+      }
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const long long m = m0 + row;
-      const bool row_ok = m < p.M;
 #pragma unroll 1
-      for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk) {
+      for (int chunk = 0; chunk < CHUNKS; ++chunk) {
         uint8_t* sout = smem_out + out_buf * OUT_STAGE_BYTES;
+        const int slot = CHUNKS == 1 ? (it & 1) : (chunk & 1);
+        const uint8_t* sres = smem_res + slot * OUT_STAGE_BYTES;
         if (et == 0) tma_store_wait_read<1>();     // the store that last read this buffer is done
         epi_bar_sync();                            // (also publishes bias_s)
+        if (has_res) {
+          mbar_wait(&res_full[slot], (res_phase >> slot) & 1u);
+          res_phase ^= 1u << slot;
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t v[32];
@@ -306,11 +219,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_s[cbase + j];
-          if (p.res != nullptr && row_ok) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + m * p.Cout + n0 + cbase);
+          if (has_res) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint4 t = __ldg(rp + q);
+              const int j16 = half * 4 + q;
+              const uint4 t = *reinterpret_cast<const uint4*>(sres + row * 128 + ((j16 ^ (row & 7)) << 4));
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -333,15 +246,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             *reinterpret_cast<uint4*>(sout + row * 128 + ((j16 ^ (row & 7)) << 4)) = t;
           }
         }
-        if (chunk == BLOCK_N / 64 - 1) {           // all TMEM reads of this accumulator are done
+        if (chunk == CHUNKS - 1) {                 // all TMEM reads of this accumulator are done
           tc_fence_before();
           mbar_arrive(&tmem_empty[as]);
         }
         fence_proxy_async_smem();
-        epi_bar_sync();
+        epi_bar_sync();                            // out tile complete; residual slot fully consumed
         if (et == 0) {
           tma_store_2d(&tm_y, sout, n0 + chunk * 64, (int)m0);
           tma_store_commit();
+          if (has_res && chunk + 2 < CHUNKS) {     // refill the slot just drained
+            mbar_expect_tx(&res_full[slot], OUT_STAGE_BYTES);
+            tma_load_2d(smem_res + slot * OUT_STAGE_BYTES, &tm_r, &res_full[slot], n0 + (chunk + 2) * 64, (int)m0);
+          }
         }
         out_buf ^= 1;
       }
@@ -373,7 +290,8 @@ int g_driver_version = 0;
 bool g_corner_dhw = false;    // AFB200_IM2COL_CORNERS=dhw flips the corner array order (bring-up knob)
 
 template <int BLOCK_N, int STAGES>
-int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const UmmaParams& up, cudaStream_t s) {
+int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const CUtensorMap& tr,
+             const UmmaParams& up, cudaStream_t s) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   static bool configured = false;
   auto kern = conv_umma_kernel<BLOCK_N, STAGES>;
@@ -383,7 +301,7 @@ int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty
   }
   const int tiles = up.num_m_tiles * up.num_n_tiles;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, NUM_THREADS, L::DYN_BYTES, s>>>(ta, tb, ty, up);
+  kern<<<grid, NUM_THREADS, L::DYN_BYTES, s>>>(ta, tb, ty, tr, up);
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;
@@ -459,7 +377,7 @@ int conv_umma_launch(const ConvProblem& p, cudaStream_t s) {
   if (fbn) { int v = atoi(fbn); if ((v == 64 || v == 128 || v == 256) && p.Cout % v == 0) bn = v; }
   up.num_n_tiles = p.Cout / bn;
 
-  alignas(64) CUtensorMap ta, tb, ty;
+  alignas(64) CUtensorMap ta, tb, ty, tr;
   if (up.im2col) {
     cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Ti, (cuuint64_t)p.B};
     cuuint64_t strides[4] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Wi * p.Cin * 2, (cuuint64_t)p.Hi * p.Wi * p.Cin * 2,
@@ -489,11 +407,13 @@ int conv_umma_launch(const ConvProblem& p, cudaStream_t s) {
   if (rc) return rc;
   rc = encode_2d(&ty, p.y, (uint64_t)p.M, (uint64_t)p.Cout, BLOCK_M, "Y");
   if (rc) return rc;
+  rc = encode_2d(&tr, p.res ? p.res : p.y, (uint64_t)p.M, (uint64_t)p.Cout, BLOCK_M, "R");
+  if (rc) return rc;
 
   switch (bn) {
-    case 256: return launch_t<256, 4>(ta, tb, ty, up, s);
-    case 128: return launch_t<128, 5>(ta, tb, ty, up, s);
-    default: return launch_t<64, 6>(ta, tb, ty, up, s);
+    case 256: return launch_t<256, 3>(ta, tb, ty, tr, up, s);
+    case 128: return launch_t<128, 4>(ta, tb, ty, tr, up, s);
+    default: return launch_t<64, 6>(ta, tb, ty, tr, up, s);
   }
 }
 

@@ -12,7 +12,7 @@ eng = afb200.Engine(sd, max_batch=B, precision="bf16")
 if cf: eng.set_option("chunk_front", cf)
 if cb: eng.set_option("chunk_back", cb)
 u8 = torch.randint(0, 256, (B, 32, 224, 224, 3), dtype=torch.uint8, device="cuda")
-os.environ["AFB200_TRACE"] = "0"
+
 eng.infer_u8(u8); torch.cuda.synchronize()
 print("---- traced pass B=%d" % B, file=sys.stderr)
 eng.infer_u8(u8); torch.cuda.synchronize()
