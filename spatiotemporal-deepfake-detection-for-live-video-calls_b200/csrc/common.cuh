@@ -53,6 +53,10 @@ int conv_simt_launch(const ConvProblem& p, bool is_bf16, cudaStream_t s);
 bool conv_umma_supported(const ConvProblem& p);
 int conv_umma_launch(const ConvProblem& p, cudaStream_t s);
 int conv_umma_init();
+// conv_rows.cu (row-halo tcgen05 kernel for Cout=64 layers with vertical taps)
+bool conv_rows_supported(const ConvProblem& p);
+int conv_rows_launch(const ConvProblem& p, cudaStream_t s);
+int conv_rows_init();
 // pool_head.cu
 int maxpool_spatial_launch(const void* x, void* y, int B, int T, int H, int W, int C, bool is_bf16,
                            cudaStream_t s);   // k[1,3,3] s[1,2,2] p[0,1,1]

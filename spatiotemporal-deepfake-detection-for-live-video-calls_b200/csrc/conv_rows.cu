@@ -1,0 +1,337 @@
+// K2b: "row-halo" tcgen05 conv for the wide, shallow layers (the unfolded stem and the
+// 1x3x3 convs of s2) where Cout = 64 makes the generic implicit-GEMM kernel L2-bandwidth
+// bound: there every filter tap re-loads its own 128x64 activation tile and its weight tile.
+//
+// Here an output tile is an 8-wide x 16-tall patch of one frame.  For each (channel block,
+// dt, dx) "column-tap group" ONE TMA box [8 x (16+kh-1) rows x 64 ch] is loaded; the kh
+// vertical taps are just different views of that box: the UMMA descriptor's start address
+// moves by dy*1024 bytes (8 pixels x 128 B = one swizzle atom, so the 128B-swizzle phase is
+// unchanged).  Zero padding comes from TMA out-of-bounds fill.  The group's kh weight tiles
+// are loaded once per work unit of G=4 tiles (4 accumulators live in TMEM, 2 units double
+// buffered = 512 columns), so operand traffic per tile drops from taps*(16+8) KB to
+// groups*(~19 + 8*kh/4) KB.
+//
+// Same warp roles as conv_umma.cu: warp 0 TMA producer, warp 1 MMA issuer / TMEM owner,
+// warps 2-5 epilogue (bias + ReLU -> bf16 -> swizzled smem -> 4-D TMA store).
+// Stride 1 only; no residual (neither the stem nor `b` convs have one:
+// altfreezing/slowfast/models/stem_helper.py:173-178, resnet_helper.py:311-326).
+#include <cuda.h>
+
+#include "../../include/afb200.h"
+#include "common.cuh"
+#include "umma_ptx.cuh"
+
+namespace afb {
+namespace {
+
+constexpr int RB_N = 64;          // output channels per tile (== Cout)
+constexpr int RB_X = 8, RB_R = 16;  // tile: 8 columns x 16 rows = 128 output pixels
+constexpr int RB_G = 4;           // tiles per work unit (accumulators sharing one weight load)
+constexpr int RB_THREADS = 192;
+constexpr int RB_OUT_BYTES = 128 * 64 * 2;
+
+struct RowsParams {
+  const float* bias;
+  int Cin, kt, kh, kw, pt, ph, pw;
+  int B, To, Ho, Wo;
+  int x_tiles, y_tiles, num_tiles, num_units;
+  int relu;
+  int stages;          // A ring depth
+  int a_stage_bytes;   // (16 + kh - 1) * 1024
+  int w_buf_bytes;     // kh * 64 * 128
+};
+
+__device__ __forceinline__ void tma_load_tile_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+      "%7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   (uint64_t)m),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(RB_THREADS, 1)
+conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                 const __grid_constant__ CUtensorMap tm_y, const RowsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // carve-up: [A ring][W double buffer][out ring x2][bias][barriers][tmem ptr]
+  uint8_t* smem_a = smem;
+  uint8_t* smem_w = smem_a + p.stages * p.a_stage_bytes;
+  uint8_t* smem_out = smem_w + 2 * p.w_buf_bytes;
+  float* bias_s = reinterpret_cast<float*>(smem_out + 2 * RB_OUT_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + RB_N);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* w_full = empty_bar + 8;
+  uint64_t* w_empty = w_full + 2;
+  uint64_t* tmem_full = w_empty + 2;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cblocks = p.Cin / 64;
+  const int num_phases = cblocks * p.kt * p.kw;
+  constexpr uint32_t TMEM_COLS = 2 * RB_G * RB_N;   // 512
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_y);
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
+      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  } else if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + RB_N) bias_s[threadIdx.x - 64] = __ldg(p.bias + threadIdx.x - 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t wcount = 0;                 // weight-buffer uses so far
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        for (int ph = 0; ph < num_phases; ++ph) {
+          // phase -> (channel block, dt, dx)
+          const int dx = ph % p.kw, q = ph / p.kw, dt = q % p.kt, cb = q / p.kt;
+          const int wb = wcount & 1;
+          mbar_wait(&w_empty[wb], ((wcount >> 1) & 1) ^ 1);
+          mbar_expect_tx(&w_full[wb], p.w_buf_bytes);
+          for (int dy = 0; dy < p.kh; ++dy) {
+            const int tap = (dt * p.kh + dy) * p.kw + dx;
+            tma_load_2d(smem_w + wb * p.w_buf_bytes + dy * (RB_N * 128), &tm_w, &w_full[wb], cb * 64, tap * RB_N);
+          }
+          ++wcount;
+          for (int g = 0; g < RB_G; ++g) {
+            const int tile = unit * RB_G + g;
+            if (tile >= p.num_tiles) break;
+            int r = tile;
+            const int xt = r % p.x_tiles; r /= p.x_tiles;
+            const int yt = r % p.y_tiles; r /= p.y_tiles;
+            const int to = r % p.To;
+            const int b = r / p.To;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], p.a_stage_bytes);
+            tma_load_tile_5d(smem_a + stage * p.a_stage_bytes, &tm_a, &full_bar[stage], cb * 64,
+                             xt * RB_X + dx - p.pw, yt * RB_R - p.ph, to + dt - p.pt, b);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(RB_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t wcount = 0;
+      int it = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        for (int ph = 0; ph < num_phases; ++ph) {
+          const int wb = wcount & 1;
+          mbar_wait(&w_full[wb], (wcount >> 1) & 1);
+          tc_fence_after();
+          const uint32_t w_addr = smem_u32(smem_w + wb * p.w_buf_bytes);
+          for (int g = 0; g < RB_G; ++g) {
+            const int tile = unit * RB_G + g;
+            if (tile >= p.num_tiles) break;
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem_a + stage * p.a_stage_bytes);
+            const uint32_t d_tmem = tmem_base + (as * RB_G + g) * RB_N;
+            for (int dy = 0; dy < p.kh; ++dy) {
+              const uint64_t adesc = make_smem_desc(a_addr + dy * (RB_X * 128));     // next image row: +1 swizzle atom
+              const uint64_t bdesc = make_smem_desc(w_addr + dy * (RB_N * 128));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ph | dy | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&w_empty[wb]);
+          ++wcount;
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5)
+    const int et = threadIdx.x - 64;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int it = 0, out_buf = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < RB_G; ++g) {
+        const int tile = unit * RB_G + g;
+        if (tile >= p.num_tiles) break;
+        int r = tile;
+        const int xt = r % p.x_tiles; r /= p.x_tiles;
+        const int yt = r % p.y_tiles; r /= p.y_tiles;   // r = b*To + to
+        uint8_t* sout = smem_out + out_buf * RB_OUT_BYTES;
+        if (et == 0) tma_store_wait_read<1>();
+        epi_bar_sync();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (as * RB_G + g) * RB_N + half * 32;
+          TMEM_LD_32x32b_x32(taddr, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            f[j] = __uint_as_float(v[j]) + bias_s[half * 32 + j];
+            if (p.relu) f[j] = fmaxf(f[j], 0.f);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 t;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1]);
+            const int j16 = half * 4 + q;
+            *reinterpret_cast<uint4*>(sout + row * 128 + ((j16 ^ (row & 7)) << 4)) = t;
+          }
+        }
+        fence_proxy_async_smem();
+        epi_bar_sync();
+        if (et == 0) {
+          tma_store_4d(&tm_y, sout, 0, xt * RB_X, yt * RB_R, r);
+          tma_store_commit();
+        }
+        out_buf ^= 1;
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+    }
+    if (et == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_rows_encode = nullptr;
+int g_rows_sms = 0;
+int g_rows_max_smem = 0;
+
+int encode_nd(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+              const cuuint32_t* box, const char* what) {
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_rows_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides,
+                             box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r); return AF_ERR_CUDA; }
+  return AF_OK;
+}
+
+}  // namespace
+
+int conv_rows_init() {
+  if (g_rows_encode) return AF_OK;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  AFB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return AF_ERR_UNSUPPORTED; }
+  g_rows_encode = (EncodeTiledFn)fn;
+  int dev = 0;
+  AFB_CUDA(cudaGetDevice(&dev));
+  AFB_CUDA(cudaDeviceGetAttribute(&g_rows_sms, cudaDevAttrMultiProcessorCount, dev));
+  AFB_CUDA(cudaDeviceGetAttribute(&g_rows_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  AFB_CUDA(cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
+  return AF_OK;
+}
+
+bool conv_rows_supported(const ConvProblem& p) {
+  if (!g_rows_encode) return false;
+  if (p.Cout != RB_N || p.Cin % 64 != 0 || p.res != nullptr) return false;
+  if (p.st != 1 || p.sh != 1 || p.sw != 1) return false;
+  if (p.Wo % RB_X != 0 || p.kh < 2 || p.kh > 8) return false;    // needs vertical taps to pay off
+  if (p.xsW != p.Cin || p.xsH != (long long)p.Wi * p.Cin || p.xsT != (long long)p.Hi * p.Wi * p.Cin ||
+      p.xsB != (long long)p.Ti * p.Hi * p.Wi * p.Cin)
+    return false;
+  return true;
+}
+
+int conv_rows_launch(const ConvProblem& p, cudaStream_t s) {
+  RowsParams rp;
+  rp.bias = p.bias; rp.Cin = p.Cin; rp.kt = p.kt; rp.kh = p.kh; rp.kw = p.kw; rp.pt = p.pt; rp.ph = p.ph; rp.pw = p.pw;
+  rp.B = p.B; rp.To = p.To; rp.Ho = p.Ho; rp.Wo = p.Wo; rp.relu = p.relu;
+  rp.x_tiles = p.Wo / RB_X;
+  rp.y_tiles = (p.Ho + RB_R - 1) / RB_R;
+  rp.num_tiles = p.B * p.To * rp.y_tiles * rp.x_tiles;
+  rp.num_units = (rp.num_tiles + RB_G - 1) / RB_G;
+  rp.a_stage_bytes = (RB_R + p.kh - 1) * RB_X * 128;
+  rp.w_buf_bytes = p.kh * RB_N * 128;
+  const int fixed = 2 * rp.w_buf_bytes + 2 * RB_OUT_BYTES + RB_N * 4 + 32 * 8 + 16 + 1024;
+  rp.stages = (g_rows_max_smem - fixed) / rp.a_stage_bytes;
+  if (rp.stages > 8) rp.stages = 8;
+  if (rp.stages < 2) { set_error("conv_rows: not enough shared memory"); return AF_ERR_INVALID; }
+  const int dyn = fixed + rp.stages * rp.a_stage_bytes;
+
+  alignas(64) CUtensorMap ta, tw, ty;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Ti, (cuuint64_t)p.B};
+    cuuint64_t strides[4] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Wi * p.Cin * 2, (cuuint64_t)p.Hi * p.Wi * p.Cin * 2,
+                             (cuuint64_t)p.Ti * p.Hi * p.Wi * p.Cin * 2};
+    cuuint32_t box[5] = {64, RB_X, (cuuint32_t)(RB_R + p.kh - 1), 1, 1};
+    int rc = encode_nd(&ta, p.x, 5, dims, strides, box, "rows A");
+    if (rc) return rc;
+  }
+  {
+    const int taps = p.kt * p.kh * p.kw;
+    cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)taps * p.Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)p.Cin * 2};
+    cuuint32_t box[2] = {64, RB_N};
+    int rc = encode_nd(&tw, p.w, 2, dims, strides, box, "rows W");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.B * p.To};
+    cuuint64_t strides[3] = {(cuuint64_t)p.Cout * 2, (cuuint64_t)p.Wo * p.Cout * 2, (cuuint64_t)p.Ho * p.Wo * p.Cout * 2};
+    cuuint32_t box[4] = {64, RB_X, RB_R, 1};
+    int rc = encode_nd(&ty, p.y, 4, dims, strides, box, "rows Y");
+    if (rc) return rc;
+  }
+  const int grid = rp.num_units < g_rows_sms ? rp.num_units : g_rows_sms;
+  conv_rows_kernel<<<grid, RB_THREADS, dyn, s>>>(ta, tw, ty, rp);
+  ++g_launches;
+  AFB_CUDA(cudaGetLastError());
+  return AF_OK;
+}
+
+}  // namespace afb

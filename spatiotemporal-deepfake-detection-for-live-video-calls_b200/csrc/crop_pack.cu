@@ -161,11 +161,12 @@ __global__ void __launch_bounds__(256) stem_unfold_kernel(const bf16* __restrict
                                                           bf16* __restrict__ U, long long total) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    long long r_ = i;
-    const int j = (int)(r_ & 7); r_ >>= 3;
-    const int xo = (int)(r_ % Wo); r_ /= Wo;
-    const int r = (int)(r_ % Hu); r_ /= Hu;
-    const int t = (int)(r_ % T_); r_ /= T_;
+    // 32-bit decode (total < 2^31 is checked by the launcher): 64-bit div/mod would dominate
+    unsigned r_ = (unsigned)i;
+    const int j = (int)(r_ & 7u); r_ >>= 3;
+    const int xo = (int)(r_ % (unsigned)Wo); r_ /= (unsigned)Wo;
+    const int r = (int)(r_ % (unsigned)Hu); r_ /= (unsigned)Hu;
+    const int t = (int)(r_ % (unsigned)T_); r_ /= (unsigned)T_;
     const bf16* src = clip + r_ * sB + t * sT;
     uint2 px[2];
 #pragma unroll
@@ -214,6 +215,7 @@ int crop_launch(const FrameDesc* frames, const ClipGeom* geom, int B, int T, int
 int stem_unfold_launch(const ClipLayout& clip, int clip0, int B, void* U, cudaStream_t s) {
   const int Wo = clip.S / 2, Hu = clip.S / 2 + 3;
   const long long total = (long long)B * clip.T * Hu * Wo * 8;
+  if (total >= (1LL << 31)) { set_error("stem_unfold: chunk too large"); return AF_ERR_INVALID; }
   const bf16* base = (const bf16*)clip.base + (long long)clip0 * clip.sB;
   stem_unfold_kernel<<<flat_grid(total, 256), 256, 0, s>>>(base, clip.sB, clip.sT, clip.sH, clip.sW, clip.T, Hu, Wo,
                                                            (bf16*)U, total);

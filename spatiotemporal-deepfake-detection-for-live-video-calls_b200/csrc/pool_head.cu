@@ -48,10 +48,10 @@ __global__ void maxpool_spatial_kernel(const T* __restrict__ x, T* __restrict__ 
   const long long total = (long long)BT * Ho * Wo * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    long long r = i;
-    const int c = (int)(r % cv) * V; r /= cv;
-    const int wo = (int)(r % Wo); r /= Wo;
-    const int ho = (int)(r % Ho); r /= Ho;
+    unsigned r = (unsigned)i;              // total < 2^31 checked by the launcher
+    const int c = (int)(r % (unsigned)cv) * V; r /= (unsigned)cv;
+    const int wo = (int)(r % (unsigned)Wo); r /= (unsigned)Wo;
+    const int ho = (int)(r % (unsigned)Ho); r /= (unsigned)Ho;
     const long long bt = r;
     Vec<T> m;
 #pragma unroll
@@ -187,6 +187,7 @@ int maxpool_spatial_launch(const void* x, void* y, int B, int T, int H, int W, i
   const int V = is_bf16 ? 8 : 4;
   if (C % V) { set_error("maxpool_spatial: C=%d not a multiple of %d", C, V); return AF_ERR_INVALID; }
   const long long total = (long long)B * T * Ho * Wo * (C / V);
+  if (total >= (1LL << 31)) { set_error("maxpool_spatial: chunk too large"); return AF_ERR_INVALID; }
   if (is_bf16)
     maxpool_spatial_kernel<bf16><<<flat_grid(total, 256), 256, 0, s>>>((const bf16*)x, (bf16*)y, B * T, H, W, C, Ho, Wo);
   else

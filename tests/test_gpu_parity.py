@@ -115,6 +115,31 @@ def test_conv_kernels_vs_torch_fp32(dev, case, mode):
         assert (got - want).abs().max().item() <= tol
 
 
+ROWS_CASES = [
+    # cin, cout, kernel, pad, B, T, H, W  (stride 1; row-halo tcgen05 kernel, impl=3)
+    (64, 64, (1, 3, 3), (0, 1, 1), 2, 3, 20, 16),      # partial last row tile (20 = 16 + 4)
+    (64, 64, (1, 3, 3), (0, 1, 1), 1, 5, 56, 56),      # s2.b geometry
+    (64, 64, (5, 4, 1), (2, 0, 0), 1, 6, 35, 24),      # unfolded-stem geometry (Ho = 32)
+    (128, 64, (3, 3, 1), (1, 1, 0), 1, 4, 16, 8),      # two channel blocks, temporal + vertical taps
+    (64, 64, (1, 2, 3), (0, 0, 1), 3, 1, 17, 8),       # even kernel height, 11 tiles (odd unit count)
+]
+
+
+@pytest.mark.parametrize("case", ROWS_CASES)
+def test_rows_kernel_vs_torch_fp32(dev, case):
+    cin, cout, k, p, B, T, H, W = case
+    g = torch.Generator().manual_seed(cin + 31 * k[0] + 7 * k[1])
+    x = torch.randn(B, T, H, W, cin, generator=g).to(dev, torch.bfloat16)
+    w = torch.randn(cout, cin, *k, generator=g) * (2.0 / (cin * k[0] * k[1] * k[2])) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    for relu in (True, False):
+        want = _conv_ref(x, w.to(torch.bfloat16).float(), b, (1, 1, 1), p, relu, None)
+        got = afb200.conv_ndhwc(x, w, b, (1, 1, 1), p, relu, None, impl=3).float().cpu()
+        assert got.shape == want.shape
+        tol = 2.0 ** -8 * max(1.0, want.abs().max().item()) + 1e-3
+        assert (got - want).abs().max().item() <= tol
+
+
 def test_umma_and_simt_bf16_agree_closely(dev):
     """Same bf16 inputs, both fp32-accumulating: results may differ only by accumulation
     order, i.e. by at most one bf16 ulp after the final rounding."""
