@@ -27,7 +27,7 @@ namespace {
 constexpr int RB_N = 64;          // output channels per tile (== Cout)
 constexpr int RB_X = 8, RB_R = 16;  // tile: 8 columns x 16 rows = 128 output pixels
 constexpr int RB_G = 4;           // tiles per work unit (accumulators sharing one weight load)
-constexpr int RB_THREADS = 192;
+constexpr int RB_THREADS = 320;   // TMA warp, MMA warp, 2 epilogue warpgroups
 constexpr int RB_OUT_BYTES = 128 * 64 * 2;
 
 struct RowsParams {
@@ -86,7 +86,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
-      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256);
     }
     fence_barrier_init();
   } else if (warp == 1) {
@@ -178,55 +178,53 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..5)
-    const int et = threadIdx.x - 64;
+    // ===================================================== epilogue (warps 2..9): two warpgroups,
+    // alternate tiles of the unit, one output slot each
+    const int eg = (warp - 2) >> 2;
+    const int et = (threadIdx.x - 64) & 127;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    int it = 0, out_buf = 0;
+    uint8_t* sout = smem_out + eg * RB_OUT_BYTES;
+    int it = 0;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int g = 0; g < RB_G; ++g) {
+      for (int g = eg; g < RB_G; g += 2) {
         const int tile = unit * RB_G + g;
         if (tile >= p.num_tiles) break;
         int r = tile;
         const int xt = r % p.x_tiles; r /= p.x_tiles;
         const int yt = r % p.y_tiles; r /= p.y_tiles;   // r = b*To + to
-        uint8_t* sout = smem_out + out_buf * RB_OUT_BYTES;
-        if (et == 0) tma_store_wait_read<1>();
-        epi_bar_sync();
+        if (et == 0) tma_store_wait_read<0>();
+        epi_bar_sync(eg);
+        uint32_t v[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (as * RB_G + g) * RB_N;
+        TMEM_LD_32x32b_x32(taddr, v);
+        TMEM_LD_32x32b_x32(taddr + 32, (v + 32));
+        tmem_ld_wait();
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (as * RB_G + g) * RB_N + half * 32;
-          TMEM_LD_32x32b_x32(taddr, v);
-          tmem_ld_wait();
-          float f[32];
+        for (int q = 0; q < 8; ++q) {
+          float f[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            f[j] = __uint_as_float(v[j]) + bias_s[half * 32 + j];
-            if (p.relu) f[j] = fmaxf(f[j], 0.f);
+          for (int e = 0; e < 8; ++e) {
+            f[e] = __uint_as_float(v[q * 8 + e]) + bias_s[q * 8 + e];
+            if (p.relu) f[e] = fmaxf(f[e], 0.f);
           }
+          uint4 o;
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 t;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&t);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1]);
-            const int j16 = half * 4 + q;
-            *reinterpret_cast<uint4*>(sout + row * 128 + ((j16 ^ (row & 7)) << 4)) = t;
-          }
+          for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+          *reinterpret_cast<uint4*>(sout + row * 128 + ((q ^ (row & 7)) << 4)) = o;
         }
         fence_proxy_async_smem();
-        epi_bar_sync();
+        epi_bar_sync(eg);
         if (et == 0) {
           tma_store_4d(&tm_y, sout, 0, xt * RB_X, yt * RB_R, r);
           tma_store_commit();
         }
-        out_buf ^= 1;
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);

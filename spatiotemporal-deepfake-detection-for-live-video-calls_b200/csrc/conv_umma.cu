@@ -33,8 +33,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;             // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_THREADS = 320;          // TMA warp, MMA warp, 2 epilogue warpgroups
+constexpr int EPI_THREADS = 128;          // per epilogue warpgroup
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 constexpr int OUT_STAGE_BYTES = BLOCK_M * 64 * 2;      // one 64-column output chunk, 16 KiB
 
@@ -56,7 +56,7 @@ template <int BLOCK_N, int STAGES> struct SmemLayout {
   static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
   static constexpr int OFF_RES = OFF_OUT + 2 * OUT_STAGE_BYTES;        // residual tiles (TMA-loaded)
   static constexpr int OFF_BIAS = OFF_RES + 2 * OUT_STAGE_BYTES;
-  static constexpr int OFF_BAR = OFF_BIAS + BLOCK_N * 4;
+  static constexpr int OFF_BAR = OFF_BIAS + 2 * BLOCK_N * 4;   // one bias copy per epilogue group
   static constexpr int NUM_BARS = 2 * STAGES + 6;
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
@@ -92,7 +92,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tma_prefetch_desc(&tm_b);
     tma_prefetch_desc(&tm_y);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_THREADS); mbar_init(&res_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], (BLOCK_N >= 128 ? 2 : 1) * EPI_THREADS); mbar_init(&res_full[i], 1); }
     tma_prefetch_desc(&tm_r);
     fence_barrier_init();
   } else if (warp == 1) {
@@ -170,97 +170,91 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..5)
-    const int et = threadIdx.x - 64;               // 0..127
+    // ===================================================== epilogue (warps 2..9)
+    // Two warpgroups work on alternate 64-column chunks (alternate tiles when BLOCK_N = 64), each
+    // with its own output slot, residual slot, bias copy and named barrier, so one group's TMEM
+    // reads / maths overlap the other's smem writes and TMA stores.
+    const int eg = (warp - 2) >> 2;                // epilogue group 0 / 1
+    const int et = (threadIdx.x - 64) & 127;       // thread within the group
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;              // accumulator row == output pixel within the tile
-    int it = 0;
-    int out_buf = 0;
-    uint32_t res_phase = 0;                        // bit s = parity of the next completion of residual slot s
-    const bool has_res = p.res != nullptr;
     constexpr int CHUNKS = BLOCK_N / 64;
+    const bool has_res = p.res != nullptr;
+    uint8_t* sout = smem_out + eg * OUT_STAGE_BYTES;
+    uint8_t* sres = smem_res + eg * OUT_STAGE_BYTES;
+    float* bias_g = bias_s + eg * BLOCK_N;
+    uint32_t res_phase = 0;
+    int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if (CHUNKS == 1 && (it & 1) != eg) continue;       // whole tiles alternate between the groups
       const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
       const long long m0 = (long long)m_tile * BLOCK_M;
       const int n0 = n_tile * BLOCK_N;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      for (int i = et; i < BLOCK_N; i += EPI_THREADS) bias_s[i] = __ldg(p.bias + n0 + i);
-      // Residual tiles arrive by TMA into their own 2-deep ring, prefetched ahead of the math.
-      // chunk c of a tile uses ring slot (c & 1): CHUNKS is 1, 2 or 4, so slot use is in order.
+      // residual for this group's first chunk of the tile arrives by TMA while the main loop runs
+      const int first_chunk = CHUNKS == 1 ? 0 : eg;
       if (has_res && et == 0) {
-#pragma unroll
-        for (int c = 0; c < (CHUNKS < 2 ? CHUNKS : 2); ++c) {
-          const int slot = CHUNKS == 1 ? (it & 1) : c;
-          mbar_expect_tx(&res_full[slot], OUT_STAGE_BYTES);
-          tma_load_2d(smem_res + slot * OUT_STAGE_BYTES, &tm_r, &res_full[slot], n0 + c * 64, (int)m0);
-        }
+        mbar_expect_tx(&res_full[eg], OUT_STAGE_BYTES);
+        tma_load_2d(sres, &tm_r, &res_full[eg], n0 + first_chunk * 64, (int)m0);
       }
+      epi_bar_sync(eg);                            // previous tile's bias reads are finished
+      for (int i = et; i < BLOCK_N; i += EPI_THREADS) bias_g[i] = __ldg(p.bias + n0 + i);
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int chunk = 0; chunk < CHUNKS; ++chunk) {
-        uint8_t* sout = smem_out + out_buf * OUT_STAGE_BYTES;
-        const int slot = CHUNKS == 1 ? (it & 1) : (chunk & 1);
-        const uint8_t* sres = smem_res + slot * OUT_STAGE_BYTES;
-        if (et == 0) tma_store_wait_read<1>();     // the store that last read this buffer is done
-        epi_bar_sync();                            // (also publishes bias_s)
+      for (int chunk = first_chunk; chunk < CHUNKS; chunk += (CHUNKS == 1 ? 1 : 2)) {
+        if (et == 0) tma_store_wait_read<0>();     // this group's previous store has drained its slot
+        epi_bar_sync(eg);                          // (also publishes bias_g)
+        uint32_t v[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BLOCK_N + chunk * 64;
+        TMEM_LD_32x32b_x32(taddr, v);
+        TMEM_LD_32x32b_x32(taddr + 32, (v + 32));
         if (has_res) {
-          mbar_wait(&res_full[slot], (res_phase >> slot) & 1u);
-          res_phase ^= 1u << slot;
+          mbar_wait(&res_full[eg], res_phase);
+          res_phase ^= 1u;
         }
+        tmem_ld_wait();
+        if (chunk + (CHUNKS == 1 ? 1 : 2) >= CHUNKS) {   // last TMEM read of this accumulator by this group
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[as]);
+        }
+        const int cbase = chunk * 64;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BLOCK_N + chunk * 64 + half * 32;
-          TMEM_LD_32x32b_x32(taddr, v);
-          tmem_ld_wait();
-          const int cbase = chunk * 64 + half * 32;
-          float f[32];
+        for (int q = 0; q < 8; ++q) {              // 8 x 16 bytes of output per row
+          float f[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_s[cbase + j];
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + bias_g[cbase + q * 8 + e];
+          const int off = row * 128 + ((q ^ (row & 7)) << 4);
           if (has_res) {
+            const uint4 t = *reinterpret_cast<const uint4*>(sres + off);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int j16 = half * 4 + q;
-              const uint4 t = *reinterpret_cast<const uint4*>(sres + row * 128 + ((j16 ^ (row & 7)) << 4));
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                f[q * 8 + 2 * e] += __low2float(h2[e]);
-                f[q * 8 + 2 * e + 1] += __high2float(h2[e]);
-              }
+            for (int e = 0; e < 4; ++e) {
+              f[2 * e] += __low2float(h2[e]);
+              f[2 * e + 1] += __high2float(h2[e]);
             }
           }
           if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
           }
+          uint4 o;
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 t;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&t);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1]);
-            const int j16 = half * 4 + q;          // 16-byte chunk index within the 128-byte row
-            *reinterpret_cast<uint4*>(sout + row * 128 + ((j16 ^ (row & 7)) << 4)) = t;
-          }
-        }
-        if (chunk == CHUNKS - 1) {                 // all TMEM reads of this accumulator are done
-          tc_fence_before();
-          mbar_arrive(&tmem_empty[as]);
+          for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+          *reinterpret_cast<uint4*>(sout + off) = o;
         }
         fence_proxy_async_smem();
-        epi_bar_sync();                            // out tile complete; residual slot fully consumed
+        epi_bar_sync(eg);                          // out tile complete; residual slot fully consumed
         if (et == 0) {
           tma_store_2d(&tm_y, sout, n0 + chunk * 64, (int)m0);
           tma_store_commit();
-          if (has_res && chunk + 2 < CHUNKS) {     // refill the slot just drained
-            mbar_expect_tx(&res_full[slot], OUT_STAGE_BYTES);
-            tma_load_2d(smem_res + slot * OUT_STAGE_BYTES, &tm_r, &res_full[slot], n0 + (chunk + 2) * 64, (int)m0);
+          if (has_res && chunk + 2 < CHUNKS) {     // next chunk of this group in the same tile
+            mbar_expect_tx(&res_full[eg], OUT_STAGE_BYTES);
+            tma_load_2d(sres, &tm_r, &res_full[eg], n0 + (chunk + 2) * 64, (int)m0);
           }
         }
-        out_buf ^= 1;
       }
     }
     if (et == 0) tma_store_wait<0>();
