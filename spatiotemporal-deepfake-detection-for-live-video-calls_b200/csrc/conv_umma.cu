@@ -48,52 +48,69 @@ struct UmmaParams {
   int num_m_tiles, num_n_tiles;
   int relu;
   int im2col;
+  int stages;          // depth of the A/B operand ring
+  int out_per_group;   // output staging slots per epilogue group (1 or 2)
 };
 
-template <int BLOCK_N, int STAGES> struct SmemLayout {
-  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
-  static constexpr int OFF_RES = OFF_OUT + 2 * OUT_STAGE_BYTES;        // residual tiles (TMA-loaded)
-  static constexpr int OFF_BIAS = OFF_RES + 2 * OUT_STAGE_BYTES;
-  static constexpr int OFF_BAR = OFF_BIAS + 2 * BLOCK_N * 4;   // one bias copy per epilogue group
-  static constexpr int NUM_BARS = 2 * STAGES + 6;
-  static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
-  static constexpr int TOTAL = OFF_TMEM + 16;
-  static constexpr int DYN_BYTES = TOTAL + 1024;   // slack for the 1024-byte alignment of the base
+constexpr int MAX_STAGES = 8;
+
+// Walks, in order, the (tile, 64-column chunk) pairs one epilogue group handles: with
+// BLOCK_N >= 128 the two groups take alternate chunks of every tile; with BLOCK_N = 64 they take
+// alternate tiles.
+template <int CHUNKS> struct EpiIter {
+  int tile, it, chunk, num_tiles, stride, eg;
+  __device__ __forceinline__ void init(int first_tile, int grid_stride, int n_tiles, int group) {
+    num_tiles = n_tiles; stride = grid_stride; eg = group;
+    if (CHUNKS == 1) { it = group; tile = first_tile + group * grid_stride; chunk = 0; }
+    else { it = 0; tile = first_tile; chunk = group; }
+  }
+  __device__ __forceinline__ bool valid() const { return tile < num_tiles; }
+  __device__ __forceinline__ bool first_in_tile() const { return CHUNKS == 1 || chunk == eg; }
+  __device__ __forceinline__ bool last_in_tile() const { return CHUNKS == 1 || chunk + 2 >= CHUNKS; }
+  __device__ __forceinline__ void next() {
+    if (CHUNKS == 1) { it += 2; tile += 2 * stride; }
+    else if (chunk + 2 < CHUNKS) { chunk += 2; }
+    else { chunk = eg; ++it; tile += stride; }
+  }
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_r,
                  const UmmaParams p) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int CHUNKS = BLOCK_N / 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_out = smem + L::OFF_OUT;
-  uint8_t* smem_res = smem + L::OFF_RES;
-  float* bias_s = reinterpret_cast<float*>(smem + L::OFF_BIAS);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+  const bool has_res = p.res != nullptr;
+  // carve-up: [operand ring][out slots: 2 groups x out_per_group][residual slots: 2 groups x 2][bias x2][barriers]
+  uint8_t* smem_out = smem + p.stages * STAGE_BYTES;
+  uint8_t* smem_res = smem_out + 2 * p.out_per_group * OUT_STAGE_BYTES;
+  float* bias_s = reinterpret_cast<float*>(smem_res + (has_res ? 4 : 0) * OUT_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + 2 * BLOCK_N);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_full = tmem_empty + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM);
+  uint64_t* res_full = tmem_empty + 2;                 // [4]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int cblocks = p.Cin / BLOCK_K;
   const int num_kb = p.kt * p.kh * p.kw * cblocks;
+  const int stages = p.stages;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     tma_prefetch_desc(&tm_y);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], (BLOCK_N >= 128 ? 2 : 1) * EPI_THREADS); mbar_init(&res_full[i], 1); }
     tma_prefetch_desc(&tm_r);
+    for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], (CHUNKS >= 2 ? 2 : 1) * EPI_THREADS); }
+    for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
   } else if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
@@ -123,9 +140,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int wb = wo * p.sw - p.pw, hb = ho * p.sh - p.ph, tb = to * p.st - p.pt;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           const int tap = kb / cblocks, cb = kb - tap * cblocks;
-          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           if (p.im2col) {
             const int dx = tap % p.kw, q = tap / p.kw, dy = q % p.kh, dt = q / p.kh;
@@ -135,7 +152,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             tma_load_2d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, (int)m0);
           }
           tma_load_2d(sb, &tm_b, &full_bar[stage], cb * BLOCK_K, tap * p.Cout + n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -155,7 +172,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(a_addr);
           const uint64_t bdesc = make_smem_desc(a_addr + A_STAGE_BYTES);
 #pragma unroll
@@ -164,97 +181,101 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[as]);               // accumulator complete -> epilogue
       }
     }
   } else {
     // ===================================================== epilogue (warps 2..9)
-    // Two warpgroups work on alternate 64-column chunks (alternate tiles when BLOCK_N = 64), each
-    // with its own output slot, residual slot, bias copy and named barrier, so one group's TMEM
-    // reads / maths overlap the other's smem writes and TMA stores.
+    // Two warpgroups, each with its own named barrier, bias copy, output slots and two residual
+    // slots.  Residual tiles are TMA-prefetched two chunks ahead (a whole tile ahead for the
+    // usual BLOCK_N = 256), so their HBM latency hides behind the current chunk's work.
     const int eg = (warp - 2) >> 2;                // epilogue group 0 / 1
     const int et = (threadIdx.x - 64) & 127;       // thread within the group
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;              // accumulator row == output pixel within the tile
-    constexpr int CHUNKS = BLOCK_N / 64;
-    const bool has_res = p.res != nullptr;
-    uint8_t* sout = smem_out + eg * OUT_STAGE_BYTES;
-    uint8_t* sres = smem_res + eg * OUT_STAGE_BYTES;
     float* bias_g = bias_s + eg * BLOCK_N;
-    uint32_t res_phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      if (CHUNKS == 1 && (it & 1) != eg) continue;       // whole tiles alternate between the groups
-      const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
-      const long long m0 = (long long)m_tile * BLOCK_M;
-      const int n0 = n_tile * BLOCK_N;
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      // residual for this group's first chunk of the tile arrives by TMA while the main loop runs
-      const int first_chunk = CHUNKS == 1 ? 0 : eg;
-      if (has_res && et == 0) {
-        mbar_expect_tx(&res_full[eg], OUT_STAGE_BYTES);
-        tma_load_2d(sres, &tm_r, &res_full[eg], n0 + first_chunk * 64, (int)m0);
-      }
-      epi_bar_sync(eg);                            // previous tile's bias reads are finished
-      for (int i = et; i < BLOCK_N; i += EPI_THREADS) bias_g[i] = __ldg(p.bias + n0 + i);
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
+    uint8_t* out_g = smem_out + eg * p.out_per_group * OUT_STAGE_BYTES;
+    uint8_t* res_g = smem_res + eg * 2 * OUT_STAGE_BYTES;
+    uint64_t* res_bar = res_full + eg * 2;
+
+    EpiIter<CHUNKS> cur, pre;
+    cur.init(blockIdx.x, gridDim.x, num_tiles, eg);
+    pre = cur;
+    auto issue_res = [&](const EpiIter<CHUNKS>& w, int slot) {
+      const int m_tile = w.tile / p.num_n_tiles, n_tile = w.tile - m_tile * p.num_n_tiles;
+      mbar_expect_tx(&res_bar[slot], OUT_STAGE_BYTES);
+      tma_load_2d(res_g + slot * OUT_STAGE_BYTES, &tm_r, &res_bar[slot], n_tile * BLOCK_N + w.chunk * 64, m_tile * BLOCK_M);
+    };
+    if (has_res && et == 0) {
+      for (int j = 0; j < 2; ++j)
+        if (pre.valid()) { issue_res(pre, j); pre.next(); }
+    }
+    int n0 = 0;
+    long long m0 = 0;
+    int as = 0;
 #pragma unroll 1
-      for (int chunk = first_chunk; chunk < CHUNKS; chunk += (CHUNKS == 1 ? 1 : 2)) {
-        if (et == 0) tma_store_wait_read<0>();     // this group's previous store has drained its slot
-        epi_bar_sync(eg);                          // (also publishes bias_g)
-        uint32_t v[64];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BLOCK_N + chunk * 64;
-        TMEM_LD_32x32b_x32(taddr, v);
-        TMEM_LD_32x32b_x32(taddr + 32, (v + 32));
+    for (uint32_t k = 0; cur.valid(); cur.next(), ++k) {
+      const int slot = k & 1;
+      uint8_t* sout = out_g + (p.out_per_group == 2 ? slot : 0) * OUT_STAGE_BYTES;
+      const uint8_t* sres = res_g + slot * OUT_STAGE_BYTES;
+      if (cur.first_in_tile()) {
+        const int m_tile = cur.tile / p.num_n_tiles, n_tile = cur.tile - m_tile * p.num_n_tiles;
+        m0 = (long long)m_tile * BLOCK_M;
+        n0 = n_tile * BLOCK_N;
+        as = cur.it & 1;
+        // safe to overwrite bias_g: every thread passed the closing barrier of the previous chunk
+        for (int i = et; i < BLOCK_N; i += EPI_THREADS) bias_g[i] = __ldg(p.bias + n0 + i);
+        mbar_wait(&tmem_full[as], (cur.it >> 1) & 1);
+        tc_fence_after();
+      }
+      if (et == 0) {                               // the store that last read this out slot has drained it
+        if (p.out_per_group == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+      }
+      epi_bar_sync(eg);                            // (also publishes bias_g)
+      uint32_t v[64];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BLOCK_N + cur.chunk * 64;
+      TMEM_LD_32x32b_x32(taddr, v);
+      TMEM_LD_32x32b_x32(taddr + 32, (v + 32));
+      if (has_res) mbar_wait(&res_bar[slot], (k >> 1) & 1u);
+      tmem_ld_wait();
+      if (cur.last_in_tile()) {                    // this group's last TMEM read of the accumulator
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[as]);
+      }
+      const int cbase = cur.chunk * 64;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {                // 8 x 16 bytes of output per row
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + bias_g[cbase + q * 8 + e];
+        const int off = row * 128 + ((q ^ (row & 7)) << 4);
         if (has_res) {
-          mbar_wait(&res_full[eg], res_phase);
-          res_phase ^= 1u;
-        }
-        tmem_ld_wait();
-        if (chunk + (CHUNKS == 1 ? 1 : 2) >= CHUNKS) {   // last TMEM read of this accumulator by this group
-          tc_fence_before();
-          mbar_arrive(&tmem_empty[as]);
-        }
-        const int cbase = chunk * 64;
+          const uint4 t = *reinterpret_cast<const uint4*>(sres + off);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {              // 8 x 16 bytes of output per row
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + bias_g[cbase + q * 8 + e];
-          const int off = row * 128 + ((q ^ (row & 7)) << 4);
-          if (has_res) {
-            const uint4 t = *reinterpret_cast<const uint4*>(sres + off);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              f[2 * e] += __low2float(h2[e]);
-              f[2 * e + 1] += __high2float(h2[e]);
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-          }
-          uint4 o;
-          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-          *reinterpret_cast<uint4*>(sout + off) = o;
-        }
-        fence_proxy_async_smem();
-        epi_bar_sync(eg);                          // out tile complete; residual slot fully consumed
-        if (et == 0) {
-          tma_store_2d(&tm_y, sout, n0 + chunk * 64, (int)m0);
-          tma_store_commit();
-          if (has_res && chunk + 2 < CHUNKS) {     // next chunk of this group in the same tile
-            mbar_expect_tx(&res_full[eg], OUT_STAGE_BYTES);
-            tma_load_2d(sres, &tm_r, &res_full[eg], n0 + (chunk + 2) * 64, (int)m0);
+          for (int e = 0; e < 4; ++e) {
+            f[2 * e] += __low2float(h2[e]);
+            f[2 * e + 1] += __high2float(h2[e]);
           }
         }
+        if (p.relu) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+        }
+        uint4 o;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+        *reinterpret_cast<uint4*>(sout + off) = o;
+      }
+      fence_proxy_async_smem();
+      epi_bar_sync(eg);                            // out tile complete; residual slot fully consumed
+      if (et == 0) {
+        tma_store_2d(&tm_y, sout, n0 + cbase, (int)m0);
+        tma_store_commit();
+        if (has_res && pre.valid()) { issue_res(pre, slot); pre.next(); }   // refill the slot just drained
       }
     }
     if (et == 0) tma_store_wait<0>();
@@ -283,19 +304,31 @@ int g_num_sms = 0;
 int g_driver_version = 0;
 bool g_corner_dhw = false;    // AFB200_IM2COL_CORNERS=dhw flips the corner array order (bring-up knob)
 
-template <int BLOCK_N, int STAGES>
+int g_max_smem = 0;
+
+template <int BLOCK_N>
 int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const CUtensorMap& tr,
-             const UmmaParams& up, cudaStream_t s) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+             UmmaParams up, cudaStream_t s) {
   static bool configured = false;
-  auto kern = conv_umma_kernel<BLOCK_N, STAGES>;
+  auto kern = conv_umma_kernel<BLOCK_N>;
   if (!configured) {
-    AFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    AFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     configured = true;
   }
+  // shared-memory budget: residual layers trade operand stages for 4 residual + 4 output slots
+  const int stage_bytes = A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2;
+  const bool has_res = up.res != nullptr;
+  up.out_per_group = BLOCK_N <= 128 ? 2 : 1;
+  const int fixed = (2 * up.out_per_group + (has_res ? 4 : 0)) * OUT_STAGE_BYTES + 2 * BLOCK_N * 4 +
+                    (2 * MAX_STAGES + 8) * 8 + 16 + 1024;
+  int stages = (g_max_smem - fixed) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) { set_error("conv_umma: shared memory budget too small"); return AF_ERR_INVALID; }
+  up.stages = stages;
+  const int dyn = fixed + stages * stage_bytes;
   const int tiles = up.num_m_tiles * up.num_n_tiles;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, NUM_THREADS, L::DYN_BYTES, s>>>(ta, tb, ty, tr, up);
+  kern<<<grid, NUM_THREADS, dyn, s>>>(ta, tb, ty, tr, up);
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;
@@ -334,6 +367,7 @@ int conv_umma_init() {
   AFB_CUDA(cudaGetDevice(&dev));
   AFB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   AFB_CUDA(cudaDriverGetVersion(&g_driver_version));
+  AFB_CUDA(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const char* c = getenv("AFB200_IM2COL_CORNERS");
   g_corner_dhw = c && c[0] == 'd';
   return AF_OK;
@@ -405,9 +439,9 @@ int conv_umma_launch(const ConvProblem& p, cudaStream_t s) {
   if (rc) return rc;
 
   switch (bn) {
-    case 256: return launch_t<256, 3>(ta, tb, ty, tr, up, s);
-    case 128: return launch_t<128, 4>(ta, tb, ty, tr, up, s);
-    default: return launch_t<64, 6>(ta, tb, ty, tr, up, s);
+    case 256: return launch_t<256>(ta, tb, ty, tr, up, s);
+    case 128: return launch_t<128>(ta, tb, ty, tr, up, s);
+    default: return launch_t<64>(ta, tb, ty, tr, up, s);
   }
 }
 
