@@ -96,7 +96,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint64_t* res_full = tmem_empty + 2;                 // [4]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle so the compiler knows it is warp-uniform (keeps the role loops'
+  // address arithmetic in uniform registers: tcgen05/TMA operands must be uniform)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int cblocks = p.Cin / BLOCK_K;
   const int num_kb = p.kt * p.kh * p.kw * cblocks;
@@ -121,7 +123,58 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (all lanes walk the loop,
+    // one elected lane issues; see the MMA warp for why)
+    {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+        const int m0 = m_tile * BLOCK_M;
+        const int n0 = n_tile * BLOCK_N;
+        int r = m0;
+        const int wo = r % p.Wo; r /= p.Wo;
+        const int ho = r % p.Ho; r /= p.Ho;
+        const int to = r % p.To; r /= p.To;
+        const int b = r;
+        const int wb = wo * p.sw - p.pw, hb = ho * p.sh - p.ph, tb = to * p.st - p.pt;
+        int tap = 0, cb = 0, dx = 0, dy = 0, dt = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if (p.im2col) {
+              tma_load_im2col_5d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, wb, hb, tb, b, (uint16_t)dx, (uint16_t)dy,
+                                 (uint16_t)dt);
+            } else {
+              tma_load_2d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, m0);
+            }
+            tma_load_2d(sb, &tm_b, &full_bar[stage], cb * BLOCK_K, tap * p.Cout + n0);
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+          if (++cb == cblocks) {                 // next filter tap (dx fastest, then dy, then dt)
+            cb = 0; ++tap;
+            if (++dx == p.kw) { dx = 0; if (++dy == p.kh) { dy = 0; ++dt; } }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -158,7 +211,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    // All 32 lanes walk the loop (uniform control flow, operands in uniform registers); lane 0
+    // alone issues the tcgen05 instructions.
+    {
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
@@ -175,15 +230,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(a_addr);
           const uint64_t bdesc = make_smem_desc(a_addr + A_STAGE_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the >>4 address field
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the >>4 address field
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);        // frees the smem slot when these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);               // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else {
