@@ -143,55 +143,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                 "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + RB_N) bias_s[threadIdx.x - 64] = __ldg(p.bias + threadIdx.x - 64);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
-
-  if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t wcount = 0;                 // weight-buffer uses so far
-      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-        for (int ph = 0; ph < num_phases; ++ph) {
-          // phase -> (channel block, dt, dx)
-          const int dx = ph % p.kw, q = ph / p.kw, dt = q % p.kt, cb = q / p.kt;
-          const int wb = wcount & 1;
-          mbar_wait(&w_empty[wb], ((wcount >> 1) & 1) ^ 1);
-          mbar_expect_tx(&w_full[wb], p.w_buf_bytes);
-          for (int dy = 0; dy < p.kh; ++dy) {
-            const int tap = (dt * p.kh + dy) * p.kw + dx;
-            tma_load_2d(smem_w + wb * p.w_buf_bytes + dy * (RB_N * 128), &tm_w, &w_full[wb], cb * 64, tap * RB_N);
-          }
-          ++wcount;
-          for (int g = 0; g < RB_G; ++g) {
-            const int tile = unit * RB_G + g;
-            if (tile >= p.num_tiles) break;
-            int r = tile;
-            const int xt = r % p.x_tiles; r /= p.x_tiles;
-            const int yt = r % p.y_tiles; r /= p.y_tiles;
-            const int to = r % p.To;
-            const int b = r / p.To;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], p.a_stage_bytes);
-            tma_load_tile_5d(smem_a + stage * p.a_stage_bytes, &tm_a, &full_bar[stage], cb * 64,
-                             xt * RB_X + dx - p.pw, yt * RB_R - p.ph, to + dt - p.pt, b);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
     // ===================================================== MMA issuer (all lanes walk the loop so the
-    // operands stay warp-uniform; lane 0 issues)
+    // operands stay warp-uniform; one elected lane issues)
     {
       constexpr uint32_t idesc = make_idesc(RB_N);
       int stage = 0;

@@ -166,53 +166,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                 "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
-
-  if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
-        const long long m0 = (long long)m_tile * BLOCK_M;
-        const int n0 = n_tile * BLOCK_N;
-        long long r = m0;
-        const int wo = (int)(r % p.Wo); r /= p.Wo;
-        const int ho = (int)(r % p.Ho); r /= p.Ho;
-        const int to = (int)(r % p.To); r /= p.To;
-        const int b = (int)r;
-        const int wb = wo * p.sw - p.pw, hb = ho * p.sh - p.ph, tb = to * p.st - p.pt;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          const int tap = kb / cblocks, cb = kb - tap * cblocks;
-          uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_STAGE_BYTES;
-          if (p.im2col) {
-            const int dx = tap % p.kw, q = tap / p.kw, dy = q % p.kh, dt = q / p.kh;
-            tma_load_im2col_5d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, wb, hb, tb, b, (uint16_t)dx, (uint16_t)dy,
-                               (uint16_t)dt);
-          } else {
-            tma_load_2d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, (int)m0);
-          }
-          tma_load_2d(sb, &tm_b, &full_bar[stage], cb * BLOCK_K, tap * p.Cout + n0);
-          if (++stage == stages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
     // ===================================================== MMA issuer
-    // All 32 lanes walk the loop (uniform control flow, operands in uniform registers); lane 0
-    // alone issues the tcgen05 instructions.
+    // All 32 lanes walk the loop (uniform control flow, operands in uniform registers); one
+    // elected lane issues the tcgen05 instructions.
     {
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
       int stage = 0;
