@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -169,6 +170,8 @@ struct af_engine {
   void* gbuf = nullptr;      // group input of the back part [cb_back, ...]
   float* feat_ws = nullptr;  // [max_batch, feat_dim]
   uint8_t* u8_stage = nullptr;
+  cudaStream_t copy_stream = nullptr;          // H2D of host clips, overlapped with the trunk
+  std::vector<cudaEvent_t> copy_events;
   float* out_stage = nullptr;  // [2*max_batch] logits, scores (device staging for *_host calls)
   // event-based conv timing (option profile_events)
   bool profile_events = false;
@@ -186,7 +189,7 @@ namespace afb {
 
 static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, long long xsB, long long xsT,
                     long long xsH, long long xsW, int B, const void* res, void* y, bool relu, cudaStream_t s,
-                    int impl_override = -1) {
+                    int impl_override = -1, int pool_hw = 0) {
   ConvProblem p;
   p.x = x; p.bias = L.bias; p.res = res; p.y = y;
   p.B = B; p.Ti = in.T; p.Hi = in.H; p.Wi = in.W; p.Cin = L.cin_p;
@@ -197,6 +200,7 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
   p.pt = L.pt; p.ph = L.ph; p.pw = L.pw;
   p.relu = relu ? 1 : 0;
   p.M = (long long)B * o.T * o.H * o.W;
+  p.pool_hw = pool_hw;
   const bool is_bf16 = e ? e->is_bf16 : (L.w_umma != nullptr);
   const int impl = impl_override >= 0 ? impl_override : (e ? e->conv_impl : 0);
   OpTrace tr(s);
@@ -214,6 +218,10 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
     cudaEventRecord(ev0, s);
   }
   p.w = L.w_umma;
+  if (pool_hw && !(is_bf16 && (impl == 0 || impl == 3) && conv_rows_supported(p))) {
+    set_error("fused max-pool needs the row-halo tcgen05 kernel");
+    return AF_ERR_INVALID;
+  }
   if (is_bf16 && (impl == 0 || impl == 3) && conv_rows_supported(p)) {
     rc = conv_rows_launch(p, s);
     which = "urows";
@@ -306,8 +314,30 @@ static int run_blocks(af_engine* e, int b_begin, int b_end, const void*& x, Dims
   return AF_OK;
 }
 
-// The trunk on clips [0,B) already packed in e->clip.
-static int run_trunk(af_engine* e, int B, float* logits, float* scores, float* features, cudaStream_t s) {
+// Fills the engine's clip buffer for clips [f0, f0+fB) right before the trunk consumes them, so the
+// packed chunk is still L2-resident when the stem reads it and host copies overlap earlier chunks.
+typedef std::function<int(int f0, int fB, cudaStream_t s)> Feeder;
+
+static ClipLayout clip_at(const af_engine* e, int f0) {
+  ClipLayout c = e->clip;
+  c.base = (char*)e->clip.base + (long long)f0 * e->clip.sB * (long long)e->esz;
+  return c;
+}
+
+// (f0, fB) of every front chunk in the order run_trunk visits them
+static std::vector<std::pair<int, int>> front_chunks(const af_engine* e, int B) {
+  std::vector<std::pair<int, int>> v;
+  for (int g0 = 0; g0 < B; g0 += e->cb_back) {
+    const int gB = (B - g0) < e->cb_back ? (B - g0) : e->cb_back;
+    for (int f0 = g0; f0 < g0 + gB; f0 += e->cb_front)
+      v.push_back({f0, (g0 + gB - f0) < e->cb_front ? (g0 + gB - f0) : e->cb_front});
+  }
+  return v;
+}
+
+// The trunk on clips [0,B); `feed` packs each front chunk into e->clip just in time.
+static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, float* scores, float* features,
+                     cudaStream_t s) {
   const ConvLayer& stem = e->convs[e->stem];
   const Dims din = {e->T, e->S, e->S, stem.cin_p};
   const Dims dpre = conv_out(stem, din);
@@ -322,7 +352,9 @@ static int run_trunk(af_engine* e, int B, float* logits, float* scores, float* f
     for (int f0 = g0; f0 < g0 + gB; f0 += e->cb_front) {
       const int fB = (g0 + gB - f0) < e->cb_front ? (g0 + gB - f0) : e->cb_front;
       const char* xin = (const char*)e->clip.base + (long long)f0 * e->clip.sB * e->esz;
-      int rc;
+      int rc = feed(f0, fB, s);
+      if (rc) return rc;
+      bool fused_pool = false;
       if (e->has_stem_u && e->conv_impl != 1) {
         OpTrace tr(s);
         rc = stem_unfold_launch(e->clip, f0, fB, e->fbuf[2], s);
@@ -330,12 +362,19 @@ static int run_trunk(af_engine* e, int B, float* logits, float* scores, float* f
         const Dims du = {e->T, e->S / 2 + 3, e->S / 2, 64};
         tr.done("stem unfold", 0.0, (double)fB * (du.elems() + (double)e->T * e->S * e->S * 4) * 2.0);
         const long long sW = 64, sH = (long long)du.W * 64, sT = sH * du.H, sB = sT * du.T;
-        rc = run_conv(e, e->stem_u, e->fbuf[2], du, sB, sT, sH, sW, fB, nullptr, e->fbuf[0], true, s);
+        static const bool no_fuse = getenv("AFB200_NO_FUSED_POOL") != nullptr;
+        fused_pool = e->conv_impl == 0 && !no_fuse && (dpre.H % 2 == 0) && (dpre.W % 2 == 0);
+        if (fused_pool) {
+          AFB_CUDA(cudaMemsetAsync(e->fbuf[1], 0, (size_t)fB * dpool.elems() * e->esz, s));
+          rc = run_conv(e, e->stem_u, e->fbuf[2], du, sB, sT, sH, sW, fB, nullptr, e->fbuf[1], true, s, -1, 1);
+        } else {
+          rc = run_conv(e, e->stem_u, e->fbuf[2], du, sB, sT, sH, sW, fB, nullptr, e->fbuf[0], true, s);
+        }
       } else {
         rc = run_conv(e, stem, xin, din, e->clip.sB, e->clip.sT, e->clip.sH, e->clip.sW, fB, nullptr, e->fbuf[0], true, s);
       }
       if (rc) return rc;
-      {
+      if (!fused_pool) {
         OpTrace tr(s);
         rc = maxpool_spatial_launch(e->fbuf[0], e->fbuf[1], fB, dpre.T, dpre.H, dpre.W, dpre.C, e->is_bf16, s);
         if (rc) return rc;
@@ -441,6 +480,8 @@ af_status af_destroy(af_handle h) {
   if (h->clip_raw) cudaFree(h->clip_raw);
   if (h->feat_ws) cudaFree(h->feat_ws);
   if (h->u8_stage) cudaFree(h->u8_stage);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (auto ev : h->copy_events) cudaEventDestroy(ev);
   if (h->out_stage) cudaFree(h->out_stage);
   for (int i = 0; i < 5; ++i)
     if (h->stage_buf[i]) cudaFree(h->stage_buf[i]);
@@ -594,8 +635,13 @@ af_status af_forward(af_handle h, const void* clip_dev, int32_t dtype, const int
   AFB_CUDA(cudaSetDevice(h->device));
   const long long before = g_launches;
   long long q[5] = {strides[0], strides[1], strides[2], strides[3], strides[4]};
-  int r = pack_clip_launch(clip_dev, dtype, q, batch, h->clip, s);
-  if (!r) r = run_trunk(h, batch, logits_dev, nullptr, features_dev, s);
+  const size_t elt = dtype == AF_F32 ? 4 : 2;
+  Feeder feed = [&](int f0, int fB, cudaStream_t st) {
+    return pack_clip_launch((const char*)clip_dev + (long long)f0 * q[0] * (long long)elt, dtype, q, fB, clip_at(h, f0), st);
+  };
+  int r = (dtype == AF_F32 || dtype == AF_BF16 || dtype == AF_F16) ? AF_OK : AF_ERR_INVALID;
+  if (r) set_error("af_forward: unsupported clip dtype %d", dtype);
+  if (!r) r = run_trunk(h, batch, feed, logits_dev, nullptr, features_dev, s);
   h->launches += g_launches - before;
   return (af_status)r;
 }
@@ -609,8 +655,11 @@ af_status af_infer_u8(af_handle h, const uint8_t* clips_dev, int32_t batch, cons
   cudaStream_t s = (cudaStream_t)stream;
   AFB_CUDA(cudaSetDevice(h->device));
   const long long before = g_launches;
-  int r = pack_u8_launch(clips_dev, batch, mean255, std255, h->clip, s);
-  if (!r) r = run_trunk(h, batch, logits_dev, scores_dev, features_dev, s);
+  const size_t clip_bytes = (size_t)h->T * h->S * h->S * 3;
+  Feeder feed = [&](int f0, int fB, cudaStream_t st) {
+    return pack_u8_launch(clips_dev + (size_t)f0 * clip_bytes, fB, mean255, std255, clip_at(h, f0), st);
+  };
+  int r = run_trunk(h, batch, feed, logits_dev, scores_dev, features_dev, s);
   h->launches += g_launches - before;
   return (af_status)r;
 }
@@ -619,14 +668,39 @@ af_status af_infer_u8_host(af_handle h, const uint8_t* clips_host, int32_t batch
                            const float std255[3], float* logits_host, float* scores_host, void* stream) {
   af_status rc = check_batch(h, batch, "af_infer_u8_host");
   if (rc) return rc;
-  if (!clips_host) { set_error("af_infer_u8_host: null pointer"); return AF_ERR_INVALID; }
+  if (!clips_host || !mean255 || !std255) { set_error("af_infer_u8_host: null pointer"); return AF_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
   AFB_CUDA(cudaSetDevice(h->device));
   const size_t clip_bytes = (size_t)h->T * h->S * h->S * 3;
   if (!h->u8_stage) AFB_CUDA(cudaMalloc(&h->u8_stage, (size_t)h->max_batch * clip_bytes));
-  AFB_CUDA(cudaMemcpyAsync(h->u8_stage, clips_host, (size_t)batch * clip_bytes, cudaMemcpyHostToDevice, s));
-  rc = af_infer_u8(h, h->u8_stage, batch, mean255, std255, h->out_stage, h->out_stage + h->max_batch, nullptr, stream);
-  if (rc) return rc;
+  if (!h->copy_stream) AFB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  // H2D chunk by chunk on a side stream; the trunk waits per chunk, so copies hide behind compute
+  const auto chunks = front_chunks(h, batch);
+  while (h->copy_events.size() < chunks.size() + 1) {
+    cudaEvent_t ev;
+    AFB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    h->copy_events.push_back(ev);
+  }
+  AFB_CUDA(cudaEventRecord(h->copy_events[chunks.size()], s));          // order after earlier work on s
+  AFB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->copy_events[chunks.size()], 0));
+  for (size_t i = 0; i < chunks.size(); ++i) {
+    AFB_CUDA(cudaMemcpyAsync(h->u8_stage + (size_t)chunks[i].first * clip_bytes, clips_host + (size_t)chunks[i].first * clip_bytes,
+                             (size_t)chunks[i].second * clip_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    AFB_CUDA(cudaEventRecord(h->copy_events[i], h->copy_stream));
+  }
+  {
+    const long long before = g_launches;
+    size_t next = 0;
+    Feeder feed = [&](int f0, int fB, cudaStream_t st) {
+      if (next >= chunks.size() || chunks[next].first != f0) { set_error("internal: chunk order"); return (int)AF_ERR_INVALID; }
+      if (cudaStreamWaitEvent(st, h->copy_events[next], 0) != cudaSuccess) { set_error("cudaStreamWaitEvent failed"); return (int)AF_ERR_CUDA; }
+      ++next;
+      return pack_u8_launch(h->u8_stage + (size_t)f0 * clip_bytes, fB, mean255, std255, clip_at(h, f0), st);
+    };
+    int r = run_trunk(h, batch, feed, h->out_stage, h->out_stage + h->max_batch, nullptr, s);
+    h->launches += g_launches - before;
+    if (r) return (af_status)r;
+  }
   if (logits_host)
     AFB_CUDA(cudaMemcpyAsync(logits_host, h->out_stage, batch * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (scores_host)
@@ -656,9 +730,12 @@ af_status af_crop_infer(af_handle h, const af_frame_desc* frames_dev, const af_c
   cudaStream_t s = (cudaStream_t)stream;
   AFB_CUDA(cudaSetDevice(h->device));
   const long long before = g_launches;
-  int r = crop_launch((const FrameDesc*)frames_dev, (const ClipGeom*)geom_dev, batch, h->T, h->S, bgr, nullptr, &h->clip,
-                      mean255, std255, s);
-  if (!r) r = run_trunk(h, batch, logits_dev, scores_dev, features_dev, s);
+  Feeder feed = [&](int f0, int fB, cudaStream_t st) {
+    const ClipLayout dst = clip_at(h, f0);
+    return crop_launch((const FrameDesc*)frames_dev + (size_t)f0 * h->T, (const ClipGeom*)geom_dev + f0, fB, h->T, h->S, bgr,
+                       nullptr, &dst, mean255, std255, st);
+  };
+  int r = run_trunk(h, batch, feed, logits_dev, scores_dev, features_dev, s);
   h->launches += g_launches - before;
   return (af_status)r;
 }
@@ -678,7 +755,14 @@ af_status af_conv_ndhwc(const void* x_dev, const af_conv_desc* conv_host, const 
   if (!rc) {
     Dims in = {t, hgt, wid, L.cin_p};
     const long long sW = in.C, sH = (long long)in.W * in.C, sT = sH * in.H, sB = sT * in.T;
-    rc = run_conv(nullptr, L, x_dev, in, sB, sT, sH, sW, batch, residual_dev, y_dev, relu != 0, (cudaStream_t)stream, impl);
+    const int pool = impl == 4 ? 1 : 0;
+    if (pool) {
+      const Dims o = conv_out(L, in);
+      rc = cudaMemsetAsync(y_dev, 0, (size_t)batch * o.T * (o.H / 2) * (o.W / 2) * o.C * 2, (cudaStream_t)stream) == cudaSuccess ? 0 : AF_ERR_CUDA;
+    }
+    if (!rc)
+      rc = run_conv(nullptr, L, x_dev, in, sB, sT, sH, sW, batch, residual_dev, y_dev, relu != 0, (cudaStream_t)stream,
+                    pool ? 3 : impl, pool);
     if (!rc && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
       set_error("af_conv_ndhwc: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
       rc = AF_ERR_CUDA;

@@ -39,6 +39,8 @@ struct RowsParams {
   int stages;          // A ring depth
   int a_stage_bytes;   // (16 + kh - 1) * 1024
   int w_buf_bytes;     // kh * 64 * 128
+  int pool;            // fused 3x3/2 max-pool epilogue
+  bf16* pool_out;      // [B*To, Ho/2, Wo/2, 64], zero-initialised by the caller
 };
 
 __device__ __forceinline__ void tma_load_tile_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
@@ -231,11 +233,50 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
           *reinterpret_cast<uint4*>(sout + row * 128 + ((q ^ (row & 7)) << 4)) = o;
         }
-        fence_proxy_async_smem();
-        epi_bar_sync(eg);
-        if (et == 0) {
-          tma_store_4d(&tm_y, sout, 0, xt * RB_X, yt * RB_R, r);
-          tma_store_commit();
+        if (!p.pool) {
+          fence_proxy_async_smem();
+          epi_bar_sync(eg);
+          if (et == 0) {
+            tma_store_4d(&tm_y, sout, 0, xt * RB_X, yt * RB_R, r);
+            tma_store_commit();
+          }
+        } else {
+          // Fused MaxPool3d k[1,3,3] s[1,2,2] p[0,1,1] (stem_helper.py:166-168): the 8x16 conv tile in
+          // smem feeds 5x9 pooled positions.  The 3x7 interior ones are complete and stored plainly;
+          // the border ones are shared with neighbouring tiles and merged with a 16-byte vector
+          // red.max into the zero-initialised output (post-ReLU values are >= 0).
+          epi_bar_sync(eg);
+          const int Hp = p.Ho >> 1, Wp = p.Wo >> 1;
+          const int py0 = yt * (RB_R / 2), px0 = xt * (RB_X / 2);
+          for (int item = et; item < 45 * 8; item += 128) {
+            const int ch = item & 7, pos = item >> 3;
+            const int k = pos / 5, j = pos - k * 5;
+            const int py = py0 + k, px = px0 + j;
+            if (py >= Hp || px >= Wp) continue;
+            const int ly0 = k == 0 ? 0 : 2 * k - 1, ly1 = k == 8 ? 15 : 2 * k + 1;
+            const int lx0 = j == 0 ? 0 : 2 * j - 1, lx1 = j == 4 ? 7 : 2 * j + 1;
+            uint4 m = make_uint4(0u, 0u, 0u, 0u);
+            __nv_bfloat162* m2 = reinterpret_cast<__nv_bfloat162*>(&m);
+            for (int ly = ly0; ly <= ly1; ++ly) {
+              if (yt * RB_R + ly >= p.Ho) break;             // rows past the image hold garbage
+              for (int lx = lx0; lx <= lx1; ++lx) {
+                const int rr = ly * RB_X + lx;
+                const uint4 t = *reinterpret_cast<const uint4*>(sout + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                const __nv_bfloat162* t2 = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) m2[e] = __hmax2(m2[e], t2[e]);
+              }
+            }
+            bf16* dst = p.pool_out + (((long long)r * Hp + py) * Wp + px) * RB_N + ch * 8;
+            const bool interior = k >= 1 && k <= 7 && j >= 1 && j <= 3;
+            if (interior) {
+              *reinterpret_cast<uint4*>(dst) = m;
+            } else {
+              asm volatile("red.global.v4.bf16x2.max.noftz [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(m.x), "r"(m.y), "r"(m.z),
+                           "r"(m.w)
+                           : "memory");
+            }
+          }
         }
       }
       tc_fence_before();
@@ -291,6 +332,7 @@ bool conv_rows_supported(const ConvProblem& p) {
   if (p.Cout != RB_N || p.Cin % 64 != 0 || p.res != nullptr) return false;
   if (p.st != 1 || p.sh != 1 || p.sw != 1) return false;
   if (p.Wo % RB_X != 0 || p.kh < 2 || p.kh > 8) return false;    // needs vertical taps to pay off
+  if (p.pool_hw && (!p.relu || (p.Ho & 1) || (p.Wo & 1))) return false;
   if (p.xsW != p.Cin || p.xsH != (long long)p.Wi * p.Cin || p.xsT != (long long)p.Hi * p.Wi * p.Cin ||
       p.xsB != (long long)p.Ti * p.Hi * p.Wi * p.Cin)
     return false;
@@ -301,6 +343,7 @@ int conv_rows_launch(const ConvProblem& p, cudaStream_t s) {
   RowsParams rp;
   rp.bias = p.bias; rp.Cin = p.Cin; rp.kt = p.kt; rp.kh = p.kh; rp.kw = p.kw; rp.pt = p.pt; rp.ph = p.ph; rp.pw = p.pw;
   rp.B = p.B; rp.To = p.To; rp.Ho = p.Ho; rp.Wo = p.Wo; rp.relu = p.relu;
+  rp.pool = p.pool_hw; rp.pool_out = (bf16*)p.y;
   rp.x_tiles = p.Wo / RB_X;
   rp.y_tiles = (p.Ho + RB_R - 1) / RB_R;
   rp.num_tiles = p.B * p.To * rp.y_tiles * rp.x_tiles;
@@ -331,8 +374,9 @@ int conv_rows_launch(const ConvProblem& p, cudaStream_t s) {
     if (rc) return rc;
   }
   {
-    cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.B * p.To};
-    cuuint64_t strides[3] = {(cuuint64_t)p.Cout * 2, (cuuint64_t)p.Wo * p.Cout * 2, (cuuint64_t)p.Ho * p.Wo * p.Cout * 2};
+    const int yo_w = p.pool_hw ? p.Wo / 2 : p.Wo, yo_h = p.pool_hw ? p.Ho / 2 : p.Ho;   // (map unused in pool mode)
+    cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)yo_w, (cuuint64_t)yo_h, (cuuint64_t)p.B * p.To};
+    cuuint64_t strides[3] = {(cuuint64_t)p.Cout * 2, (cuuint64_t)yo_w * p.Cout * 2, (cuuint64_t)yo_h * yo_w * p.Cout * 2};
     cuuint32_t box[4] = {64, RB_X, RB_R, 1};
     int rc = encode_nd(&ty, p.y, 4, dims, strides, box, "rows Y");
     if (rc) return rc;

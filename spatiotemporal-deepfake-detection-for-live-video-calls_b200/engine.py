@@ -182,6 +182,8 @@ def conv_ndhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride
     d.st, d.sh, d.sw = stride
     d.pt, d.ph, d.pw = pad
     To, Ho, Wo = [(n + 2 * p - k) // s + 1 for n, k, s, p in zip((T, H, W), (kt, kh, kw), stride, pad)]
+    if impl == 4:                       # row-halo kernel with the fused 3x3/2 max-pool epilogue
+        Ho, Wo = Ho // 2, Wo // 2
     y = torch.empty((B, To, Ho, Wo, cout), dtype=x.dtype, device=x.device)
     if residual is not None:
         assert residual.shape == y.shape and residual.dtype == x.dtype and residual.is_contiguous()

@@ -140,6 +140,25 @@ def test_rows_kernel_vs_torch_fp32(dev, case):
         assert (got - want).abs().max().item() <= tol
 
 
+@pytest.mark.parametrize("case", [(64, 64, (5, 4, 1), (2, 0, 0), 1, 4, 35, 24),      # stem geometry, Ho=32 Wo=24
+                                  (64, 64, (1, 3, 3), (0, 1, 1), 2, 2, 24, 16),      # partial row tile (24 = 16 + 8)
+                                  (64, 64, (1, 2, 1), (0, 0, 0), 1, 3, 113, 112)])   # Ho = Wo = 112 like the real stem
+def test_rows_kernel_fused_maxpool(dev, case):
+    """conv + ReLU + MaxPool3d k[1,3,3] s[1,2,2] p[0,1,1] in one kernel (impl=4) vs torch."""
+    cin, cout, k, p, B, T, H, W = case
+    g = torch.Generator().manual_seed(17 + H)
+    x = torch.randn(B, T, H, W, cin, generator=g).to(dev, torch.bfloat16)
+    w = torch.randn(cout, cin, *k, generator=g) * (2.0 / (cin * k[0] * k[1] * k[2])) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    y = F.relu(F.conv3d(x.float().cpu().permute(0, 4, 1, 2, 3), w.to(torch.bfloat16).float(), b, 1, p))
+    y = y.to(torch.bfloat16).float()                     # the kernel pools the bf16-rounded conv output
+    want = F.max_pool3d(y, (1, 3, 3), (1, 2, 2), (0, 1, 1)).permute(0, 2, 3, 4, 1).contiguous()
+    got = afb200.conv_ndhwc(x, w, b, (1, 1, 1), p, True, None, impl=4).float().cpu()
+    assert got.shape == want.shape
+    tol = 2.0 ** -8 * max(1.0, want.abs().max().item()) + 1e-3
+    assert (got - want).abs().max().item() <= tol
+
+
 def test_umma_and_simt_bf16_agree_closely(dev):
     """Same bf16 inputs, both fp32-accumulating: results may differ only by accumulation
     order, i.e. by at most one bf16 ulp after the final rounding."""
