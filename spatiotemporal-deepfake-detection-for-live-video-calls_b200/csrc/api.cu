@@ -153,7 +153,7 @@ struct af_engine {
   float* fc_w = nullptr;
   float fc_b = 0.f;
   int feat_dim = 0;
-  int cb_front = 4, cb_back = 32;   // clips per chunk: stem..s2 / s3..head (tuned on B200)
+  int cb_front = 32, cb_back = 32;  // clips per chunk: stem..s2 / s3..head (tuned on B200)
   int conv_impl = 0;       // 0 auto, 1 force SIMT, 2 force UMMA where supported
   bool keep_stages = false;
   long long launches = 0;
