@@ -61,6 +61,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 __global__ void __launch_bounds__(RB_THREADS, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                  const __grid_constant__ CUtensorMap tm_y, const RowsParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // carve-up: [A ring][W double buffer][out ring x2][bias][barriers][tmem ptr]
@@ -102,6 +103,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  pdl_wait_prior_grid();      // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================================================== TMA producer (all lanes walk, one issues)
@@ -382,7 +384,13 @@ int conv_rows_launch(const ConvProblem& p, cudaStream_t s) {
     if (rc) return rc;
   }
   const int grid = rp.num_units < g_rows_sms ? rp.num_units : g_rows_sms;
-  conv_rows_kernel<<<grid, RB_THREADS, dyn, s>>>(ta, tw, ty, rp);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(RB_THREADS); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_rows_kernel, ta, tw, ty, rp));
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;

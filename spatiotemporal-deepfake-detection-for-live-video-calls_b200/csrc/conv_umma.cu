@@ -82,6 +82,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr int CHUNKS = BLOCK_N / 64;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const bool has_res = p.res != nullptr;
@@ -124,6 +125,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  pdl_wait_prior_grid();      // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================================================== TMA producer (all lanes walk the loop,
@@ -343,7 +345,13 @@ int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty
   const int dyn = fixed + stages * stage_bytes;
   const int tiles = up.num_m_tiles * up.num_n_tiles;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, NUM_THREADS, dyn, s>>>(ta, tb, ty, tr, up);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  AFB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ty, tr, up));
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;
