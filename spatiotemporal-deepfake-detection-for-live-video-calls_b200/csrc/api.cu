@@ -156,6 +156,7 @@ struct af_engine {
   int cb_front = 32, cb_back = 32;  // clips per chunk: stem..s2 / s3..head (tuned on B200)
   int conv_impl = 0;       // 0 auto, 1 force SIMT, 2 force UMMA where supported
   bool keep_stages = false;
+  bool pooled_already = false;   // the previous block's `c` conv already applied the temporal max-pool
   long long launches = 0;
 
   // clip buffer (padded NDHWC4) for max_batch clips
@@ -189,7 +190,7 @@ namespace afb {
 
 static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, long long xsB, long long xsT,
                     long long xsH, long long xsW, int B, const void* res, void* y, bool relu, cudaStream_t s,
-                    int impl_override = -1, int pool_hw = 0) {
+                    int impl_override = -1, int pool_hw = 0, int pool_t = 0) {
   ConvProblem p;
   p.x = x; p.bias = L.bias; p.res = res; p.y = y;
   p.B = B; p.Ti = in.T; p.Hi = in.H; p.Wi = in.W; p.Cin = L.cin_p;
@@ -201,6 +202,7 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
   p.relu = relu ? 1 : 0;
   p.M = (long long)B * o.T * o.H * o.W;
   p.pool_hw = pool_hw;
+  p.pool_t = pool_t;
   const bool is_bf16 = e ? e->is_bf16 : (L.w_umma != nullptr);
   const int impl = impl_override >= 0 ? impl_override : (e ? e->conv_impl : 0);
   OpTrace tr(s);
@@ -222,7 +224,11 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
     set_error("fused max-pool needs the row-halo tcgen05 kernel");
     return AF_ERR_INVALID;
   }
-  if (is_bf16 && (impl == 0 || impl == 3) && conv_rows_supported(p)) {
+  if (pool_t && !(is_bf16 && impl != 1 && impl != 3 && conv_umma_supported(p))) {
+    set_error("fused temporal max-pool needs the pointwise tcgen05 kernel");
+    return AF_ERR_INVALID;
+  }
+  if (!pool_t && is_bf16 && (impl == 0 || impl == 3) && conv_rows_supported(p)) {
     rc = conv_rows_launch(p, s);
     which = "urows";
   } else if (is_bf16 && impl != 1 && impl != 3 && conv_umma_supported(p)) {
@@ -276,7 +282,9 @@ static int run_blocks(af_engine* e, int b_begin, int b_end, const void*& x, Dims
     std::vector<void*> freeb;
     for (int i = 0; i < 5; ++i)
       if (buf[i] != x) freeb.push_back(buf[i]);
-    if (blk.temporal_pool_before) {
+    if (blk.temporal_pool_before && e->pooled_already) {
+      e->pooled_already = false;                 // fused into the producer's epilogue
+    } else if (blk.temporal_pool_before) {
       void* pooled = freeb.back();
       freeb.pop_back();
       OpTrace tr(s);
@@ -301,9 +309,19 @@ static int run_blocks(af_engine* e, int b_begin, int b_end, const void*& x, Dims
     rc = dense_conv(e, blk.b, ya, da, B, nullptr, yb, true, s);
     if (rc) return rc;
     Dims db = conv_out(e->convs[blk.b], da);
-    rc = dense_conv(e, blk.c, yb, db, B, shortcut, yout, true, s);
+    // fuse the next block's temporal max-pool into this `c` conv's epilogue when possible
+    static const bool no_tfuse = getenv("AFB200_NO_FUSED_TPOOL") != nullptr;
+    const ConvLayer& Lc = e->convs[blk.c];
+    const bool fuse_t = e->is_bf16 && e->conv_impl == 0 && !e->keep_stages && !no_tfuse && bi + 1 < (int)e->blocks.size() &&
+                        e->blocks[bi + 1].temporal_pool_before && (db.T % 2 == 0) && ((db.H * db.W) % 64 == 0) &&
+                        Lc.kt == 1 && Lc.kh == 1 && Lc.kw == 1 && Lc.sh == 1 && Lc.sw == 1 && Lc.st == 1;
+    {
+      const long long sW = db.C, sH = (long long)db.W * db.C, sT = sH * db.H, sB = sT * db.T;
+      rc = run_conv(e, Lc, yb, db, sB, sT, sH, sW, B, shortcut, yout, true, s, -1, 0, fuse_t ? 1 : 0);
+    }
     if (rc) return rc;
     d = conv_out(e->convs[blk.c], db);
+    if (fuse_t) { d.T /= 2; e->pooled_already = true; }
     x = yout;
     if (is_stage_end(e, bi)) {
       rc = keep_stage(e, stage_no, x, d, clip0, B, s);
@@ -345,6 +363,7 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
   const int nblk = (int)e->blocks.size();
   const int split = e->split < 0 ? nblk : e->split;
   e->stage_batch = B;
+  e->pooled_already = false;
 
   for (int g0 = 0; g0 < B; g0 += e->cb_back) {
     const int gB = (B - g0) < e->cb_back ? (B - g0) : e->cb_back;
@@ -674,7 +693,13 @@ af_status af_infer_u8_host(af_handle h, const uint8_t* clips_host, int32_t batch
   const size_t clip_bytes = (size_t)h->T * h->S * h->S * 3;
   if (!h->u8_stage) AFB_CUDA(cudaMalloc(&h->u8_stage, (size_t)h->max_batch * clip_bytes));
   if (!h->copy_stream) AFB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-  // H2D chunk by chunk on a side stream; the trunk waits per chunk, so copies hide behind compute
+  // H2D chunk by chunk on a side stream; the trunk waits per chunk, so copies hide behind compute.
+  // Host-fed calls use front chunks of at most 8 clips so that there is something to overlap with.
+  struct ChunkGuard {
+    af_engine* e; int saved;
+    ChunkGuard(af_engine* e_) : e(e_), saved(e_->cb_front) { if (e->cb_front > 8) e->cb_front = 8; }
+    ~ChunkGuard() { e->cb_front = saved; }
+  } chunk_guard(h);
   const auto chunks = front_chunks(h, batch);
   while (h->copy_events.size() < chunks.size() + 1) {
     cudaEvent_t ev;
@@ -756,13 +781,14 @@ af_status af_conv_ndhwc(const void* x_dev, const af_conv_desc* conv_host, const 
     Dims in = {t, hgt, wid, L.cin_p};
     const long long sW = in.C, sH = (long long)in.W * in.C, sT = sH * in.H, sB = sT * in.T;
     const int pool = impl == 4 ? 1 : 0;
+    const int tpool = impl == 5 ? 1 : 0;
     if (pool) {
       const Dims o = conv_out(L, in);
       rc = cudaMemsetAsync(y_dev, 0, (size_t)batch * o.T * (o.H / 2) * (o.W / 2) * o.C * 2, (cudaStream_t)stream) == cudaSuccess ? 0 : AF_ERR_CUDA;
     }
     if (!rc)
       rc = run_conv(nullptr, L, x_dev, in, sB, sT, sH, sW, batch, residual_dev, y_dev, relu != 0, (cudaStream_t)stream,
-                    pool ? 3 : impl, pool);
+                    pool ? 3 : (tpool ? 2 : impl), pool, tpool);
     if (!rc && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
       set_error("af_conv_ndhwc: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
       rc = AF_ERR_CUDA;

@@ -23,6 +23,8 @@ struct ConvProblem {
   int kt, kh, kw, st, sh, sw, pt, ph, pw;
   int relu;
   long long M;         // B*To*Ho*Wo
+  int pool_t = 0;      // conv_umma pointwise only: fuse MaxPool3d k=s=[2,1,1] over frame pairs; y is then
+                       // [B, To/2, Ho, Wo, Cout] (needs relu, To even, Ho*Wo % 64 == 0)
   int pool_hw = 0;     // conv_rows only: fuse MaxPool3d k[1,3,3] s[1,2,2] p[0,1,1]; y is then the
                        // ZERO-INITIALISED pooled tensor [B*To, Ho/2, Wo/2, Cout] (needs relu)
 };

@@ -184,9 +184,11 @@ def conv_ndhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride
     To, Ho, Wo = [(n + 2 * p - k) // s + 1 for n, k, s, p in zip((T, H, W), (kt, kh, kw), stride, pad)]
     if impl == 4:                       # row-halo kernel with the fused 3x3/2 max-pool epilogue
         Ho, Wo = Ho // 2, Wo // 2
+    if impl == 5:                       # pointwise kernel with the fused temporal [2,1,1] max-pool epilogue
+        To = To // 2
     y = torch.empty((B, To, Ho, Wo, cout), dtype=x.dtype, device=x.device)
     if residual is not None:
-        assert residual.shape == y.shape and residual.dtype == x.dtype and residual.is_contiguous()
+        assert residual.dtype == x.dtype and residual.is_contiguous()
     prec = AF_PREC_BF16 if x.dtype == torch.bfloat16 else AF_PREC_FP32
     with torch.cuda.device(x.device):
         check(L.af_conv_ndhwc(C.c_void_p(x.data_ptr()), C.byref(d),

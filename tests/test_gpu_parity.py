@@ -159,6 +159,25 @@ def test_rows_kernel_fused_maxpool(dev, case):
     assert (got - want).abs().max().item() <= tol
 
 
+@pytest.mark.parametrize("case", [(64, 256, 1, 4, 8, 8), (128, 64, 2, 2, 16, 12), (64, 256, 1, 32, 56, 56)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_pointwise_kernel_fused_temporal_maxpool(dev, case, with_res):
+    """1x1x1 conv (+residual) + ReLU + MaxPool3d k=s=[2,1,1] in one kernel (impl=5) vs torch."""
+    cin, cout, B, T, H, W = case
+    g = torch.Generator().manual_seed(3 + cin + T)
+    x = torch.randn(B, T, H, W, cin, generator=g).to(dev, torch.bfloat16)
+    w = torch.randn(cout, cin, 1, 1, 1, generator=g) * (2.0 / cin) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    res = torch.randn(B, T, H, W, cout, generator=g).to(dev, torch.bfloat16) if with_res else None
+    y = _conv_ref(x, w.to(torch.bfloat16).float(), b, (1, 1, 1), (0, 0, 0), True, res)      # NDHWC fp32
+    y = y.to(torch.bfloat16).float().permute(0, 4, 1, 2, 3)
+    want = F.max_pool3d(y, (2, 1, 1), (2, 1, 1)).permute(0, 2, 3, 4, 1).contiguous()
+    got = afb200.conv_ndhwc(x, w, b, (1, 1, 1), (0, 0, 0), True, res, impl=5).float().cpu()
+    assert got.shape == want.shape
+    tol = 2.0 ** -8 * max(1.0, want.abs().max().item()) + 1e-3
+    assert (got - want).abs().max().item() <= tol
+
+
 def test_umma_and_simt_bf16_agree_closely(dev):
     """Same bf16 inputs, both fp32-accumulating: results may differ only by accumulation
     order, i.e. by at most one bf16 ulp after the final rounding."""
@@ -220,6 +239,12 @@ def test_bf16_path_within_tolerance_and_same_decision(dev, state_dict, clips_u8,
     # the launch counter moves: these were our kernels, not a fallback
     assert eng.launch_count >= 60
     eng.close()
+    # production schedule (no kept stages: stem max-pool and temporal max-pool fused into conv epilogues)
+    eng2 = afb200.Engine(sd, max_batch=4, precision="bf16")
+    logits2 = eng2.forward(x.to(dev)).cpu()
+    assert (logits2 - ref).abs().max().item() <= 2e-2
+    assert (logits2 - logits).abs().max().item() <= 5e-3
+    eng2.close()
 
 
 def test_input_layouts_and_dtypes_give_same_logits(dev, state_dict, clips_u8):
