@@ -52,26 +52,38 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
                                                    int bgr, uint8_t* __restrict__ out_u8, T* dst,
                                                    long long sB, long long sT, long long sH,
                                                    long long sW, Norm nrm) {
-  const int x = blockIdx.x * 32 + threadIdx.x;
-  const int y = blockIdx.y * 8 + threadIdx.y;
+  // Per block (32 columns x 8 rows of one frame): the f64 part of OpenCV's coordinate maths is done
+  // once per column (adelta, bdelta) and once per row (X0, Y0) by 40 threads and shared through smem.
+  __shared__ int s_ad[32], s_bd[32], s_x0[8], s_y0[8];
   const int bt = blockIdx.z;
-  if (x >= S || y >= S) return;
   const int b = bt / T_, t = bt - b * T_;
   const ClipGeom g = geom[b];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (tid < 40) {
+    // cv::invertAffineTransform (f64)
+    double D = __dsub_rn(__dmul_rn(g.tfm[0], g.tfm[4]), __dmul_rn(g.tfm[1], g.tfm[3]));
+    D = D != 0.0 ? __ddiv_rn(1.0, D) : 0.0;
+    const double A11 = __dmul_rn(g.tfm[4], D), A22 = __dmul_rn(g.tfm[0], D);
+    const double A12 = __dmul_rn(-g.tfm[1], D), A21 = __dmul_rn(-g.tfm[3], D);
+    if (tid < 32) {
+      const double xx = (double)(blockIdx.x * 32 + tid);
+      s_ad[tid] = cv_round(__dmul_rn(__dmul_rn(A11, xx), 1024.0));
+      s_bd[tid] = cv_round(__dmul_rn(__dmul_rn(A21, xx), 1024.0));
+    } else {
+      const double b1 = __dsub_rn(__dmul_rn(-A11, g.tfm[2]), __dmul_rn(A12, g.tfm[5]));
+      const double b2 = __dsub_rn(__dmul_rn(-A21, g.tfm[2]), __dmul_rn(A22, g.tfm[5]));
+      const double yy = (double)(blockIdx.y * 8 + tid - 32);
+      s_x0[tid - 32] = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(A12, yy), b1), 1024.0)) + 16;
+      s_y0[tid - 32] = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(A22, yy), b2), 1024.0)) + 16;
+    }
+  }
+  __syncthreads();
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= S || y >= S) return;
   const FrameDesc f = frames[bt];
-
-  // cv::invertAffineTransform (f64)
-  double D = __dsub_rn(__dmul_rn(g.tfm[0], g.tfm[4]), __dmul_rn(g.tfm[1], g.tfm[3]));
-  D = D != 0.0 ? __ddiv_rn(1.0, D) : 0.0;
-  const double A11 = __dmul_rn(g.tfm[4], D), A22 = __dmul_rn(g.tfm[0], D);
-  const double A12 = __dmul_rn(-g.tfm[1], D), A21 = __dmul_rn(-g.tfm[3], D);
-  const double b1 = __dsub_rn(__dmul_rn(-A11, g.tfm[2]), __dmul_rn(A12, g.tfm[5]));
-  const double b2 = __dsub_rn(__dmul_rn(-A21, g.tfm[2]), __dmul_rn(A22, g.tfm[5]));
-
-  const int adelta = cv_round(__dmul_rn(__dmul_rn(A11, (double)x), 1024.0));
-  const int bdelta = cv_round(__dmul_rn(__dmul_rn(A21, (double)x), 1024.0));
-  const int X0 = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(A12, (double)y), b1), 1024.0)) + 16;
-  const int Y0 = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(A22, (double)y), b2), 1024.0)) + 16;
+  const int adelta = s_ad[threadIdx.x], bdelta = s_bd[threadIdx.x];
+  const int X0 = s_x0[threadIdx.y], Y0 = s_y0[threadIdx.y];
   const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
   int sx = X >> 5, sy = Y >> 5;
   sx = max(-32768, min(32767, sx));

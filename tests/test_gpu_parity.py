@@ -342,3 +342,32 @@ def test_linearity_property_of_conv_at_full_size(dev):
         afb200.conv_ndhwc(x2, w, z, (1, 1, 1), (0, 1, 1), False, None, impl=2).float()
     scale = b.abs().max().item()
     assert (a - b).abs().max().item() <= 3 * 2.0 ** -8 * scale + 576 * 0.05 * xs_err
+
+
+def test_live_ring_scoring_matches_direct_path(dev, state_dict):
+    """Streaming layer: windows over a device frame ring give the same scores as crop_u8 -> infer_u8."""
+    from afb200 import live
+    H, W = 360, 640
+    eng = afb200.Engine(state_dict, max_batch=4, precision="bf16")
+    ring = live.FrameRing(eng, 48, H, W)
+    scorer = live.LiveScorer(live.make_ring_score_fn(eng, ring), clip_size=32, stride=8)
+    track = synthetic.synthetic_track(5, t=40, h=H, w=W)
+    frames = [torch.from_numpy(synthetic.synthetic_frame_u8(100 + f, H, W)) for f in range(40)]
+    got = []
+    obs = []
+    for f in range(40):
+        box, lm = track[f]
+        big = afb200.get_crop_box((H, W), box, 0.5)
+        slot = ring.put(frames[f])
+        obs.append((slot, big, lm - big[:2][None]))
+        scorer.observe(0, slot, big, lm - big[:2][None])
+        got += scorer.flush()
+    assert [round(x) for x in [len(got)]] == [2]                    # windows end at frames 31 and 39
+    # direct path for the second window (frames 8..39)
+    win = obs[8:40]
+    bigs = np.stack([o[1] for o in win])
+    lt, wh, diff, tfm, trans = afb200.clip_geometry(bigs, [o[2] for o in win], 224)
+    u8 = afb200.crop.crop_u8([frames[f].to(dev) for f in range(8, 40)], bigs, [(tfm, lt, wh)], 32, 224)
+    lg, sc = eng.infer_u8(u8)
+    assert abs(float(sc[0]) - got[1][1]) <= 1e-6
+    eng.close()
