@@ -126,6 +126,22 @@ static int upload_stem_unfolded(const af_conv_desc& d, ConvLayer& L) {
   return AF_OK;
 }
 
+// Direct stem (conv_rows.cu: conv_stem_direct_launch): W35[dt*7+dy][cout][dx*4+c] = W[cout][c][dt][dy][dx].
+static int upload_stem_direct(const af_conv_desc& d, bf16** out) {
+  const size_t n = (size_t)35 * d.cout * 32;
+  std::vector<bf16> w(n, __float2bfloat16_rn(0.f));
+  for (int co = 0; co < d.cout; ++co)
+    for (int c = 0; c < 3; ++c)
+      for (int dt = 0; dt < 5; ++dt)
+        for (int dy = 0; dy < 7; ++dy)
+          for (int dx = 0; dx < 7; ++dx)
+            w[((size_t)(dt * 7 + dy) * d.cout + co) * 32 + dx * 4 + c] =
+                __float2bfloat16_rn(d.weight[((((size_t)co * 3 + c) * 5 + dt) * 7 + dy) * 7 + dx]);
+  AFB_CUDA(cudaMalloc(out, n * sizeof(bf16)));
+  AFB_CUDA(cudaMemcpy(*out, w.data(), n * sizeof(bf16), cudaMemcpyHostToDevice));
+  return AF_OK;
+}
+
 struct Dims { int T, H, W, C; long long elems() const { return (long long)T * H * W * C; } };
 
 static Dims conv_out(const ConvLayer& L, Dims in) {
@@ -148,6 +164,8 @@ struct af_engine {
   std::vector<ConvLayer> convs;
   ConvLayer stem_u;          // unfolded stem (bf16 engine), valid if has_stem_u
   bool has_stem_u = false;
+  bf16* stem_w35 = nullptr;  // direct stem weights [35 (dt,dy)][cout][32 (dx*4+c)] bf16
+  int stem_direct = 0;       // 1 usable, 0 not tried / disabled, -1 tensor-map encode refused
   int stem = 0;
   std::vector<af_block_desc> blocks;
   float* fc_w = nullptr;
@@ -188,6 +206,26 @@ struct af_engine {
 
 namespace afb {
 
+// Brackets one conv launch with CUDA events when option profile_events is on (no synchronisation).
+struct ProfRec {
+  af_engine* e;
+  cudaStream_t s;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  bool on;
+  ProfRec(af_engine* e_, cudaStream_t s_) : e(e_), s(s_), on(e_ && e_->profile_events) {
+    if (!on) return;
+    for (cudaEvent_t* pe : {&e0, &e1}) {
+      if (e->ev_pool.empty()) { cudaEventCreate(pe); } else { *pe = e->ev_pool.back(); e->ev_pool.pop_back(); }
+    }
+    cudaEventRecord(e0, s);
+  }
+  void done(int kind, double flops, double bytes) {
+    if (!on) return;
+    cudaEventRecord(e1, s);
+    e->ev_recs.push_back({e0, e1, kind, flops, bytes});
+  }
+};
+
 static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, long long xsB, long long xsT,
                     long long xsH, long long xsW, int B, const void* res, void* y, bool relu, cudaStream_t s,
                     int impl_override = -1, int pool_hw = 0, int pool_t = 0) {
@@ -211,14 +249,7 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
   const double Kd = (double)L.kt * L.kh * L.kw * L.cin_p;
   const double conv_flops = 2.0 * (double)p.M * L.cout * Kd;
   const double conv_bytes = ((double)B * in.elems() + (double)p.M * L.cout * (res ? 2 : 1) + Kd * L.cout) * (is_bf16 ? 2.0 : 4.0);
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  const bool prof = e && e->profile_events;
-  if (prof) {
-    for (cudaEvent_t* pe : {&ev0, &ev1}) {
-      if (e->ev_pool.empty()) { cudaEventCreate(pe); } else { *pe = e->ev_pool.back(); e->ev_pool.pop_back(); }
-    }
-    cudaEventRecord(ev0, s);
-  }
+  ProfRec prec(e, s);
   p.w = L.w_umma;
   if (pool_hw && !(is_bf16 && (impl == 0 || impl == 3) && conv_rows_supported(p))) {
     set_error("fused max-pool needs the row-halo tcgen05 kernel");
@@ -241,10 +272,7 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
     p.w = L.w_simt;
     rc = conv_simt_launch(p, is_bf16, s);
   }
-  if (prof) {
-    cudaEventRecord(ev1, s);
-    e->ev_recs.push_back({ev0, ev1, which[0] == 'u' ? 0 : 1, conv_flops, conv_bytes});
-  }
+  prec.done(which[0] == 'u' ? 0 : 1, conv_flops, conv_bytes);
   if (OpTrace::enabled()) {
     char nm[128];
     snprintf(nm, sizeof(nm), "conv %s k%dx%dx%d s%d M=%lld N=%d K=%d%s", which, L.kt, L.kh, L.kw, L.sh, p.M, L.cout,
@@ -374,7 +402,29 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
       int rc = feed(f0, fB, s);
       if (rc) return rc;
       bool fused_pool = false;
-      if (e->has_stem_u && e->conv_impl != 1) {
+      bool stem_done = false;
+      if (e->stem_direct == 1 && e->conv_impl == 0 && (dpre.H % 2 == 0) && (dpre.W % 2 == 0)) {
+        // stem conv + BN + ReLU + max-pool in ONE kernel, reading the padded clip directly
+        OpTrace tr(s);
+        AFB_CUDA(cudaMemsetAsync(e->fbuf[1], 0, (size_t)fB * dpool.elems() * e->esz, s));
+        ProfRec prec(e, s);
+        const char* phys = (const char*)e->clip_raw + (long long)f0 * e->clip.sB * (long long)e->esz;
+        rc = conv_stem_direct_launch(phys, fB, e->T, e->S, e->stem_w35, e->stem_u.bias, e->fbuf[1], 1, s);
+        if (rc == AF_ERR_CUDA && strstr(af_last_error(), "cuTensorMapEncodeTiled")) {
+          e->stem_direct = -1;                    // driver refused the overlapping-window map: use the unfolded path
+        } else {
+          if (rc) return rc;
+          stem_done = true;
+          fused_pool = true;
+          // algorithmic stem FLOPs (K = 3*5*7*7 = 735), not the 1120 issued
+          prec.done(0, 2.0 * (double)fB * dpre.elems() * 735.0,
+                    (double)fB * ((double)(e->T + 4) * (e->S + 6) * (e->S + 8) * 4 + dpool.elems()) * 2.0);
+          tr.done("stem direct k5x7x7 s2 +pool (urows)", 2.0 * (double)fB * dpre.elems() * 1120.0,
+                  (double)fB * ((double)(e->T + 4) * (e->S + 6) * (e->S + 8) * 4 + dpool.elems()) * 2.0);
+        }
+      }
+      if (stem_done) {
+      } else if (e->has_stem_u && e->conv_impl != 1) {
         OpTrace tr(s);
         rc = stem_unfold_launch(e->clip, f0, fB, e->fbuf[2], s);
         if (rc) return rc;
@@ -494,6 +544,7 @@ af_status af_destroy(af_handle h) {
   cudaSetDevice(h->device);
   for (auto& L : h->convs) free_layer(L);
   free_layer(h->stem_u);
+  if (h->stem_w35) cudaFree(h->stem_w35);
   free_workspace(h);
   if (h->fc_w) cudaFree(h->fc_w);
   if (h->clip_raw) cudaFree(h->clip_raw);
@@ -532,6 +583,11 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
     int rc = upload_stem_unfolded(w->convs[w->stem], e->stem_u);
     if (rc == AF_OK) e->has_stem_u = true;
     else if (rc != AF_ERR_INVALID) return (af_status)rc;
+    if (e->has_stem_u && e->stem_u.cout == 64 && getenv("AFB200_NO_STEM_DIRECT") == nullptr) {
+      rc = upload_stem_direct(w->convs[w->stem], &e->stem_w35);
+      if (rc) return (af_status)rc;
+      e->stem_direct = 1;
+    }
   }
   e->blocks.assign(w->blocks, w->blocks + w->n_blocks);
   AFB_CUDA(cudaMalloc(&e->fc_w, w->feature_dim * sizeof(float)));

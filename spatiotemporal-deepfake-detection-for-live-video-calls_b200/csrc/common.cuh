@@ -61,6 +61,8 @@ int conv_umma_init();
 bool conv_rows_supported(const ConvProblem& p);
 int conv_rows_launch(const ConvProblem& p, cudaStream_t s);
 int conv_rows_init();
+int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const void* w35, const float* bias, void* y,
+                            int pool, cudaStream_t s);
 // pool_head.cu
 int maxpool_spatial_launch(const void* x, void* y, int B, int T, int H, int W, int C, bool is_bf16,
                            cudaStream_t s);   // k[1,3,3] s[1,2,2] p[0,1,1]

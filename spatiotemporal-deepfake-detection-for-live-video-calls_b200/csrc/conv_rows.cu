@@ -39,6 +39,13 @@ struct RowsParams {
   int stages;          // A ring depth
   int a_stage_bytes;   // (16 + kh - 1) * 1024
   int w_buf_bytes;     // kh * 64 * 128
+  // operand geometry (generic NDHWC-64 mode vs the direct stem mode, see conv_stem_direct_launch)
+  int direct_stem;     // 1: A boxes come straight from the padded NDHWC4 clip (64-byte K rows, SWIZZLE_64B)
+  int ksteps;          // MMAs (K=16) per vertical tap: 4 (64 channels) or 2 (32 = 7 dx x 4 c + pad)
+  int a_tap_bytes;     // descriptor offset between vertical taps: 8 pixels x row bytes
+  int w_tile_bytes;    // one tap's weight tile: 64 x row bytes
+  int sbo_b;           // 8 weight rows
+  int layout;          // UMMA layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
   int pool;            // fused 3x3/2 max-pool epilogue
   bf16* pool_out;      // [B*To, Ho/2, Wo/2, 64], zero-initialised by the caller
 };
@@ -121,7 +128,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             mbar_expect_tx(&w_full[wb], p.w_buf_bytes);
             for (int dy = 0; dy < p.kh; ++dy) {
               const int tap = (dt * p.kh + dy) * p.kw + dx;
-              tma_load_2d(smem_w + wb * p.w_buf_bytes + dy * (RB_N * 128), &tm_w, &w_full[wb], cb * 64, tap * RB_N);
+              tma_load_2d(smem_w + wb * p.w_buf_bytes + dy * p.w_tile_bytes, &tm_w, &w_full[wb], cb * 64, tap * RB_N);
             }
           }
           __syncwarp();
@@ -137,8 +144,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&full_bar[stage], p.a_stage_bytes);
-              tma_load_tile_5d(smem_a + stage * p.a_stage_bytes, &tm_a, &full_bar[stage], cb * 64,
-                               xt * RB_X + dx - p.pw, yt * RB_R - p.ph, to + dt - p.pt, b);
+              if (p.direct_stem)   // physical pads in the clip: output (yo,xo) reads rows 2yo.., pixels 2xo.. of frame to+dt
+                tma_load_tile_5d(smem_a + stage * p.a_stage_bytes, &tm_a, &full_bar[stage], 0, xt * RB_X, 2 * yt * RB_R,
+                                 to + dt, b);
+              else
+                tma_load_tile_5d(smem_a + stage * p.a_stage_bytes, &tm_a, &full_bar[stage], cb * 64,
+                                 xt * RB_X + dx - p.pw, yt * RB_R - p.ph, to + dt - p.pt, b);
             }
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -174,10 +185,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const uint32_t d_tmem = tmem_base + (as * RB_G + g) * RB_N;
             if (elect_one()) {
               for (int dy = 0; dy < p.kh; ++dy) {
-                const uint64_t adesc = make_smem_desc(a_addr + dy * (RB_X * 128));   // next image row: +1 swizzle atom
-                const uint64_t bdesc = make_smem_desc(w_addr + dy * (RB_N * 128));
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
+                // vertical tap dy = the same box viewed one image row (8 pixels) further down
+                const uint64_t adesc = make_smem_desc_ex(a_addr + dy * p.a_tap_bytes, 1024, p.layout);
+                const uint64_t bdesc = make_smem_desc_ex(w_addr + dy * p.w_tile_bytes, p.sbo_b, p.layout);
+                for (int k = 0; k < p.ksteps; ++k)
                   umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ph | dy | k) != 0 ? 1u : 0u);
               }
               umma_commit(&empty_bar[stage]);
@@ -303,10 +314,10 @@ int g_rows_sms = 0;
 int g_rows_max_smem = 0;
 
 int encode_nd(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-              const cuuint32_t* box, const char* what) {
+              const cuuint32_t* box, const char* what, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = g_rows_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides,
-                             box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r); return AF_ERR_CUDA; }
   return AF_OK;
@@ -352,6 +363,7 @@ int conv_rows_launch(const ConvProblem& p, cudaStream_t s) {
   rp.num_units = (rp.num_tiles + RB_G - 1) / RB_G;
   rp.a_stage_bytes = (RB_R + p.kh - 1) * RB_X * 128;
   rp.w_buf_bytes = p.kh * RB_N * 128;
+  rp.direct_stem = 0; rp.ksteps = 4; rp.a_tap_bytes = RB_X * 128; rp.w_tile_bytes = RB_N * 128; rp.sbo_b = 1024; rp.layout = 2;
   const int fixed = 2 * rp.w_buf_bytes + 2 * RB_OUT_BYTES + RB_N * 4 + 32 * 8 + 16 + 1024;
   rp.stages = (g_rows_max_smem - fixed) / rp.a_stage_bytes;
   if (rp.stages > 8) rp.stages = 8;
@@ -381,6 +393,72 @@ int conv_rows_launch(const ConvProblem& p, cudaStream_t s) {
     cuuint64_t strides[3] = {(cuuint64_t)p.Cout * 2, (cuuint64_t)yo_w * p.Cout * 2, (cuuint64_t)yo_h * yo_w * p.Cout * 2};
     cuuint32_t box[4] = {64, RB_X, RB_R, 1};
     int rc = encode_nd(&ty, p.y, 4, dims, strides, box, "rows Y");
+    if (rc) return rc;
+  }
+  const int grid = rp.num_units < g_rows_sms ? rp.num_units : g_rows_sms;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(RB_THREADS); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_rows_kernel, ta, tw, ty, rp));
+  ++g_launches;
+  AFB_CUDA(cudaGetLastError());
+  return AF_OK;
+}
+
+
+// The reference stem, Conv3d(3->64, k[5,7,7], s[1,2,2], p[2,3,3]) (stem_helper.py:156-163), straight from the
+// engine's padded NDHWC4 clip [B, T+4, S+6, S+8, 4] -- no unfolded copy.  For output column xo the 7 dx taps x 4
+// channels of one input row are 28 contiguous bf16 (+4 that meet zero weights) starting at padded pixel 2xo:
+// a tensor map whose xo-stride (16 B) is smaller than its 64-byte inner extent hands TMA exactly those
+// overlapping windows.  GEMM K = 35 (dt,dy) taps x 32; the 7 dy taps are views of one 37-row box (+512 B each),
+// output rows are 2 input rows = 1024 B apart (the descriptor's SBO).  Weights: [35][64][32] bf16.
+// y is the zero-initialised POOLED output (fused MaxPool3d [1,3,3]/[1,2,2]) or the dense conv output.
+int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const void* w35, const float* bias, void* y,
+                            int pool, cudaStream_t s) {
+  if (!g_rows_encode) { set_error("conv_stem_direct: not initialised"); return AF_ERR_INVALID; }
+  const int Ho = S / 2, Wo = S / 2, Tp = T + 4, Hp = S + 6, Wp = S + 8;
+  if ((S & 1) || Wo % RB_X) { set_error("conv_stem_direct: unsupported clip size %d", S); return AF_ERR_INVALID; }
+  RowsParams rp;
+  rp.bias = bias; rp.Cin = 64; rp.kt = 5; rp.kh = 7; rp.kw = 1; rp.pt = 0; rp.ph = 0; rp.pw = 0;
+  rp.B = B; rp.To = T; rp.Ho = Ho; rp.Wo = Wo; rp.relu = 1;
+  rp.x_tiles = Wo / RB_X; rp.y_tiles = (Ho + RB_R - 1) / RB_R;
+  rp.num_tiles = B * T * rp.y_tiles * rp.x_tiles;
+  rp.num_units = (rp.num_tiles + RB_G - 1) / RB_G;
+  const int box_rows = 2 * RB_R + 5;                       // input rows 2*yo0 .. 2*yo0+36
+  rp.a_stage_bytes = ((box_rows * RB_X * 64) + 1023) / 1024 * 1024;
+  rp.w_buf_bytes = 7 * RB_N * 64;
+  rp.direct_stem = 1; rp.ksteps = 2; rp.a_tap_bytes = RB_X * 64; rp.w_tile_bytes = RB_N * 64; rp.sbo_b = 512; rp.layout = 4;
+  rp.pool = pool; rp.pool_out = (bf16*)y;
+  const int fixed = 2 * rp.w_buf_bytes + 2 * RB_OUT_BYTES + RB_N * 4 + 32 * 8 + 16 + 1024;
+  rp.stages = (g_rows_max_smem - fixed) / rp.a_stage_bytes;
+  if (rp.stages > 8) rp.stages = 8;
+  const int dyn = fixed + rp.stages * rp.a_stage_bytes;
+
+  alignas(64) CUtensorMap ta, tw, ty;
+  {
+    const cuuint64_t rowpitch = (cuuint64_t)Wp * 8;
+    cuuint64_t dims[5] = {32, (cuuint64_t)Wo, (cuuint64_t)Hp, (cuuint64_t)Tp, (cuuint64_t)B};
+    cuuint64_t strides[4] = {16, rowpitch, rowpitch * Hp, rowpitch * Hp * Tp};
+    cuuint32_t box[5] = {32, RB_X, (cuuint32_t)box_rows, 1, 1};
+    int rc = encode_nd(&ta, clip_phys, 5, dims, strides, box, "stem-direct A (overlapping windows)", CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {32, (cuuint64_t)35 * RB_N};
+    cuuint64_t strides[1] = {64};
+    cuuint32_t box[2] = {32, RB_N};
+    int rc = encode_nd(&tw, w35, 2, dims, strides, box, "stem-direct W", CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  {
+    const int yo_w = pool ? Wo / 2 : Wo, yo_h = pool ? Ho / 2 : Ho;
+    cuuint64_t dims[4] = {64, (cuuint64_t)yo_w, (cuuint64_t)yo_h, (cuuint64_t)B * T};
+    cuuint64_t strides[3] = {128, (cuuint64_t)yo_w * 128, (cuuint64_t)yo_h * yo_w * 128};
+    cuuint32_t box[4] = {64, RB_X, RB_R, 1};
+    int rc = encode_nd(&ty, y, 4, dims, strides, box, "stem-direct Y");
     if (rc) return rc;
   }
   const int grid = rp.num_units < g_rows_sms ? rp.num_units : g_rows_sms;

@@ -94,6 +94,17 @@ template <int N> __device__ __forceinline__ void tma_store_wait() {
 // 1024 bytes apart). Encoding per the PTX ISA "shared memory descriptor" / CUTLASS
 // cute/arch/mma_sm100_desc.hpp: addr>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+// General form: `sbo` = byte distance between consecutive 8-row groups, `layout` = 2 (SWIZZLE_128B,
+// 128-byte rows) or 4 (SWIZZLE_64B, 64-byte rows).
+__device__ __forceinline__ uint64_t make_smem_desc_ex(uint32_t addr, uint32_t sbo, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
   uint64_t d = 0;
   d |= (uint64_t)((addr & 0x3FFFF) >> 4);
