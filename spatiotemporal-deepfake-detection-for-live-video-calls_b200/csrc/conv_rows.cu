@@ -37,7 +37,8 @@ struct RowsParams {
   int x_tiles, y_tiles, num_tiles, num_units;
   int relu;
   int stages;          // A ring depth
-  int a_stage_bytes;   // (16 + kh - 1) * 1024
+  int a_stage_bytes;   // ring slot size (1024-aligned)
+  int a_tx_bytes;      // bytes one A box actually delivers (mbarrier expect_tx)
   int w_buf_bytes;     // kh * 64 * 128
   // operand geometry (generic NDHWC-64 mode vs the direct stem mode, see conv_stem_direct_launch)
   int direct_stem;     // 1: A boxes come straight from the padded NDHWC4 clip (64-byte K rows, SWIZZLE_64B)
@@ -143,7 +144,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int b = r / p.To;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(&full_bar[stage], p.a_stage_bytes);
+              mbar_expect_tx(&full_bar[stage], p.a_tx_bytes);
               if (p.direct_stem)   // physical pads in the clip: output (yo,xo) reads rows 2yo.., pixels 2xo.. of frame to+dt
                 tma_load_tile_5d(smem_a + stage * p.a_stage_bytes, &tm_a, &full_bar[stage], 0, xt * RB_X, 2 * yt * RB_R,
                                  to + dt, b);
@@ -362,6 +363,7 @@ int conv_rows_launch(const ConvProblem& p, cudaStream_t s) {
   rp.num_tiles = p.B * p.To * rp.y_tiles * rp.x_tiles;
   rp.num_units = (rp.num_tiles + RB_G - 1) / RB_G;
   rp.a_stage_bytes = (RB_R + p.kh - 1) * RB_X * 128;
+  rp.a_tx_bytes = rp.a_stage_bytes;
   rp.w_buf_bytes = p.kh * RB_N * 128;
   rp.direct_stem = 0; rp.ksteps = 4; rp.a_tap_bytes = RB_X * 128; rp.w_tile_bytes = RB_N * 128; rp.sbo_b = 1024; rp.layout = 2;
   const int fixed = 2 * rp.w_buf_bytes + 2 * RB_OUT_BYTES + RB_N * 4 + 32 * 8 + 16 + 1024;
@@ -428,7 +430,8 @@ int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const vo
   rp.num_tiles = B * T * rp.y_tiles * rp.x_tiles;
   rp.num_units = (rp.num_tiles + RB_G - 1) / RB_G;
   const int box_rows = 2 * RB_R + 5;                       // input rows 2*yo0 .. 2*yo0+36
-  rp.a_stage_bytes = ((box_rows * RB_X * 64) + 1023) / 1024 * 1024;
+  rp.a_tx_bytes = box_rows * RB_X * 64;
+  rp.a_stage_bytes = (rp.a_tx_bytes + 1023) / 1024 * 1024;
   rp.w_buf_bytes = 7 * RB_N * 64;
   rp.direct_stem = 1; rp.ksteps = 2; rp.a_tap_bytes = RB_X * 64; rp.w_tile_bytes = RB_N * 64; rp.sbo_b = 512; rp.layout = 4;
   rp.pool = pool; rp.pool_out = (bf16*)y;
