@@ -40,13 +40,6 @@ struct RowsParams {
   int a_stage_bytes;   // ring slot size (1024-aligned)
   int a_tx_bytes;      // bytes one A box actually delivers (mbarrier expect_tx)
   int w_buf_bytes;     // kh * 64 * 128
-  // operand geometry (generic NDHWC-64 mode vs the direct stem mode, see conv_stem_direct_launch)
-  int direct_stem;     // 1: A boxes come straight from the padded NDHWC4 clip (64-byte K rows, SWIZZLE_64B)
-  int ksteps;          // MMAs (K=16) per vertical tap: 4 (64 channels) or 2 (32 = 7 dx x 4 c + pad)
-  int a_tap_bytes;     // descriptor offset between vertical taps: 8 pixels x row bytes
-  int w_tile_bytes;    // one tap's weight tile: 64 x row bytes
-  int sbo_b;           // 8 weight rows
-  int layout;          // UMMA layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
   int pool;            // fused 3x3/2 max-pool epilogue
   bf16* pool_out;      // [B*To, Ho/2, Wo/2, 64], zero-initialised by the caller
 };
@@ -66,10 +59,18 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                : "memory");
 }
 
+// kDirect selects the operand geometry at compile time so the MMA issue loop stays branch-free:
+//   false: NDHWC-64 activations, 128-byte K rows (SWIZZLE_128B), 4 MMAs per vertical tap
+//   true : padded NDHWC4 clip windows, 64-byte K rows (SWIZZLE_64B), 2 MMAs per vertical tap
+template <bool kDirect>
 __global__ void __launch_bounds__(RB_THREADS, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                  const __grid_constant__ CUtensorMap tm_y, const RowsParams p) {
   pdl_launch_dependents();
+  constexpr int ROW_BYTES = kDirect ? 64 : 128;
+  constexpr int KSTEPS = ROW_BYTES / 32;
+  constexpr uint32_t LAYOUT = kDirect ? 4u : 2u;
+  constexpr uint32_t A_TAP_BYTES = RB_X * ROW_BYTES, W_TILE_BYTES = RB_N * ROW_BYTES, SBO_B = 8 * ROW_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // carve-up: [A ring][W double buffer][out ring x2][bias][barriers][tmem ptr]
@@ -129,7 +130,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             mbar_expect_tx(&w_full[wb], p.w_buf_bytes);
             for (int dy = 0; dy < p.kh; ++dy) {
               const int tap = (dt * p.kh + dy) * p.kw + dx;
-              tma_load_2d(smem_w + wb * p.w_buf_bytes + dy * p.w_tile_bytes, &tm_w, &w_full[wb], cb * 64, tap * RB_N);
+              tma_load_2d(smem_w + wb * p.w_buf_bytes + dy * W_TILE_BYTES, &tm_w, &w_full[wb], cb * 64, tap * RB_N);
             }
           }
           __syncwarp();
@@ -145,7 +146,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&full_bar[stage], p.a_tx_bytes);
-              if (p.direct_stem)   // physical pads in the clip: output (yo,xo) reads rows 2yo.., pixels 2xo.. of frame to+dt
+              if (kDirect)   // physical pads in the clip: output (yo,xo) reads rows 2yo.., pixels 2xo.. of frame to+dt
                 tma_load_tile_5d(smem_a + stage * p.a_stage_bytes, &tm_a, &full_bar[stage], 0, xt * RB_X, 2 * yt * RB_R,
                                  to + dt, b);
               else
@@ -187,9 +188,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (elect_one()) {
               for (int dy = 0; dy < p.kh; ++dy) {
                 // vertical tap dy = the same box viewed one image row (8 pixels) further down
-                const uint64_t adesc = make_smem_desc_ex(a_addr + dy * p.a_tap_bytes, 1024, p.layout);
-                const uint64_t bdesc = make_smem_desc_ex(w_addr + dy * p.w_tile_bytes, p.sbo_b, p.layout);
-                for (int k = 0; k < p.ksteps; ++k)
+                const uint64_t adesc = make_smem_desc_ex(a_addr + dy * A_TAP_BYTES, 1024, LAYOUT);
+                const uint64_t bdesc = make_smem_desc_ex(w_addr + dy * W_TILE_BYTES, SBO_B, LAYOUT);
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k)
                   umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ph | dy | k) != 0 ? 1u : 0u);
               }
               umma_commit(&empty_bar[stage]);
@@ -337,7 +339,8 @@ int conv_rows_init() {
   AFB_CUDA(cudaGetDevice(&dev));
   AFB_CUDA(cudaDeviceGetAttribute(&g_rows_sms, cudaDevAttrMultiProcessorCount, dev));
   AFB_CUDA(cudaDeviceGetAttribute(&g_rows_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  AFB_CUDA(cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
+  AFB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
+  AFB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
   return AF_OK;
 }
 
@@ -365,7 +368,7 @@ int conv_rows_launch(const ConvProblem& p, cudaStream_t s) {
   rp.a_stage_bytes = (RB_R + p.kh - 1) * RB_X * 128;
   rp.a_tx_bytes = rp.a_stage_bytes;
   rp.w_buf_bytes = p.kh * RB_N * 128;
-  rp.direct_stem = 0; rp.ksteps = 4; rp.a_tap_bytes = RB_X * 128; rp.w_tile_bytes = RB_N * 128; rp.sbo_b = 1024; rp.layout = 2;
+
   const int fixed = 2 * rp.w_buf_bytes + 2 * RB_OUT_BYTES + RB_N * 4 + 32 * 8 + 16 + 1024;
   rp.stages = (g_rows_max_smem - fixed) / rp.a_stage_bytes;
   if (rp.stages > 8) rp.stages = 8;
@@ -404,7 +407,7 @@ int conv_rows_launch(const ConvProblem& p, cudaStream_t s) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_rows_kernel, ta, tw, ty, rp));
+  AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_rows_kernel<false>, ta, tw, ty, rp));
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;
@@ -433,7 +436,6 @@ int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const vo
   rp.a_tx_bytes = box_rows * RB_X * 64;
   rp.a_stage_bytes = (rp.a_tx_bytes + 1023) / 1024 * 1024;
   rp.w_buf_bytes = 7 * RB_N * 64;
-  rp.direct_stem = 1; rp.ksteps = 2; rp.a_tap_bytes = RB_X * 64; rp.w_tile_bytes = RB_N * 64; rp.sbo_b = 512; rp.layout = 4;
   rp.pool = pool; rp.pool_out = (bf16*)y;
   const int fixed = 2 * rp.w_buf_bytes + 2 * RB_OUT_BYTES + RB_N * 4 + 32 * 8 + 16 + 1024;
   rp.stages = (g_rows_max_smem - fixed) / rp.a_stage_bytes;
@@ -471,7 +473,7 @@ int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const vo
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_rows_kernel, ta, tw, ty, rp));
+  AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_rows_kernel<true>, ta, tw, ty, rp));
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;
