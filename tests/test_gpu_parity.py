@@ -371,3 +371,32 @@ def test_live_ring_scoring_matches_direct_path(dev, state_dict):
     lg, sc = eng.infer_u8(u8)
     assert abs(float(sc[0]) - got[1][1]) <= 1e-6
     eng.close()
+
+
+def test_odd_batches_and_tail_tiles_are_batch_invariant(dev, state_dict, clips_u8):
+    """B=3 (M tails in s5: 3*784 rows is not a multiple of 128; frame-pair tiles; partial chunks) must give
+    exactly the per-clip results of B=1 runs: every clip's arithmetic is independent of its batch mates."""
+    eng = afb200.Engine(state_dict, max_batch=3, precision="bf16")
+    u8 = torch.from_numpy(clips_u8[:3]).to(dev)
+    lg3, _ = eng.infer_u8(u8)
+    for i in range(3):
+        lg1, _ = eng.infer_u8(u8[i:i + 1].contiguous())
+        assert abs(float(lg1[0]) - float(lg3[i])) <= 1e-6, i
+    # chunk sizes must not change results either
+    eng.set_option("chunk_front", 1)
+    eng.set_option("chunk_back", 2)
+    lg3b, _ = eng.infer_u8(u8)
+    assert torch.equal(lg3, lg3b)
+    eng.close()
+
+
+def test_bad_arguments_are_reported_not_crashed(dev, state_dict):
+    eng = afb200.Engine(state_dict, max_batch=1, precision="fp32")
+    with pytest.raises(afb200.Afb200Error, match="unknown option"):
+        eng.set_option("no_such_option", 1)
+    with pytest.raises(afb200.Afb200Error, match="not kept"):
+        eng.get_stage(2)
+    with pytest.raises(afb200.Afb200Error):
+        afb200.conv_ndhwc(torch.zeros(1, 2, 8, 8, 6, device=dev), torch.zeros(64, 6, 1, 1, 1), torch.zeros(64),
+                          (1, 1, 1), (0, 0, 0), True)          # cin % 4 != 0
+    eng.close()
