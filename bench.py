@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -249,6 +249,11 @@ def run_ours(args):
             return parallel.gather_scores(scores, n_total)
         return scores
 
+    # clocks are sampled from the warm-up on (the GPU is under the same load) so that short timed regions
+    # still get samples; the timed region itself is bracketed below
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -257,9 +262,6 @@ def run_ours(args):
     eng.set_option("reset_stats", 1)
     eng.set_option("profile_events", 1)
     launches0 = eng.launch_count
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
@@ -278,6 +280,7 @@ def run_ours(args):
     conv_flops = eng.get_stat("conv_umma_flops")
     conv_n = eng.get_stat("conv_umma_launches")
     simt_ms = eng.get_stat("conv_simt_ms")
+    conv_alg_bytes = eng.get_stat("conv_bytes")
     value = n_total * args.steps / (ms / 1e3)
 
     # end-to-end through the host-buffer C-ABI call (ClassifierSvc.infer_scores boundary)
@@ -323,6 +326,12 @@ def run_ours(args):
     if rank == 0:
         achieved = conv_flops / (conv_ms * 1e9) if conv_ms > 0 else 0.0
         peak = peaks["bf16_sustained"]
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("batch") == B and args.precision == "bf16":
+                traffic, traffic_src = tj["conv_dram_bytes_per_step"], tj["source"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
@@ -333,8 +342,11 @@ def run_ours(args):
                            "weights": "seeded synthetic (no checkpoint ships with the reference)"},
                 "e2e": e2e, "gpu_launches": int(launches_t.item()),
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": achieved / peak, "traffic": None,
-                             "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM conv, all launches of the timed region)",
+                             "frac": achieved / peak, "traffic": traffic,
+                             "traffic_note": "DRAM bytes (read+write) of the %d tcgen05 conv launches of ONE step, from %s" % (int(conv_n / args.steps), traffic_src) if traffic else None,
+                             "algorithmic_bytes_per_step": conv_alg_bytes / args.steps,
+                             "algorithmic_flops_per_step": conv_flops / args.steps,
+                             "kernel": "tcgen05 conv kernels (conv_umma_kernel<64|128|256> + conv_rows_kernel), all launches of the timed region",
                              "launches": int(conv_n), "kernel_ms_per_step": conv_ms / args.steps,
                              "share_of_step": conv_ms / ms if ms > 0 else None,
                              "peak_source": "%s bf16_tflops_sustained (MEASURED_PEAKS.json)" % peaks["source"],
