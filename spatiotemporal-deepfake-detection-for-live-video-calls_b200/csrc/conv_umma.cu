@@ -22,6 +22,9 @@
 //              tmem_full/tmem_empty barriers.
 #include <cuda.h>
 
+#include <cstring>
+#include <unordered_map>
+
 #include "../../include/afb200.h"
 #include "common.cuh"
 #include "umma_ptx.cuh"
@@ -444,15 +447,67 @@ bool conv_umma_supported(const ConvProblem& p) {
   return true;
 }
 
-int conv_umma_launch(const ConvProblem& p, cudaStream_t s) {
+namespace {
+// Everything a launch needs that depends only on the problem (pointers, shapes): tile width, kernel
+// parameters and the four tensor maps.  The engine's buffers are fixed, so plans are memoised — encoding four
+// tensor maps per conv is most of the host cost of a batch-1 pass.
+struct UmmaPlan {
+  alignas(64) CUtensorMap ta, tb, ty, tr;
   UmmaParams up;
+  int bn;
+};
+struct PlanKey {
+  const void *x, *w, *y, *res; const float* bias;
+  int v[20];
+  bool operator==(const PlanKey& o) const { return memcmp(this, &o, sizeof(PlanKey)) == 0; }
+};
+struct PlanKeyHash {
+  size_t operator()(const PlanKey& k) const {
+    const uint64_t* q = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ULL;
+    for (size_t i = 0; i < sizeof(PlanKey) / 8; ++i) { h ^= q[i]; h *= 1099511628211ULL; }
+    return (size_t)h;
+  }
+};
+thread_local std::unordered_map<PlanKey, UmmaPlan, PlanKeyHash> g_plans;
+
+int build_plan(const ConvProblem& p, UmmaPlan& plan);
+}  // namespace
+
+int conv_umma_launch(const ConvProblem& p, cudaStream_t s) {
+  PlanKey key;
+  memset(&key, 0, sizeof(key));
+  key.x = p.x; key.w = p.w; key.y = p.y; key.res = p.res; key.bias = p.bias;
+  const int vals[20] = {p.B, p.Ti, p.Hi, p.Wi, p.Cin, p.To, p.Ho, p.Wo, p.Cout, p.kt, p.kh, p.kw, p.st, p.sh, p.sw,
+                        p.pt, p.ph, p.pw, p.relu, p.pool_t};
+  memcpy(key.v, vals, sizeof(vals));
+  auto it = g_plans.find(key);
+  if (it == g_plans.end()) {
+    if (g_plans.size() > 4096) g_plans.clear();
+    UmmaPlan plan;
+    int rc = build_plan(p, plan);
+    if (rc) return rc;
+    it = g_plans.emplace(key, plan).first;
+  }
+  const UmmaPlan& pl = it->second;
+  switch (pl.bn) {
+    case 256: return launch_t<256>(pl.ta, pl.tb, pl.ty, pl.tr, pl.up, s);
+    case 128: return launch_t<128>(pl.ta, pl.tb, pl.ty, pl.tr, pl.up, s);
+    default: return launch_t<64>(pl.ta, pl.tb, pl.ty, pl.tr, pl.up, s);
+  }
+}
+
+namespace {
+int build_plan(const ConvProblem& p, UmmaPlan& plan) {
+  UmmaParams& up = plan.up;
+  CUtensorMap &ta = plan.ta, &tb = plan.tb, &ty = plan.ty, &tr = plan.tr;
   up.bias = p.bias; up.res = (const bf16*)p.res; up.M = p.M; up.Cout = p.Cout; up.Cin = p.Cin;
   up.kt = p.kt; up.kh = p.kh; up.kw = p.kw; up.st = p.st; up.sh = p.sh; up.sw = p.sw;
   up.pt = p.pt; up.ph = p.ph; up.pw = p.pw; up.To = p.To; up.Ho = p.Ho; up.Wo = p.Wo;
   up.relu = p.relu;
   up.pool_t = p.pool_t; up.hw = p.Ho * p.Wo;
   const bool pointwise = p.kt == 1 && p.kh == 1 && p.kw == 1 && p.st == 1 && p.sh == 1 && p.sw == 1;
-  const char* force = getenv("AFB200_FORCE_IM2COL");
+  static const char* force = getenv("AFB200_FORCE_IM2COL");
   up.im2col = (pointwise && !(force && force[0] == '1')) ? 0 : 1;
   up.num_m_tiles = (int)((p.M + BLOCK_M - 1) / BLOCK_M);      // pool_t: M/128 tiles of (2 frames x 64 pixels) too
 
@@ -461,11 +516,10 @@ int conv_umma_launch(const ConvProblem& p, cudaStream_t s) {
   for (int cand : {256, 128}) {
     if (p.Cout % cand == 0 && (long long)up.num_m_tiles * (p.Cout / cand) >= 2LL * g_num_sms) { bn = cand; break; }
   }
-  const char* fbn = getenv("AFB200_BLOCK_N");
+  static const char* fbn = getenv("AFB200_BLOCK_N");
   if (fbn) { int v = atoi(fbn); if ((v == 64 || v == 128 || v == 256) && p.Cout % v == 0) bn = v; }
   up.num_n_tiles = p.Cout / bn;
 
-  alignas(64) CUtensorMap ta, tb, ty, tr;
   if (up.im2col) {
     cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Ti, (cuuint64_t)p.B};
     cuuint64_t strides[4] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Wi * p.Cin * 2, (cuuint64_t)p.Hi * p.Wi * p.Cin * 2,
@@ -505,11 +559,9 @@ int conv_umma_launch(const ConvProblem& p, cudaStream_t s) {
     if (rc) return rc;
   }
 
-  switch (bn) {
-    case 256: return launch_t<256>(ta, tb, ty, tr, up, s);
-    case 128: return launch_t<128>(ta, tb, ty, tr, up, s);
-    default: return launch_t<64>(ta, tb, ty, tr, up, s);
-  }
+  plan.bn = bn;
+  return AF_OK;
 }
+}  // namespace
 
 }  // namespace afb
