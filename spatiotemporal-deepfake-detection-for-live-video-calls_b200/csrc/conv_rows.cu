@@ -329,18 +329,23 @@ int encode_nd(CUtensorMap* map, const void* base, int rank, const cuuint64_t* di
 }  // namespace
 
 int conv_rows_init() {
-  if (g_rows_encode) return AF_OK;
-  cudaDriverEntryPointQueryResult q;
-  void* fn = nullptr;
-  AFB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-  if (!fn || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return AF_ERR_UNSUPPORTED; }
-  g_rows_encode = (EncodeTiledFn)fn;
+  static bool configured[64] = {};            // function attributes are per device
   int dev = 0;
   AFB_CUDA(cudaGetDevice(&dev));
-  AFB_CUDA(cudaDeviceGetAttribute(&g_rows_sms, cudaDevAttrMultiProcessorCount, dev));
-  AFB_CUDA(cudaDeviceGetAttribute(&g_rows_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  AFB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
-  AFB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
+  if (!g_rows_encode) {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    AFB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return AF_ERR_UNSUPPORTED; }
+    g_rows_encode = (EncodeTiledFn)fn;
+    AFB_CUDA(cudaDeviceGetAttribute(&g_rows_sms, cudaDevAttrMultiProcessorCount, dev));
+    AFB_CUDA(cudaDeviceGetAttribute(&g_rows_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  }
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    AFB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
+    AFB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
   return AF_OK;
 }
 

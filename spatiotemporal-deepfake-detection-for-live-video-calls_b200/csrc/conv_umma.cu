@@ -361,11 +361,13 @@ int g_max_smem = 0;
 template <int BLOCK_N>
 int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const CUtensorMap& tr,
              UmmaParams up, cudaStream_t s) {
-  static bool configured = false;
+  static bool configured[64] = {};            // the opt-in shared-memory size is a per-device function attribute
   auto kern = conv_umma_kernel<BLOCK_N>;
-  if (!configured) {
+  int dev = 0;
+  AFB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     AFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   // shared-memory budget: residual layers trade operand stages for 4 residual + 4 output slots
   const int stage_bytes = A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2;
