@@ -44,9 +44,10 @@ def _fit_nonreflective(src, dst):
     one, zero = np.ones((n, 1)), np.zeros((n, 1))
     X = np.vstack((np.hstack((x, y, one, zero)), np.hstack((y, -x, zero, one))))
     U = np.vstack((src[:, 0:1], src[:, 1:2]))
-    if np.linalg.matrix_rank(X) < 4:
+    sol, _, rank, _ = np.linalg.lstsq(X, U, rcond=-1)      # same solver call as the reference; its rank replaces
+    if rank < 4:                                           # the reference's separate matrix_rank() SVD
         raise ValueError("similarity fit needs at least two distinct points")
-    r = np.squeeze(np.linalg.lstsq(X, U, rcond=-1)[0])
+    r = np.squeeze(sol)
     T = np.linalg.inv(np.array([[r[0], -r[1], 0.0], [r[1], r[0], 0.0], [r[2], r[3], 1.0]]))
     T[:, 2] = (0.0, 0.0, 1.0)
     return T
@@ -111,6 +112,29 @@ def pack_descriptors(frame_tensors: Sequence[torch.Tensor], big_boxes, geoms, de
         cg[i].canvas_wh[0], cg[i].canvas_wh[1] = int(wh[0]), int(wh[1])
     fd_t = torch.frombuffer(bytearray(bytes(fd)), dtype=torch.uint8).to(device)
     cg_t = torch.frombuffer(bytearray(bytes(cg)), dtype=torch.uint8).to(device)
+    return fd_t, cg_t
+
+
+FRAME_DESC_DTYPE = np.dtype([("data", "<u8"), ("pitch", "<i8"), ("height", "<i4"), ("width", "<i4"), ("box", "<i4", (4,))])
+CLIP_GEOM_DTYPE = np.dtype([("tfm", "<f8", (6,)), ("left_top", "<i4", (2,)), ("canvas_wh", "<i4", (2,))])
+assert FRAME_DESC_DTYPE.itemsize == 40 and CLIP_GEOM_DTYPE.itemsize == 64
+
+
+def pack_descriptors_ring(base_ptr: int, slot_stride: int, pitch: int, height: int, width: int, slots, big_boxes, geoms,
+                          device):
+    """Vectorised descriptor build for frames living in ONE device ring (live path): frame i is
+    `base_ptr + slots[i] * slot_stride`.  Same output as pack_descriptors, without a Python loop per frame."""
+    n = len(slots)
+    fd = np.zeros(n, FRAME_DESC_DTYPE)
+    fd["data"] = np.uint64(base_ptr) + np.asarray(slots, np.uint64) * np.uint64(slot_stride)
+    fd["pitch"], fd["height"], fd["width"] = pitch, height, width
+    fd["box"] = np.asarray(big_boxes, np.int32).reshape(n, 4)
+    cg = np.zeros(len(geoms), CLIP_GEOM_DTYPE)
+    cg["tfm"] = np.stack([np.asarray(g[0], np.float64).reshape(6) for g in geoms])
+    cg["left_top"] = np.stack([np.asarray(g[1], np.int32).reshape(2) for g in geoms])
+    cg["canvas_wh"] = np.stack([np.asarray(g[2], np.int32).reshape(2) for g in geoms])
+    fd_t = torch.from_numpy(fd.view(np.uint8)).to(device, non_blocking=True)
+    cg_t = torch.from_numpy(cg.view(np.uint8)).to(device, non_blocking=True)
     return fd_t, cg_t
 
 

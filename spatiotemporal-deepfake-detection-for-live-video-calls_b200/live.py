@@ -184,20 +184,26 @@ class FrameRing:
         return slot
 
 
+def ring_descriptors(ring: FrameRing, clips: List[list], size: int = 224):
+    """Descriptors (device arrays) for windows whose frames all live in `ring`."""
+    from .crop import pack_descriptors_ring
+    slots, boxes, geoms = [], [], []
+    for win in clips:
+        bigs = np.stack([np.asarray(o[1]) for o in win])
+        lt, wh, diff, tfm, trans = clip_geometry(bigs, [o[2] for o in win], size)
+        slots += [o[0] for o in win]
+        boxes.append(bigs)
+        geoms.append((tfm, lt, wh))
+    buf = ring.buf
+    return pack_descriptors_ring(buf.data_ptr(), buf.stride(0), buf.stride(1), ring.h, ring.w, slots,
+                                 np.concatenate(boxes), geoms, ring.engine.device)
+
+
 def make_ring_score_fn(engine, ring: FrameRing, size: int = 224, bgr: bool = False):
     """score_fn for LiveScorer: build descriptors for the windows and run the fused crop+trunk call."""
-    from .crop import pack_descriptors
 
     def score(clips: List[list]):
-        frames, boxes, geoms = [], [], []
-        for win in clips:
-            bigs = np.stack([np.asarray(o[1]) for o in win])
-            lt, wh, diff, tfm, trans = clip_geometry(bigs, [o[2] for o in win], size)
-            for slot, big, _ in win:
-                frames.append(ring.buf[slot])
-                boxes.append(big)
-            geoms.append((tfm, lt, wh))
-        fd, cg = pack_descriptors(frames, boxes, geoms, engine.device)
+        fd, cg = ring_descriptors(ring, clips, size)
         logits, scores = engine.crop_infer(fd, cg, len(clips), bgr=bgr)
         return scores.cpu().numpy()
     return score
