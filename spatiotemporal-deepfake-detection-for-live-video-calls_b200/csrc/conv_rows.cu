@@ -1,18 +1,23 @@
-// K2b: "row-halo" tcgen05 conv for the wide, shallow layers (the unfolded stem and the
-// 1x3x3 convs of s2) where Cout = 64 makes the generic implicit-GEMM kernel L2-bandwidth
-// bound: there every filter tap re-loads its own 128x64 activation tile and its weight tile.
+// K2b / K3: "row-halo" tcgen05 conv for the wide, shallow layers — the stem and the 1x3x3 convs of s2 —
+// where Cout = 64 makes the generic implicit-GEMM kernel L2-bandwidth bound (every filter tap would re-load
+// its own 128x64 activation tile and its weight tile).
 //
-// Here an output tile is an 8-wide x 16-tall patch of one frame.  For each (channel block,
-// dt, dx) "column-tap group" ONE TMA box [8 x (16+kh-1) rows x 64 ch] is loaded; the kh
-// vertical taps are just different views of that box: the UMMA descriptor's start address
-// moves by dy*1024 bytes (8 pixels x 128 B = one swizzle atom, so the 128B-swizzle phase is
-// unchanged).  Zero padding comes from TMA out-of-bounds fill.  The group's kh weight tiles
-// are loaded once per work unit of G=4 tiles (4 accumulators live in TMEM, 2 units double
-// buffered = 512 columns), so operand traffic per tile drops from taps*(16+8) KB to
-// groups*(~19 + 8*kh/4) KB.
+// An output tile is an 8-wide x 16-tall patch of one frame.  For each (channel block, dt, dx) "column-tap
+// group" ONE TMA box is loaded; the kh vertical taps are different views of that box: the UMMA descriptor's
+// start address moves by one image row of 8 pixels (a whole swizzle atom, so the swizzle phase is unchanged).
+// Zero padding comes from TMA out-of-bounds fill (generic mode) or the clip's physical pads (direct stem).
+// The group's kh weight tiles are loaded once per work unit of G=4 tiles (4 accumulators live in TMEM, 2 units
+// double buffered = 512 columns).
 //
-// Same warp roles as conv_umma.cu: warp 0 TMA producer, warp 1 MMA issuer / TMEM owner,
-// warps 2-5 epilogue (bias + ReLU -> bf16 -> swizzled smem -> 4-D TMA store).
+//   conv_rows_kernel<false>  NDHWC-64 activations, 128-byte K rows, SWIZZLE_128B: s2 `b` convs (K2b) and the
+//                            unfolded-stem fallback
+//   conv_rows_kernel<true>   the stem straight from the padded NDHWC4 clip (K3): overlapping-window tensor map,
+//                            64-byte K rows, SWIZZLE_64B, output rows two input rows (1024 B) apart
+//
+// Warp roles as in conv_umma.cu: warp 0 TMA producer, warp 1 MMA issuer / TMEM owner (both walk their loops
+// with all lanes and issue through elect.sync so operands stay in uniform registers), warps 2-9 two epilogue
+// warpgroups (bias + ReLU -> bf16 -> swizzled smem -> 4-D TMA store, or the fused 3x3/2 max-pool: interior
+// windows stored, tile-border windows merged with 16-byte red.global.max.bf16x2).  Programmatic dependent launch.
 // Stride 1 only; no residual (neither the stem nor `b` convs have one:
 // altfreezing/slowfast/models/stem_helper.py:173-178, resnet_helper.py:311-326).
 #include <cuda.h>

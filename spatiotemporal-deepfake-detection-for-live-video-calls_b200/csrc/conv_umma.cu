@@ -14,12 +14,17 @@
 // B tiles: BLOCK_N output channels x 64 input channels of one tap from W[tap][Cout][Cin].
 // Both land in 128B-swizzled K-major shared memory, which is what the UMMA descriptors read.
 //
-// One persistent CTA per SM, warp-specialised:
-//   warp 0   : TMA producer (one lane)        -- STAGES-deep full/empty mbarrier ring
-//   warp 1   : tcgen05.mma issuer (one lane)  -- owns the TMEM allocation (2 accumulators)
-//   warps 2-5: epilogue: tcgen05.ld -> +bias (+residual) -> ReLU -> bf16 -> swizzled smem
-//              -> TMA store; double-buffered against the next tile's main loop through the
-//              tmem_full/tmem_empty barriers.
+// One persistent CTA per SM, warp-specialised (320 threads):
+//   warp 0   : TMA producer                   -- operand ring of `stages` slots, full/empty mbarriers
+//   warp 1   : tcgen05.mma issuer             -- owns the TMEM allocation (2 accumulators)
+//              (both walk their loops with all 32 lanes and issue through elect.sync, so descriptors and
+//               coordinates live in uniform registers and UTCHMMA/UTMALDG go out back to back)
+//   warps 2-9: two epilogue warpgroups on alternate 64-column chunks: tcgen05.ld -> +bias (+residual tile,
+//              TMA-prefetched two chunks ahead) -> ReLU -> bf16 -> swizzled smem -> TMA store; optional fused
+//              temporal max-pool (tile = 64 pixels x 2 frames).  Double-buffered against the next tile's main
+//              loop through the tmem_full/tmem_empty barriers.
+// Shared memory is carved at launch: residual layers trade operand stages for residual/output slots.
+// Programmatic dependent launch overlaps each kernel's prologue with its predecessor's tail.
 #include <cuda.h>
 
 #include <cstring>
