@@ -64,6 +64,79 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                : "memory");
 }
 
+// One 8x16-pixel output tile of the epilogue: accumulator (TMEM, fp32) -> +bias, ReLU -> bf16 tile in swizzled
+// smem -> either a 4-D TMA store or the fused 3x3/2 max-pool.  Called by all 128 threads of one epilogue group.
+__device__ __forceinline__ void rows_epilogue_tile(const RowsParams& p, const CUtensorMap* tm_y_ptr, uint8_t* sout,
+                                                   const float* bias_s, uint32_t taddr, int eg, int et, int row, int xt,
+                                                   int yt, int r) {
+  const CUtensorMap& tm_y = *tm_y_ptr;
+  if (et == 0) tma_store_wait_read<0>();
+  epi_bar_sync(eg);
+  uint32_t v[64];
+  TMEM_LD_32x32b_x32(taddr, v);
+  TMEM_LD_32x32b_x32(taddr + 32, (v + 32));
+  tmem_ld_wait();
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      f[e] = __uint_as_float(v[q * 8 + e]) + bias_s[q * 8 + e];
+      if (p.relu) f[e] = fmaxf(f[e], 0.f);
+    }
+    uint4 o;
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    *reinterpret_cast<uint4*>(sout + row * 128 + ((q ^ (row & 7)) << 4)) = o;
+  }
+  if (!p.pool) {
+    fence_proxy_async_smem();
+    epi_bar_sync(eg);
+    if (et == 0) {
+      tma_store_4d(&tm_y, sout, 0, xt * RB_X, yt * RB_R, r);
+      tma_store_commit();
+    }
+  } else {
+    // Fused MaxPool3d k[1,3,3] s[1,2,2] p[0,1,1] (stem_helper.py:166-168): the 8x16 conv tile in
+    // smem feeds 5x9 pooled positions.  The 3x7 interior ones are complete and stored plainly;
+    // the border ones are shared with neighbouring tiles and merged with a 16-byte vector
+    // red.max into the zero-initialised output (post-ReLU values are >= 0).
+    epi_bar_sync(eg);
+    const int Hp = p.Ho >> 1, Wp = p.Wo >> 1;
+    const int py0 = yt * (RB_R / 2), px0 = xt * (RB_X / 2);
+    for (int item = et; item < 45 * 8; item += 128) {
+      const int ch = item & 7, pos = item >> 3;
+      const int k = pos / 5, j = pos - k * 5;
+      const int py = py0 + k, px = px0 + j;
+      if (py >= Hp || px >= Wp) continue;
+      const int ly0 = k == 0 ? 0 : 2 * k - 1, ly1 = k == 8 ? 15 : 2 * k + 1;
+      const int lx0 = j == 0 ? 0 : 2 * j - 1, lx1 = j == 4 ? 7 : 2 * j + 1;
+      uint4 m = make_uint4(0u, 0u, 0u, 0u);
+      __nv_bfloat162* m2 = reinterpret_cast<__nv_bfloat162*>(&m);
+      for (int ly = ly0; ly <= ly1; ++ly) {
+        if (yt * RB_R + ly >= p.Ho) break;             // rows past the image hold garbage
+        for (int lx = lx0; lx <= lx1; ++lx) {
+          const int rr = ly * RB_X + lx;
+          const uint4 t = *reinterpret_cast<const uint4*>(sout + rr * 128 + ((ch ^ (rr & 7)) << 4));
+          const __nv_bfloat162* t2 = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) m2[e] = __hmax2(m2[e], t2[e]);
+        }
+      }
+      bf16* dst = p.pool_out + (((long long)r * Hp + py) * Wp + px) * RB_N + ch * 8;
+      const bool interior = k >= 1 && k <= 7 && j >= 1 && j <= 3;
+      if (interior) {
+        *reinterpret_cast<uint4*>(dst) = m;
+      } else {
+        asm volatile("red.global.v4.bf16x2.max.noftz [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(m.x), "r"(m.y), "r"(m.z),
+                     "r"(m.w)
+                     : "memory");
+      }
+    }
+  }
+}
+
 // kDirect selects the operand geometry at compile time so the MMA issue loop stays branch-free:
 //   false: NDHWC-64 activations, 128-byte K rows (SWIZZLE_128B), 4 MMAs per vertical tap
 //   true : padded NDHWC4 clip windows, 64-byte K rows (SWIZZLE_64B), 2 MMAs per vertical tap
@@ -233,73 +306,162 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         int r = tile;
         const int xt = r % p.x_tiles; r /= p.x_tiles;
         const int yt = r % p.y_tiles; r /= p.y_tiles;   // r = b*To + to
-        if (et == 0) tma_store_wait_read<0>();
-        epi_bar_sync(eg);
-        uint32_t v[64];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (as * RB_G + g) * RB_N;
-        TMEM_LD_32x32b_x32(taddr, v);
-        TMEM_LD_32x32b_x32(taddr + 32, (v + 32));
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            f[e] = __uint_as_float(v[q * 8 + e]) + bias_s[q * 8 + e];
-            if (p.relu) f[e] = fmaxf(f[e], 0.f);
-          }
-          uint4 o;
-          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-          *reinterpret_cast<uint4*>(sout + row * 128 + ((q ^ (row & 7)) << 4)) = o;
-        }
-        if (!p.pool) {
-          fence_proxy_async_smem();
-          epi_bar_sync(eg);
-          if (et == 0) {
-            tma_store_4d(&tm_y, sout, 0, xt * RB_X, yt * RB_R, r);
-            tma_store_commit();
-          }
-        } else {
-          // Fused MaxPool3d k[1,3,3] s[1,2,2] p[0,1,1] (stem_helper.py:166-168): the 8x16 conv tile in
-          // smem feeds 5x9 pooled positions.  The 3x7 interior ones are complete and stored plainly;
-          // the border ones are shared with neighbouring tiles and merged with a 16-byte vector
-          // red.max into the zero-initialised output (post-ReLU values are >= 0).
-          epi_bar_sync(eg);
-          const int Hp = p.Ho >> 1, Wp = p.Wo >> 1;
-          const int py0 = yt * (RB_R / 2), px0 = xt * (RB_X / 2);
-          for (int item = et; item < 45 * 8; item += 128) {
-            const int ch = item & 7, pos = item >> 3;
-            const int k = pos / 5, j = pos - k * 5;
-            const int py = py0 + k, px = px0 + j;
-            if (py >= Hp || px >= Wp) continue;
-            const int ly0 = k == 0 ? 0 : 2 * k - 1, ly1 = k == 8 ? 15 : 2 * k + 1;
-            const int lx0 = j == 0 ? 0 : 2 * j - 1, lx1 = j == 4 ? 7 : 2 * j + 1;
-            uint4 m = make_uint4(0u, 0u, 0u, 0u);
-            __nv_bfloat162* m2 = reinterpret_cast<__nv_bfloat162*>(&m);
-            for (int ly = ly0; ly <= ly1; ++ly) {
-              if (yt * RB_R + ly >= p.Ho) break;             // rows past the image hold garbage
-              for (int lx = lx0; lx <= lx1; ++lx) {
-                const int rr = ly * RB_X + lx;
-                const uint4 t = *reinterpret_cast<const uint4*>(sout + rr * 128 + ((ch ^ (rr & 7)) << 4));
-                const __nv_bfloat162* t2 = reinterpret_cast<const __nv_bfloat162*>(&t);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) m2[e] = __hmax2(m2[e], t2[e]);
-              }
-            }
-            bf16* dst = p.pool_out + (((long long)r * Hp + py) * Wp + px) * RB_N + ch * 8;
-            const bool interior = k >= 1 && k <= 7 && j >= 1 && j <= 3;
-            if (interior) {
-              *reinterpret_cast<uint4*>(dst) = m;
-            } else {
-              asm volatile("red.global.v4.bf16x2.max.noftz [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(m.x), "r"(m.y), "r"(m.z),
-                           "r"(m.w)
-                           : "memory");
-            }
-          }
-        }
+        rows_epilogue_tile(p, &tm_y, sout, bias_s, tmem_base + ((uint32_t)(quad * 32) << 16) + (as * RB_G + g) * RB_N, eg, et, row,
+                           xt, yt, r);
       }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+    }
+    if (et == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// K3 (default stem path): temporal-sweep variant of the direct stem.  A work unit is one 8x16 spatial tile over
+// FOUR consecutive output frames (4 accumulators).  The 35 (dt,dy) weight tiles (140 KB) stay resident in shared
+// memory for the CTA's lifetime, and each of the unit's 8 input-frame boxes is loaded ONCE and used by every
+// (output frame, dt) pair it participates in (input frame f feeds output g with dt = f - g): 2 boxes per output
+// tile instead of 5 boxes + 5 weight groups, which takes the stem off the L2->SM bandwidth limit.
+constexpr int SW_W_BYTES = 35 * RB_N * 64;        // 143360
+constexpr int SW_A_STAGES = 2;
+
+__global__ void __launch_bounds__(RB_THREADS, 1)
+stem_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                  const __grid_constant__ CUtensorMap tm_y, const RowsParams p) {
+  pdl_launch_dependents();
+  constexpr uint32_t LAYOUT = 4u, A_TAP_BYTES = RB_X * 64, W_TILE_BYTES = RB_N * 64, SBO_B = 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_w = smem;                                        // [35][64][32] bf16, SWIZZLE_64B
+  uint8_t* smem_a = smem_w + SW_W_BYTES;                         // [2] boxes
+  uint8_t* smem_out = smem_a + SW_A_STAGES * p.a_stage_bytes;    // [2] x 16 KB
+  float* bias_s = reinterpret_cast<float*>(smem_out + 2 * RB_OUT_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + RB_N);
+  uint64_t* empty_bar = full_bar + SW_A_STAGES;
+  uint64_t* w_full = empty_bar + SW_A_STAGES;
+  uint64_t* tmem_full = w_full + 1;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 2 * RB_G * RB_N;   // 512
+  const int tgroups = p.To / RB_G;                  // output-frame groups per clip (To % 4 == 0)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_w);
+    for (int i = 0; i < SW_A_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
+    fence_barrier_init();
+  } else if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + RB_N) bias_s[threadIdx.x - 64] = __ldg(p.bias + threadIdx.x - 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (elect_one()) {                              // weights are constants: no need to wait for the prior grid
+      mbar_expect_tx(w_full, SW_W_BYTES);
+      for (int i = 0; i < 35; ++i) tma_load_2d(smem_w + i * W_TILE_BYTES, &tm_w, w_full, 0, i * RB_N);
+    }
+    __syncwarp();
+    pdl_wait_prior_grid();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int r = unit;
+      const int xt = r % p.x_tiles; r /= p.x_tiles;
+      const int yt = r % p.y_tiles; r /= p.y_tiles;
+      const int tg = r % tgroups;
+      const int b = r / tgroups;
+      for (int f = 0; f < RB_G + 4; ++f) {          // padded frame index of logical frame tg*4 - 2 + f
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[stage], p.a_tx_bytes);
+          tma_load_tile_5d(smem_a + stage * p.a_stage_bytes, &tm_a, &full_bar[stage], 0, xt * RB_X, 2 * yt * RB_R,
+                           tg * RB_G + f, b);
+        }
+        __syncwarp();
+        if (++stage == SW_A_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    pdl_wait_prior_grid();
+    constexpr uint32_t idesc = make_idesc(RB_N);
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    const uint32_t w_base = smem_u32(smem_w);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int f = 0; f < RB_G + 4; ++f) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + stage * p.a_stage_bytes);
+        if (elect_one()) {
+          const int g_lo = f > 4 ? f - 4 : 0, g_hi = f < RB_G - 1 ? f : RB_G - 1;
+          for (int g = g_lo; g <= g_hi; ++g) {      // output frame g of the unit sees this input frame as tap dt = f - g
+            const int dt = f - g;
+            const uint32_t d_tmem = tmem_base + (as * RB_G + g) * RB_N;
+            const uint32_t w_addr = w_base + dt * 7 * W_TILE_BYTES;
+#pragma unroll
+            for (int dy = 0; dy < 7; ++dy) {
+              const uint64_t adesc = make_smem_desc_ex(a_addr + dy * A_TAP_BYTES, 1024, LAYOUT);
+              const uint64_t bdesc = make_smem_desc_ex(w_addr + dy * W_TILE_BYTES, SBO_B, LAYOUT);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (dt | dy) != 0 ? 1u : 0u);
+              umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == SW_A_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&tmem_full[as]);
+      __syncwarp();
+    }
+  } else {
+    // ===================================================== epilogue: two warpgroups, alternate frames of the unit
+    pdl_wait_prior_grid();
+    const int eg = (warp - 2) >> 2;
+    const int et = (threadIdx.x - 64) & 127;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    uint8_t* sout = smem_out + eg * RB_OUT_BYTES;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&tmem_full[as], (it >> 1) & 1);
+      tc_fence_after();
+      int r = unit;
+      const int xt = r % p.x_tiles; r /= p.x_tiles;
+      const int yt = r % p.y_tiles; r /= p.y_tiles;
+      const int tg = r % tgroups;
+      const int b = r / tgroups;
+#pragma unroll 1
+      for (int g = eg; g < RB_G; g += 2)
+        rows_epilogue_tile(p, &tm_y, sout, bias_s, tmem_base + ((uint32_t)(quad * 32) << 16) + (as * RB_G + g) * RB_N, eg, et,
+                           row, xt, yt, b * p.To + tg * RB_G + g);
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
     }
@@ -349,6 +511,7 @@ int conv_rows_init() {
   if (dev < 0 || dev >= 64 || !configured[dev]) {
     AFB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
     AFB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
+    AFB_CUDA(cudaFuncSetAttribute(stem_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   return AF_OK;
@@ -476,14 +639,25 @@ int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const vo
     int rc = encode_nd(&ty, y, 4, dims, strides, box, "stem-direct Y");
     if (rc) return rc;
   }
-  const int grid = rp.num_units < g_rows_sms ? rp.num_units : g_rows_sms;
+  static const bool no_sweep = getenv("AFB200_NO_STEM_SWEEP") != nullptr;
+  const int sweep_dyn = SW_W_BYTES + SW_A_STAGES * rp.a_stage_bytes + 2 * RB_OUT_BYTES + RB_N * 4 + 16 * 8 + 16 + 1024;
+  const bool sweep = !no_sweep && (T % RB_G == 0) && sweep_dyn <= g_rows_max_smem;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(RB_THREADS); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
+  cfg.blockDim = dim3(RB_THREADS); cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_rows_kernel<true>, ta, tw, ty, rp));
+  if (sweep) {
+    rp.num_units = B * (T / RB_G) * rp.y_tiles * rp.x_tiles;      // unit = spatial tile x 4 consecutive output frames
+    cfg.gridDim = dim3(rp.num_units < g_rows_sms ? rp.num_units : g_rows_sms);
+    cfg.dynamicSmemBytes = sweep_dyn;
+    AFB_CUDA(cudaLaunchKernelEx(&cfg, stem_sweep_kernel, ta, tw, ty, rp));
+  } else {
+    cfg.gridDim = dim3(rp.num_units < g_rows_sms ? rp.num_units : g_rows_sms);
+    cfg.dynamicSmemBytes = dyn;
+    AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_rows_kernel<true>, ta, tw, ty, rp));
+  }
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;
