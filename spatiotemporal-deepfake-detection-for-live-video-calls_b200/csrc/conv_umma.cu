@@ -286,12 +286,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         mbar_arrive(&tmem_empty[as]);
       }
       const int cbase = cur.chunk * 64;
-      // fused temporal max-pool: rows r and r+64 are the same pixel in frames 2j and 2j+1.  The upper half
-      // (rows 64..127) parks its bf16 row in the staging tile, the lower half combines it with its registers.
-      const bool upper = p.pool_t && row >= 64;
-      const bool lower = p.pool_t && row < 64;
-      const int srow = upper ? row - 64 : row;       // (row - 64) & 7 == row & 7: same swizzle phase
-      uint4 keep[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {                // 8 x 16 bytes of output per row
         float f[8];
@@ -315,23 +309,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
         for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-        if (lower) keep[q] = o;
-        else *reinterpret_cast<uint4*>(sout + srow * 128 + ((q ^ (row & 7)) << 4)) = o;
+        *reinterpret_cast<uint4*>(sout + off) = o;
       }
       if (p.pool_t) {
-        // MaxPool3d k=s=[2,1,1] (pathway0_pool, video_model_builder.py:474-480,566-568)
+        // MaxPool3d k=s=[2,1,1] (pathway0_pool): rows r and r+64 are the same pixel in frames 2j, 2j+1
         epi_bar_sync(eg);
-        if (lower) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            uint8_t* pa = sout + row * 128 + ((q ^ (row & 7)) << 4);
-            const uint4 b4 = *reinterpret_cast<const uint4*>(pa);
-            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b4);
-            __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&keep[q]);
+        for (int i2 = 0; i2 < 4; ++i2) {
+          const int item = et + i2 * EPI_THREADS, r2 = item >> 3, q2 = item & 7;
+          uint8_t* pa = sout + r2 * 128 + ((q2 ^ (r2 & 7)) << 4);
+          uint4 a4 = *reinterpret_cast<uint4*>(pa);
+          const uint4 b4 = *reinterpret_cast<const uint4*>(pa + 64 * 128);     // (r2+64)&7 == r2&7
+          __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&a4);
+          const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b4);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) a2[e] = __hmax2(a2[e], b2[e]);
-            *reinterpret_cast<uint4*>(pa) = keep[q];
-          }
+          for (int e = 0; e < 4; ++e) a2[e] = __hmax2(a2[e], b2[e]);
+          *reinterpret_cast<uint4*>(pa) = a4;
         }
       }
       fence_proxy_async_smem();
