@@ -262,7 +262,10 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
   if (!pool_t && is_bf16 && (impl == 0 || impl == 3) && conv_rows_supported(p)) {
     rc = conv_rows_launch(p, s);
     which = "urows";
-  } else if (is_bf16 && impl != 1 && impl != 3 && conv_umma_supported(p)) {
+  } else if (!pool_t && is_bf16 && (impl == 0 || impl == 6) && conv_tsweep_supported(p)) {
+    rc = conv_tsweep_launch(p, s);
+    which = "usweep";
+  } else if (is_bf16 && impl != 1 && impl != 3 && impl != 6 && conv_umma_supported(p)) {
     rc = conv_umma_launch(p, s);
     which = "umma";
   } else if (is_bf16 && impl >= 2) {
@@ -572,6 +575,7 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
   if (e->is_bf16) {
     int rc = conv_umma_init();
     if (!rc) rc = conv_rows_init();
+    if (!rc) rc = conv_tsweep_init();
     if (rc) return (af_status)rc;
   }
   e->convs.resize(w->n_convs);
@@ -830,7 +834,7 @@ af_status af_conv_ndhwc(const void* x_dev, const af_conv_desc* conv_host, const 
     return AF_ERR_INVALID;
   }
   const bool is_bf16 = precision == AF_PREC_BF16;
-  if (is_bf16) { int rc = conv_umma_init(); if (!rc) rc = conv_rows_init(); if (rc) return (af_status)rc; }
+  if (is_bf16) { int rc = conv_umma_init(); if (!rc) rc = conv_rows_init(); if (!rc) rc = conv_tsweep_init(); if (rc) return (af_status)rc; }
   ConvLayer L;
   int rc = upload_layer(*conv_host, is_bf16, L);
   if (!rc) {

@@ -61,6 +61,10 @@ int conv_umma_init();
 bool conv_rows_supported(const ConvProblem& p);
 int conv_rows_launch(const ConvProblem& p, cudaStream_t s);
 int conv_rows_init();
+// conv_tsweep.cu (temporal-sweep tcgen05 kernel for 3x1x1 convs with Cout = 64)
+bool conv_tsweep_supported(const ConvProblem& p);
+int conv_tsweep_launch(const ConvProblem& p, cudaStream_t s);
+int conv_tsweep_init();
 int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const void* w35, const float* bias, void* y,
                             int pool, cudaStream_t s);
 // pool_head.cu
