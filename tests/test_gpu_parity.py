@@ -178,6 +178,21 @@ def test_pointwise_kernel_fused_temporal_maxpool(dev, case, with_res):
     assert (got - want).abs().max().item() <= tol
 
 
+@pytest.mark.parametrize("case", [(64, 1, 4, 8, 8), (256, 2, 8, 12, 12), (128, 1, 4, 56, 56), (256, 1, 32, 20, 7)])
+def test_temporal_sweep_kernel_vs_torch_fp32(dev, case):
+    """3x1x1 conv, Cout 64 (s2 `a` convs) through the temporal-sweep tcgen05 kernel (impl=6): temporal zero
+    padding at both clip ends, several clips, ragged last pixel tile (H*W not a multiple of 128)."""
+    cin, B, T, H, W = case
+    g = torch.Generator().manual_seed(cin + T + H)
+    x = torch.randn(B, T, H, W, cin, generator=g).to(dev, torch.bfloat16)
+    w = torch.randn(64, cin, 3, 1, 1, generator=g) * (2.0 / (cin * 3)) ** 0.5
+    b = torch.randn(64, generator=g) * 0.1
+    want = _conv_ref(x, w.to(torch.bfloat16).float(), b, (1, 1, 1), (1, 0, 0), True, None)
+    got = afb200.conv_ndhwc(x, w, b, (1, 1, 1), (1, 0, 0), True, None, impl=6).float().cpu()
+    tol = 2.0 ** -8 * max(1.0, want.abs().max().item()) + 1e-3
+    assert (got - want).abs().max().item() <= tol
+
+
 def test_umma_and_simt_bf16_agree_closely(dev):
     """Same bf16 inputs, both fp32-accumulating: results may differ only by accumulation
     order, i.e. by at most one bf16 ulp after the final rounding."""
