@@ -45,6 +45,7 @@ struct RowsParams {
   int a_stage_bytes;   // ring slot size (1024-aligned)
   int a_tx_bytes;      // bytes one A box actually delivers (mbarrier expect_tx)
   int w_buf_bytes;     // kh * 64 * 128
+  int w_resident;      // all phases' weights fit in smem: loaded once per CTA instead of once per unit
   int pool;            // fused 3x3/2 max-pool epilogue
   bf16* pool_out;      // [B*To, Ho/2, Wo/2, 64], zero-initialised by the caller
 };
@@ -154,7 +155,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   // carve-up: [A ring][W double buffer][out ring x2][bias][barriers][tmem ptr]
   uint8_t* smem_a = smem;
   uint8_t* smem_w = smem_a + p.stages * p.a_stage_bytes;
-  uint8_t* smem_out = smem_w + 2 * p.w_buf_bytes;
+  const int cblocks = p.Cin / 64;
+  const int num_phases = cblocks * p.kt * p.kw;
+  uint8_t* smem_out = smem_w + (p.w_resident ? num_phases : 2) * p.w_buf_bytes;
   float* bias_s = reinterpret_cast<float*>(smem_out + 2 * RB_OUT_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + RB_N);
   uint64_t* empty_bar = full_bar + 8;
@@ -165,8 +168,6 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int cblocks = p.Cin / 64;
-  const int num_phases = cblocks * p.kt * p.kw;
   constexpr uint32_t TMEM_COLS = 2 * RB_G * RB_N;   // 512
 
   if (warp == 0 && lane == 0) {
@@ -198,21 +199,35 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       uint32_t wcount = 0;                 // weight-buffer uses so far
+      if (p.w_resident) {                  // every phase's kh weight tiles, once per CTA
+        if (elect_one()) {
+          mbar_expect_tx(&w_full[0], num_phases * p.w_buf_bytes);
+          for (int ph = 0; ph < num_phases; ++ph) {
+            const int dx = ph % p.kw, q = ph / p.kw, dt = q % p.kt, cb = q / p.kt;
+            for (int dy = 0; dy < p.kh; ++dy)
+              tma_load_2d(smem_w + ph * p.w_buf_bytes + dy * W_TILE_BYTES, &tm_w, &w_full[0], cb * 64,
+                          ((dt * p.kh + dy) * p.kw + dx) * RB_N);
+          }
+        }
+        __syncwarp();
+      }
       for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
         for (int ph = 0; ph < num_phases; ++ph) {
           // phase -> (channel block, dt, dx)
           const int dx = ph % p.kw, q = ph / p.kw, dt = q % p.kt, cb = q / p.kt;
-          const int wb = wcount & 1;
-          mbar_wait(&w_empty[wb], ((wcount >> 1) & 1) ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&w_full[wb], p.w_buf_bytes);
-            for (int dy = 0; dy < p.kh; ++dy) {
-              const int tap = (dt * p.kh + dy) * p.kw + dx;
-              tma_load_2d(smem_w + wb * p.w_buf_bytes + dy * W_TILE_BYTES, &tm_w, &w_full[wb], cb * 64, tap * RB_N);
+          if (!p.w_resident) {
+            const int wb = wcount & 1;
+            mbar_wait(&w_empty[wb], ((wcount >> 1) & 1) ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&w_full[wb], p.w_buf_bytes);
+              for (int dy = 0; dy < p.kh; ++dy) {
+                const int tap = (dt * p.kh + dy) * p.kw + dx;
+                tma_load_2d(smem_w + wb * p.w_buf_bytes + dy * W_TILE_BYTES, &tm_w, &w_full[wb], cb * 64, tap * RB_N);
+              }
             }
+            __syncwarp();
+            ++wcount;
           }
-          __syncwarp();
-          ++wcount;
           for (int g = 0; g < RB_G; ++g) {
             const int tile = unit * RB_G + g;
             if (tile >= p.num_tiles) break;
@@ -246,15 +261,18 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       uint32_t phase = 0;
       uint32_t wcount = 0;
       int it = 0;
+      if (p.w_resident) { mbar_wait(&w_full[0], 0); tc_fence_after(); }
       for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         for (int ph = 0; ph < num_phases; ++ph) {
-          const int wb = wcount & 1;
-          mbar_wait(&w_full[wb], (wcount >> 1) & 1);
-          tc_fence_after();
+          const int wb = p.w_resident ? ph : (int)(wcount & 1);
+          if (!p.w_resident) {
+            mbar_wait(&w_full[wb], (wcount >> 1) & 1);
+            tc_fence_after();
+          }
           const uint32_t w_addr = smem_u32(smem_w + wb * p.w_buf_bytes);
           for (int g = 0; g < RB_G; ++g) {
             const int tile = unit * RB_G + g;
@@ -277,9 +295,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          if (elect_one()) umma_commit(&w_empty[wb]);
-          __syncwarp();
-          ++wcount;
+          if (!p.w_resident) {
+            if (elect_one()) umma_commit(&w_empty[wb]);
+            __syncwarp();
+            ++wcount;
+          }
         }
         if (elect_one()) umma_commit(&tmem_full[as]);
         __syncwarp();
@@ -542,7 +562,10 @@ int conv_rows_launch(const ConvProblem& p, cudaStream_t s) {
   rp.a_tx_bytes = rp.a_stage_bytes;
   rp.w_buf_bytes = p.kh * RB_N * 128;
 
-  const int fixed = 2 * rp.w_buf_bytes + 2 * RB_OUT_BYTES + RB_N * 4 + 32 * 8 + 16 + 1024;
+  const int phases = (p.Cin / 64) * p.kt * p.kw;
+  static const bool no_res = getenv("AFB200_NO_RESIDENT_W") != nullptr;
+  rp.w_resident = (!no_res && phases * rp.w_buf_bytes <= 96 * 1024) ? 1 : 0;
+  const int fixed = (rp.w_resident ? phases : 2) * rp.w_buf_bytes + 2 * RB_OUT_BYTES + RB_N * 4 + 32 * 8 + 16 + 1024;
   rp.stages = (g_rows_max_smem - fixed) / rp.a_stage_bytes;
   if (rp.stages > 8) rp.stages = 8;
   if (rp.stages < 2) { set_error("conv_rows: not enough shared memory"); return AF_ERR_INVALID; }
@@ -610,6 +633,7 @@ int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const vo
   rp.a_stage_bytes = (rp.a_tx_bytes + 1023) / 1024 * 1024;
   rp.w_buf_bytes = 7 * RB_N * 64;
   rp.pool = pool; rp.pool_out = (bf16*)y;
+  rp.w_resident = 0;
   const int fixed = 2 * rp.w_buf_bytes + 2 * RB_OUT_BYTES + RB_N * 4 + 32 * 8 + 16 + 1024;
   rp.stages = (g_rows_max_smem - fixed) / rp.a_stage_bytes;
   if (rp.stages > 8) rp.stages = 8;
