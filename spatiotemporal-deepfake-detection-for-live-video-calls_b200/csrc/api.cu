@@ -18,6 +18,7 @@ namespace afb {
 
 static thread_local char g_err[1024] = "";
 thread_local long long g_launches = 0;
+thread_local int g_sm_limit = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -174,6 +175,7 @@ struct af_engine {
   int cb_front = 32, cb_back = 32;  // clips per chunk: stem..s2 / s3..head (tuned on B200)
   int conv_impl = 0;       // 0 auto, 1 force SIMT, 2 force UMMA where supported
   bool keep_stages = false;
+  int sm_limit = 0;              // CTAs per conv launch (0 = all SMs)
   bool pooled_already = false;   // the previous block's `c` conv already applied the temporal max-pool
   long long launches = 0;
 
@@ -395,6 +397,7 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
   const int split = e->split < 0 ? nblk : e->split;
   e->stage_batch = B;
   e->pooled_already = false;
+  g_sm_limit = e->sm_limit;
 
   for (int g0 = 0; g0 < B; g0 += e->cb_back) {
     const int gB = (B - g0) < e->cb_back ? (B - g0) : e->cb_back;
@@ -648,6 +651,7 @@ af_status af_set_option(af_handle h, const char* name, int64_t value) {
   std::string n(name);
   if (n == "keep_stages") { h->keep_stages = value != 0; return AF_OK; }
   if (n == "conv_impl") { h->conv_impl = (int)value; return AF_OK; }
+  if (n == "sm_limit") { h->sm_limit = (int)value; return AF_OK; }
   if (n == "profile_events") { h->profile_events = value != 0; return AF_OK; }
   if (n == "reset_stats") {
     cudaSetDevice(h->device);

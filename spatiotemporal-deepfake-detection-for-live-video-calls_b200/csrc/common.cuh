@@ -30,7 +30,11 @@ struct ConvProblem {
 };
 
 void set_error(const char* fmt, ...);
-extern thread_local long long g_launches;   // kernels launched by this thread (copied into engines)
+extern thread_local long long g_launches;
+// Upper bound on the CTAs (= SMs, all tcgen05 kernels are persistent with 1 CTA/SM) a conv launch may occupy;
+// 0 = whole device.  Lets two half-batches run side by side on disjoint SM sets (engine option "sm_limit").
+extern thread_local int g_sm_limit;
+inline int limit_grid(int want, int sms) { const int cap = (g_sm_limit > 0 && g_sm_limit < sms) ? g_sm_limit : sms; return want < cap ? want : cap; }   // kernels launched by this thread (copied into engines)
 
 // Per-op timing to stderr when AFB200_TRACE=1 (synchronises; bring-up/profiling aid only).
 struct OpTrace {

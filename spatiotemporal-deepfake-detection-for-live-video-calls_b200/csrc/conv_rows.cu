@@ -596,7 +596,7 @@ int conv_rows_launch(const ConvProblem& p, cudaStream_t s) {
     int rc = encode_nd(&ty, p.y, 4, dims, strides, box, "rows Y");
     if (rc) return rc;
   }
-  const int grid = rp.num_units < g_rows_sms ? rp.num_units : g_rows_sms;
+  const int grid = limit_grid(rp.num_units, g_rows_sms);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(RB_THREADS); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -674,11 +674,11 @@ int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const vo
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (sweep) {
     rp.num_units = B * (T / RB_G) * rp.y_tiles * rp.x_tiles;      // unit = spatial tile x 4 consecutive output frames
-    cfg.gridDim = dim3(rp.num_units < g_rows_sms ? rp.num_units : g_rows_sms);
+    cfg.gridDim = dim3(limit_grid(rp.num_units, g_rows_sms));
     cfg.dynamicSmemBytes = sweep_dyn;
     AFB_CUDA(cudaLaunchKernelEx(&cfg, stem_sweep_kernel, ta, tw, ty, rp));
   } else {
-    cfg.gridDim = dim3(rp.num_units < g_rows_sms ? rp.num_units : g_rows_sms);
+    cfg.gridDim = dim3(limit_grid(rp.num_units, g_rows_sms));
     cfg.dynamicSmemBytes = dyn;
     AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_rows_kernel<true>, ta, tw, ty, rp));
   }

@@ -309,7 +309,7 @@ int conv_tsweep_launch(const ConvProblem& p, cudaStream_t s) {
     if (rc) return rc;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(tp.num_units < g_ts_sms ? tp.num_units : g_ts_sms);
+  cfg.gridDim = dim3(limit_grid(tp.num_units, g_ts_sms));
   cfg.blockDim = dim3(TS_THREADS); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

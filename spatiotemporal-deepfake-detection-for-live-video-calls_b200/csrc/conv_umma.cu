@@ -386,7 +386,7 @@ int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty
   up.stages = stages;
   const int dyn = fixed + stages * stage_bytes;
   const int tiles = up.num_m_tiles * up.num_n_tiles;
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  const int grid = limit_grid(tiles, g_num_sms);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
   cudaLaunchAttribute attr[1];
