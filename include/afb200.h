@@ -132,6 +132,13 @@ af_status af_set_option(af_handle h, const char* name, int64_t value);
 af_status af_forward(af_handle h, const void* clip_dev, int32_t dtype, const int64_t strides[5],
                      int32_t batch, float* logits_dev, float* features_dev, void* stream);
 
+/* af_forward plus per-frame features: frame_features_dev [B, T/2, feature_dim] = spatial mean of the last stage
+ * per output frame (their temporal mean is the pooled feature of af_forward).  This is the `backbone(x) -> [B,T',D]`
+ * contract of AltFreezingRGBEncoder (dualrun/model/dual_rgb.py:26-44; the reference ships no adapter, SURVEY.md
+ * §8a row A13). */
+af_status af_forward_frames(af_handle h, const void* clip_dev, int32_t dtype, const int64_t strides[5],
+                            int32_t batch, float* logits_dev, float* frame_features_dev, void* stream);
+
 /* ClassifierSvc.infer_scores (altfreezing/TEST2.py:151-204, test/af_realtime.py:75-96) on
  * device buffers: u8 aligned clips [B,T,S,S,3] RGB -> (x-255*mean)/(255*std) -> trunk ->
  * logits [B] (and sigmoid scores [B] if scores_dev != NULL). mean/std are the three

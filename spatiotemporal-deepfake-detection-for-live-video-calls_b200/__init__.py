@@ -6,13 +6,13 @@ built `libafb200.so` is missing — there is no CPU fallback.
 """
 from . import arch, live, parallel, synthetic  # noqa: F401
 from ._lib import Afb200Error, LIB_PATH, lib  # noqa: F401
-from .classifier import B200Engine, Classifier  # noqa: F401
+from .classifier import B200Engine, Classifier, RGBBackboneB200  # noqa: F401
 from .crop import CropAlignB200, clip_geometry, estimate_clip_transform, get_crop_box  # noqa: F401
 from .engine import Engine, conv_ndhwc, mean_std_255  # noqa: F401
 from .network import I3D8x8Params  # noqa: F401
 from .service import ClassifierSvc, CropAlignSvc  # noqa: F401
 from .weights import FoldedWeights, fold_conv_bn, strip_checkpoint  # noqa: F401
 
-__all__ = ["arch", "synthetic", "lib", "Engine", "B200Engine", "Classifier", "CropAlignB200", "ClassifierSvc",
+__all__ = ["arch", "synthetic", "lib", "Engine", "B200Engine", "Classifier", "RGBBackboneB200", "CropAlignB200", "ClassifierSvc",
            "CropAlignSvc", "I3D8x8Params", "FoldedWeights", "conv_ndhwc", "get_crop_box", "clip_geometry",
            "estimate_clip_transform", "mean_std_255", "Afb200Error"]

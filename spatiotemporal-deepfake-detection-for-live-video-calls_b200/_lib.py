@@ -45,7 +45,7 @@ class AfClipGeom(C.Structure):
 
 
 EXPORTS = ("af_last_error", "af_version", "af_launch_count", "af_create", "af_destroy", "af_set_option",
-           "af_forward", "af_infer_u8", "af_infer_u8_host", "af_crop_u8", "af_crop_infer",
+           "af_forward", "af_forward_frames", "af_infer_u8", "af_infer_u8_host", "af_crop_u8", "af_crop_infer",
            "af_conv_ndhwc", "af_get_stage", "af_get_stat")
 
 _lib = None
@@ -78,6 +78,8 @@ def lib():
     L.af_set_option.argtypes = [vp, C.c_char_p, i64]
     L.af_forward.restype = i32
     L.af_forward.argtypes = [vp, vp, i32, C.POINTER(i64), i32, f32p, f32p, vp]
+    L.af_forward_frames.restype = i32
+    L.af_forward_frames.argtypes = [vp, vp, i32, C.POINTER(i64), i32, f32p, f32p, vp]
     L.af_infer_u8.restype = i32
     L.af_infer_u8.argtypes = [vp, vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), f32p, f32p, f32p, vp]
     L.af_infer_u8_host.restype = i32

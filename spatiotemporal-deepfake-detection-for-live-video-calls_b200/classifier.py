@@ -128,3 +128,23 @@ class Classifier(nn.Module):
         self.network.load_state_dict(own, strict=False)
         self._warped_network.refold()
         return ok, redundant, missing, mismatch
+
+
+class RGBBackboneB200(nn.Module):
+    """Backbone adapter for dualrun's `AltFreezingRGBEncoder(backbone, out_dim=2048)`
+    (dualrun/model/dual_rgb.py:9-44): frames `[B, T, 3, H, W]` (normalised RGB) -> per-frame features
+    `[B, T/2, 2048]` from the B200 trunk.  The reference never ships such an adapter; the
+    semantics chosen here make `encoder(x)` (temporal mean) equal the pooled 2048-d input of `head.projection`."""
+
+    def __init__(self, classifier: "Classifier"):
+        super().__init__()
+        object.__setattr__(self, "_clf", classifier)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 5 or x.shape[2] != 3:
+            raise ValueError("RGBBackboneB200 takes frames [B,T,3,H,W], got %s" % (tuple(x.shape),))
+        eng = self._clf._warped_network
+        dev = x.device if x.device.index is not None else torch.device("cuda", torch.cuda.current_device())
+        logits, feats = eng.engine_for(dev).forward_frames(x.permute(0, 2, 1, 3, 4))     # strided NCTHW view
+        return feats

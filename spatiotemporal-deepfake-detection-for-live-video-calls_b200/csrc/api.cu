@@ -176,6 +176,7 @@ struct af_engine {
   int conv_impl = 0;       // 0 auto, 1 force SIMT, 2 force UMMA where supported
   bool keep_stages = false;
   int sm_limit = 0;              // CTAs per conv launch (0 = all SMs)
+  float* frame_feat_out = nullptr;   // set by af_forward_frames for the duration of one call
   bool pooled_already = false;   // the previous block's `c` conv already applied the temporal max-pool
   long long launches = 0;
 
@@ -479,6 +480,11 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
                      scores ? scores + g0 : nullptr, s);
     if (rc) return rc;
     trh.done("head avgpool+fc", 0.0, (double)gB * d.elems() * e->esz);
+    if (e->frame_feat_out) {     // per-frame spatial means [gB*T', C]: the same pooling kernel over H*W positions
+      rc = head_launch(x, gB * d.T, d.H * d.W, d.C, e->is_bf16, e->fc_w, e->fc_b,
+                       e->frame_feat_out + (long long)g0 * d.T * e->feat_dim, nullptr, nullptr, nullptr, s);
+      if (rc) return rc;
+    }
   }
   return AF_OK;
 }
@@ -727,6 +733,15 @@ af_status af_forward(af_handle h, const void* clip_dev, int32_t dtype, const int
   if (!r) r = run_trunk(h, batch, feed, logits_dev, nullptr, features_dev, s);
   h->launches += g_launches - before;
   return (af_status)r;
+}
+
+af_status af_forward_frames(af_handle h, const void* clip_dev, int32_t dtype, const int64_t strides[5], int32_t batch,
+                            float* logits_dev, float* frame_features_dev, void* stream) {
+  if (!h || !frame_features_dev) { set_error("af_forward_frames: null pointer"); return AF_ERR_INVALID; }
+  h->frame_feat_out = frame_features_dev;
+  af_status rc = af_forward(h, clip_dev, dtype, strides, batch, logits_dev, nullptr, stream);
+  h->frame_feat_out = nullptr;
+  return rc;
 }
 
 af_status af_infer_u8(af_handle h, const uint8_t* clips_dev, int32_t batch, const float mean255[3],

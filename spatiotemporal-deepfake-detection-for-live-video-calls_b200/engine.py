@@ -100,6 +100,25 @@ class Engine:
                                          self._stream()), "af_forward")
         return (logits, feats) if return_features else logits
 
+    def forward_frames(self, x: torch.Tensor):
+        """x as in forward() -> (logits [B,1], frame features [B, T/2, 2048]): per-frame spatial means of the last
+        stage, the `backbone(x) -> [B,T',D]` contract of dualrun's AltFreezingRGBEncoder."""
+        if x.dim() != 5 or tuple(x.shape[1:]) != (3, self.clip_t, self.clip_s, self.clip_s):
+            raise ValueError("afb200 engine takes [B,3,%d,%d,%d] clips, got %s" % (self.clip_t, self.clip_s, self.clip_s, tuple(x.shape)))
+        if x.dtype not in _DTYPES:
+            x = x.float()
+        B = x.shape[0]
+        logits = torch.empty((B, 1), dtype=torch.float32, device=self.device)
+        feats = torch.empty((B, self.clip_t // 2, 2048), dtype=torch.float32, device=self.device)
+        strides = (C.c_int64 * 5)(*x.stride())
+        with torch.cuda.device(self.device):
+            for b0 in range(0, B, self.max_batch):
+                nb = min(self.max_batch, B - b0)
+                check(self._L.af_forward_frames(self._h, C.c_void_p(x[b0:b0 + nb].data_ptr()), _DTYPES[x.dtype], strides, nb,
+                                                C.c_void_p(logits[b0:].data_ptr()), C.c_void_p(feats[b0:].data_ptr()),
+                                                self._stream()), "af_forward_frames")
+        return logits, feats
+
     def infer_u8(self, clips: torch.Tensor, return_features: bool = False):
         """clips: u8 [B,T,S,S,3] RGB on the device -> (logits [B], scores [B])."""
         assert clips.dtype == torch.uint8 and clips.is_contiguous() and clips.device == self.device

@@ -415,3 +415,25 @@ def test_bad_arguments_are_reported_not_crashed(dev, state_dict):
         afb200.conv_ndhwc(torch.zeros(1, 2, 8, 8, 6, device=dev), torch.zeros(64, 6, 1, 1, 1), torch.zeros(64),
                           (1, 1, 1), (0, 0, 0), True)          # cin % 4 != 0
     eng.close()
+
+
+def test_rgb_backbone_adapter_frame_features(dev, state_dict, clips_u8, oracle_out):
+    """BASELINE config 5 / SURVEY A13: the AltFreezingRGBEncoder contract — backbone([B,T,3,H,W]) -> [B,T',D], whose
+    (masked) temporal mean is the pooled feature.  Oracle: spatial mean of the oracle's last stage."""
+    x, o_logits, o_stages = oracle_out
+    clf = afb200.Classifier(precision="fp32", max_batch=2).to(dev).eval()
+    clf.load_state_dict_tolerant(state_dict)
+    backbone = afb200.RGBBackboneB200(clf)
+    frames = x[:2].permute(0, 2, 1, 3, 4).contiguous().to(dev)           # [B,T,3,H,W]
+    zt = backbone(frames)
+    assert tuple(zt.shape) == (2, 16, 2048)
+    want = o_stages[4][:2].mean(dim=(3, 4)).permute(0, 2, 1)             # [B,16,2048]
+    assert (zt.cpu() - want).abs().max().item() <= 1e-4
+    # AltFreezingRGBEncoder.forward: masked temporal mean (dual_rgb.py:37-44)
+    pooled = zt.mean(dim=1)
+    assert (pooled.cpu() - o_stages[5][:2]).abs().max().item() <= 1e-4
+    mask = torch.zeros(2, 16, dtype=torch.bool, device=dev)
+    mask[:, 8:] = True
+    valid = (~mask).float()
+    w = (valid / valid.clamp_min(1e-6).sum(dim=1, keepdim=True)).unsqueeze(-1)
+    assert ((zt * w).sum(dim=1).cpu() - want[:, :8].mean(dim=1)).abs().max().item() <= 1e-4
