@@ -75,15 +75,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_from=None, t_to=None):
+        """Summarise the samples that arrived in [t_from, t_to] (wall clock); all samples if no window given."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if t_from is not None and not (t_from <= ts <= t_to):
+                continue
             try:
                 sm.append(float(r[1])); mx = float(r[2])
             except Exception:
@@ -235,6 +238,9 @@ def run_ours(args):
         cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "%d clips, batch 1 each (cv2.warpAffine crop + normalise + fp32 forward of the oracle port), after 1 warm-up clip" % n}
 
+    sampler = ClockSampler(local_rank)      # started early so nvidia-smi is already streaming when the load begins
+    if rank == 0:
+        sampler.start()
     eng = afb200.Engine(sd, device=local_rank, max_batch=B, precision=args.precision)
     if args.chunk_front:
         eng.set_option("chunk_front", args.chunk_front)
@@ -251,9 +257,7 @@ def run_ours(args):
 
     # clocks are sampled from the warm-up on (the GPU is under the same load) so that short timed regions
     # still get samples; the timed region itself is bracketed below
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    t_load0 = time.time()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -273,7 +277,14 @@ def run_ours(args):
         dist.barrier()
     ms = e0.elapsed_time(e1)
     ms = parallel.max_over_ranks(ms, dev)
-    clocks = sampler.stop() if rank == 0 else None
+    # nvidia-smi samples every 50 ms: if warm-up + timed region were shorter than ~0.6 s keep the same load running
+    # (untimed) until enough samples exist, so `clocks` always describes the GPU under this workload
+    extra = 0
+    while rank == 0 and time.time() - t_load0 < 0.6 and extra < 200:
+        eng.crop_infer(fd, cg, B); torch.cuda.synchronize(); extra += 1      # no collective: rank 0 only
+    clocks = sampler.stop(t_load0, time.time()) if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed region + %d untimed steps of the same load" % extra
     launches = eng.launch_count - launches0
     eng.set_option("profile_events", 0)
     conv_ms = eng.get_stat("conv_umma_ms")
