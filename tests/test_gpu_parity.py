@@ -437,3 +437,15 @@ def test_rgb_backbone_adapter_frame_features(dev, state_dict, clips_u8, oracle_o
     valid = (~mask).float()
     w = (valid / valid.clamp_min(1e-6).sum(dim=1, keepdim=True)).unsqueeze(-1)
     assert ((zt * w).sum(dim=1).cpu() - want[:, :8].mean(dim=1)).abs().max().item() <= 1e-4
+
+
+def test_feature_export_infer_clip(dev, state_dict, clips_u8, oracle_out):
+    from afb200 import features
+    x, o_logits, o_stages = oracle_out
+    eng = afb200.Engine(state_dict, max_batch=1, precision="fp32")
+    logits, feat, score = features.infer_clip(eng, clips_u8[1])
+    assert tuple(logits.shape) == (1, 1) and tuple(feat.shape) == (1, 1, 1, 1, 2048) and tuple(score.shape) == (1,)
+    assert abs(float(logits) - float(o_logits[1, 0])) <= 1e-3
+    assert (feat.view(-1) - o_stages[5][1]).abs().max().item() <= 1e-3
+    assert abs(float(score) - float(torch.sigmoid(o_logits[1, 0]))) <= 1e-4
+    eng.close()

@@ -59,3 +59,19 @@ def test_pool_methods_match_numpy_definitions():
     # stability penalty only for unstable series with a moderate median
     assert live.score_with_stability(tight, 0.7) == 0.7
     assert live.score_with_stability(s, 0.7) < 0.7
+
+
+def test_feature_npz_record_schema(tmp_path):
+    """Wire format of altfreezing/feature.py:198-207 (consumed by dualrun): keys, dtypes, shapes."""
+    import torch
+    from afb200 import features
+    path = features.clip_npz_name(str(tmp_path), "vid", 3, 7)
+    assert path.endswith("vid_tid3_c00007.npz")
+    features.save_clip_npz(path, torch.tensor([[0.25]]), torch.arange(2048.).view(1, 1, 1, 1, -1), torch.tensor([0.56]),
+                           y=1, tid=3, clip_idx=7, video_rel="fake/vid.mp4")
+    z = np.load(path)
+    assert set(z.files) == {"feat", "logits", "score", "y", "tid", "clip_idx", "video_rel"}
+    assert z["feat"].dtype == np.float16 and z["feat"].shape == (1, 1, 1, 1, 2048)
+    assert z["logits"].dtype == np.float16 and z["logits"].shape == (1, 1)
+    assert abs(float(z["score"]) - 0.56) < 1e-6 and int(z["y"]) == 1 and int(z["tid"]) == 3 and int(z["clip_idx"]) == 7
+    assert str(z["video_rel"]) == "fake/vid.mp4"
