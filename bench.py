@@ -277,6 +277,8 @@ def run_ours(args):
         dist.barrier()
     ms = e0.elapsed_time(e1)
     ms = parallel.max_over_ranks(ms, dev)
+    launches = eng.launch_count - launches0      # close the counting window with the timed region
+    eng.set_option("profile_events", 0)
     # nvidia-smi samples every 50 ms: if warm-up + timed region were shorter than ~0.6 s keep the same load running
     # (untimed) until enough samples exist, so `clocks` always describes the GPU under this workload
     extra = 0
@@ -285,8 +287,6 @@ def run_ours(args):
     clocks = sampler.stop(t_load0, time.time()) if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "warm-up + timed region + %d untimed steps of the same load" % extra
-    launches = eng.launch_count - launches0
-    eng.set_option("profile_events", 0)
     conv_ms = eng.get_stat("conv_umma_ms")
     conv_flops = eng.get_stat("conv_umma_flops")
     conv_n = eng.get_stat("conv_umma_launches")

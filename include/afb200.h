@@ -177,6 +177,15 @@ af_status af_conv_ndhwc(const void* x_dev, const af_conv_desc* conv_host, const 
                         void* y_dev, int32_t batch, int32_t t, int32_t hgt, int32_t wid,
                         int32_t relu, int32_t precision, int32_t impl, void* stream);
 
+/* Test/diagnostic entry for the fused projection shortcut of a block's first ResBlock
+ * (resnet_helper.py:411-423,438-441: relu(branch1_bn(branch1(x)) + branch2(x))): the pointwise
+ * `conv` over x_dev [B,t,hgt,wid,cin] plus the pointwise, spatially strided `shortcut` over
+ * x2_dev [B,t,hgt2,wid2,cin2], accumulated in one tcgen05 GEMM (bf16 NDHWC in/out, fp32 accumulate). */
+af_status af_conv_shortcut_ndhwc(const void* x_dev, const af_conv_desc* conv_host, const void* x2_dev,
+                                 const af_conv_desc* shortcut_host, void* y_dev, int32_t batch, int32_t t,
+                                 int32_t hgt, int32_t wid, int32_t hgt2, int32_t wid2, int32_t relu,
+                                 void* stream);
+
 /* Copy intermediate activations of the LAST af_forward/af_infer call out for stage
  * parity tests: which = 1..5 (s1..s5 outputs) as fp32 NCTHW [B,C,T,H,W] into out_dev.
  * Requires option "keep_stages" = 1 (costs extra memory). */

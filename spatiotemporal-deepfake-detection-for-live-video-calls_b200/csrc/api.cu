@@ -169,6 +169,7 @@ struct af_engine {
   int stem_direct = 0;       // 1 usable, 0 not tried / disabled, -1 tensor-map encode refused
   int stem = 0;
   std::vector<af_block_desc> blocks;
+  std::vector<float*> fused_bias;   // per block: bias(c) + bias(branch1) for the fused projection shortcut (or null)
   float* fc_w = nullptr;
   float fc_b = 0.f;
   int feat_dim = 0;
@@ -229,11 +230,19 @@ struct ProfRec {
   }
 };
 
+// A projection shortcut fused into the conv it is added to (bf16 tcgen05 path only): conv `L` over `x`,
+// both folded biases pre-summed in `bias`.
+struct FusedShortcut { const ConvLayer* L; const void* x; Dims in; const float* bias; };
+
 static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, long long xsB, long long xsT,
                     long long xsH, long long xsW, int B, const void* res, void* y, bool relu, cudaStream_t s,
-                    int impl_override = -1, int pool_hw = 0, int pool_t = 0) {
+                    int impl_override = -1, int pool_hw = 0, int pool_t = 0, const FusedShortcut* sc = nullptr) {
   ConvProblem p;
-  p.x = x; p.bias = L.bias; p.res = res; p.y = y;
+  p.x = x; p.bias = sc ? sc->bias : L.bias; p.res = res; p.y = y;
+  if (sc) {
+    p.x2 = sc->x; p.w2 = sc->L->w_umma; p.Cin2 = sc->L->cin_p;
+    p.T2 = sc->in.T; p.H2 = sc->in.H; p.W2 = sc->in.W; p.sh2 = sc->L->sh; p.sw2 = sc->L->sw;
+  }
   p.B = B; p.Ti = in.T; p.Hi = in.H; p.Wi = in.W; p.Cin = L.cin_p;
   p.xsB = xsB; p.xsT = xsT; p.xsH = xsH; p.xsW = xsW;
   Dims o = conv_out(L, in);
@@ -250,8 +259,10 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
   int rc;
   const char* which = "simt";
   const double Kd = (double)L.kt * L.kh * L.kw * L.cin_p;
-  const double conv_flops = 2.0 * (double)p.M * L.cout * Kd;
-  const double conv_bytes = ((double)B * in.elems() + (double)p.M * L.cout * (res ? 2 : 1) + Kd * L.cout) * (is_bf16 ? 2.0 : 4.0);
+  const double K2d = sc ? (double)sc->L->cin_p : 0.0;
+  const double conv_flops = 2.0 * (double)p.M * L.cout * (Kd + K2d);
+  const double conv_bytes = ((double)B * in.elems() + (sc ? (double)B * sc->in.elems() : 0.0) +
+                             (double)p.M * L.cout * (res ? 2 : 1) + (Kd + K2d) * L.cout) * (is_bf16 ? 2.0 : 4.0);
   ProfRec prec(e, s);
   p.w = L.w_umma;
   if (pool_hw && !(is_bf16 && (impl == 0 || impl == 3) && conv_rows_supported(p))) {
@@ -262,7 +273,14 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
     set_error("fused temporal max-pool needs the pointwise tcgen05 kernel");
     return AF_ERR_INVALID;
   }
-  if (!pool_t && is_bf16 && (impl == 0 || impl == 3) && conv_rows_supported(p)) {
+  if (sc && !(is_bf16 && impl != 1 && impl != 3 && impl != 6 && conv_umma_supported(p))) {
+    set_error("fused projection shortcut needs the pointwise tcgen05 kernel");
+    return AF_ERR_INVALID;
+  }
+  if (sc) {
+    rc = conv_umma_launch(p, s);
+    which = "umma";
+  } else if (!pool_t && is_bf16 && (impl == 0 || impl == 3) && conv_rows_supported(p)) {
     rc = conv_rows_launch(p, s);
     which = "urows";
   } else if (!pool_t && is_bf16 && (impl == 0 || impl == 6) && conv_tsweep_supported(p)) {
@@ -281,8 +299,8 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
   prec.done(which[0] == 'u' ? 0 : 1, conv_flops, conv_bytes);
   if (OpTrace::enabled()) {
     char nm[128];
-    snprintf(nm, sizeof(nm), "conv %s k%dx%dx%d s%d M=%lld N=%d K=%d%s", which, L.kt, L.kh, L.kw, L.sh, p.M, L.cout,
-             (int)Kd, res ? " +res" : "");
+    snprintf(nm, sizeof(nm), "conv %s k%dx%dx%d s%d M=%lld N=%d K=%d%s%s", which, L.kt, L.kh, L.kw, L.sh, p.M, L.cout,
+             (int)(Kd + K2d), res ? " +res" : "", sc ? " +shortcut" : "");
     tr.done(nm, conv_flops, conv_bytes);
   }
   return rc;
@@ -332,10 +350,26 @@ static int run_blocks(af_engine* e, int b_begin, int b_end, const void*& x, Dims
     if (freeb.size() < 4) { set_error("internal: scratch exhausted"); return AF_ERR_INVALID; }
     void *ya = freeb[0], *yb = freeb[1], *ysc = freeb[2], *yout = freeb[3];
     const void* shortcut = x;
+    // Projection shortcuts are not run as convs of their own on the bf16 engine: their channel blocks are
+    // accumulated into the block's `c` conv (one GEMM over K = Cin_c + Cin_x), which saves writing and
+    // re-reading the widest tensor of the stage.
+    static const bool no_scfuse = getenv("AFB200_NO_FUSED_SHORTCUT") != nullptr;
+    FusedShortcut fsc = {nullptr, nullptr, d, nullptr};
     if (blk.branch1 >= 0) {
-      int rc = dense_conv(e, blk.branch1, x, d, B, nullptr, ysc, false, s);
-      if (rc) return rc;
-      shortcut = ysc;
+      const ConvLayer& L1 = e->convs[blk.branch1];
+      const ConvLayer& Lc1 = e->convs[blk.c];
+      const bool fuse_sc = e->is_bf16 && e->conv_impl == 0 && !no_scfuse && bi < (int)e->fused_bias.size() &&
+                           e->fused_bias[bi] && L1.kt == 1 && L1.kh == 1 && L1.kw == 1 && L1.st == 1 &&
+                           L1.cin_p % 64 == 0 && Lc1.kt == 1 && Lc1.kh == 1 && Lc1.kw == 1 && Lc1.st == 1 &&
+                           Lc1.sh == 1 && Lc1.sw == 1;
+      if (fuse_sc) {
+        fsc.L = &L1; fsc.x = x; fsc.in = d; fsc.bias = e->fused_bias[bi];
+        shortcut = nullptr;
+      } else {
+        int rc = dense_conv(e, blk.branch1, x, d, B, nullptr, ysc, false, s);
+        if (rc) return rc;
+        shortcut = ysc;
+      }
     }
     int rc = dense_conv(e, blk.a, x, d, B, nullptr, ya, true, s);
     if (rc) return rc;
@@ -346,12 +380,13 @@ static int run_blocks(af_engine* e, int b_begin, int b_end, const void*& x, Dims
     // fuse the next block's temporal max-pool into this `c` conv's epilogue when possible
     static const bool no_tfuse = getenv("AFB200_NO_FUSED_TPOOL") != nullptr;
     const ConvLayer& Lc = e->convs[blk.c];
-    const bool fuse_t = e->is_bf16 && e->conv_impl == 0 && !e->keep_stages && !no_tfuse && bi + 1 < (int)e->blocks.size() &&
+    const bool fuse_t = e->is_bf16 && e->conv_impl == 0 && !e->keep_stages && !no_tfuse && !fsc.L && bi + 1 < (int)e->blocks.size() &&
                         e->blocks[bi + 1].temporal_pool_before && (db.T % 2 == 0) && ((db.H * db.W) % 64 == 0) &&
                         Lc.kt == 1 && Lc.kh == 1 && Lc.kw == 1 && Lc.sh == 1 && Lc.sw == 1 && Lc.st == 1;
     {
       const long long sW = db.C, sH = (long long)db.W * db.C, sT = sH * db.H, sB = sT * db.T;
-      rc = run_conv(e, Lc, yb, db, sB, sT, sH, sW, B, shortcut, yout, true, s, -1, 0, fuse_t ? 1 : 0);
+      rc = run_conv(e, Lc, yb, db, sB, sT, sH, sW, B, shortcut, yout, true, s, -1, 0, fuse_t ? 1 : 0,
+                    fsc.L ? &fsc : nullptr);
     }
     if (rc) return rc;
     d = conv_out(e->convs[blk.c], db);
@@ -403,6 +438,7 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
   for (int g0 = 0; g0 < B; g0 += e->cb_back) {
     const int gB = (B - g0) < e->cb_back ? (B - g0) : e->cb_back;
     Dims dg = {0, 0, 0, 0};
+    const void* xg = e->gbuf;
     for (int f0 = g0; f0 < g0 + gB; f0 += e->cb_front) {
       const int fB = (g0 + gB - f0) < e->cb_front ? (g0 + gB - f0) : e->cb_front;
       const char* xin = (const char*)e->clip.base + (long long)f0 * e->clip.sB * e->esz;
@@ -463,12 +499,17 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
       int stage_no = 1;
       rc = run_blocks(e, 0, split, x, d, fB, e->fbuf, f0, stage_no, s);
       if (rc) return rc;
-      // hand the chunk to the group buffer of the back part
+      // hand the chunk to the back part: through the group buffer when several front chunks feed one back
+      // group, directly (no copy) when the chunk IS the group
       dg = d;
-      AFB_CUDA(cudaMemcpyAsync((char*)e->gbuf + (long long)(f0 - g0) * d.elems() * e->esz, x,
-                               (size_t)fB * d.elems() * e->esz, cudaMemcpyDeviceToDevice, s));
+      if (fB == gB) {
+        xg = x;
+      } else {
+        AFB_CUDA(cudaMemcpyAsync((char*)e->gbuf + (long long)(f0 - g0) * d.elems() * e->esz, x,
+                                 (size_t)fB * d.elems() * e->esz, cudaMemcpyDeviceToDevice, s));
+      }
     }
-    const void* x = e->gbuf;
+    const void* x = xg;
     Dims d = dg;
     int stage_no = 1;
     for (int bi = 0; bi < split; ++bi) stage_no += is_stage_end(e, bi) ? 1 : 0;
@@ -557,6 +598,8 @@ af_status af_destroy(af_handle h) {
   for (auto& L : h->convs) free_layer(L);
   free_layer(h->stem_u);
   if (h->stem_w35) cudaFree(h->stem_w35);
+  for (float* fb : h->fused_bias)
+    if (fb) cudaFree(fb);
   free_workspace(h);
   if (h->fc_w) cudaFree(h->fc_w);
   if (h->clip_raw) cudaFree(h->clip_raw);
@@ -603,6 +646,16 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
     }
   }
   e->blocks.assign(w->blocks, w->blocks + w->n_blocks);
+  e->fused_bias.assign(w->n_blocks, nullptr);
+  for (int bi = 0; bi < w->n_blocks && e->is_bf16; ++bi) {
+    const af_block_desc& blk = w->blocks[bi];
+    if (blk.branch1 < 0 || w->convs[blk.branch1].cout != w->convs[blk.c].cout) continue;
+    const int n = w->convs[blk.c].cout;
+    std::vector<float> sum(n);
+    for (int i = 0; i < n; ++i) sum[i] = w->convs[blk.c].bias[i] + w->convs[blk.branch1].bias[i];
+    AFB_CUDA(cudaMalloc(&e->fused_bias[bi], n * sizeof(float)));
+    AFB_CUDA(cudaMemcpy(e->fused_bias[bi], sum.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  }
   AFB_CUDA(cudaMalloc(&e->fc_w, w->feature_dim * sizeof(float)));
   AFB_CUDA(cudaMemcpy(e->fc_w, w->fc_weight, w->feature_dim * sizeof(float), cudaMemcpyHostToDevice));
   // padded clip buffer: T+4 frames, S+6 rows, S+8 columns, 4 channels; pads stay zero forever
@@ -874,6 +927,49 @@ af_status af_conv_ndhwc(const void* x_dev, const af_conv_desc* conv_host, const 
     }
   }
   free_layer(L);
+  return (af_status)rc;
+}
+
+af_status af_conv_shortcut_ndhwc(const void* x_dev, const af_conv_desc* conv_host, const void* x2_dev,
+                                 const af_conv_desc* shortcut_host, void* y_dev, int32_t batch, int32_t t, int32_t hgt,
+                                 int32_t wid, int32_t hgt2, int32_t wid2, int32_t relu, void* stream) {
+  if (!x_dev || !conv_host || !x2_dev || !shortcut_host || !y_dev || batch <= 0) {
+    set_error("af_conv_shortcut_ndhwc: invalid arguments");
+    return AF_ERR_INVALID;
+  }
+  if (conv_host->cin % 64 != 0 || shortcut_host->cin % 64 != 0 || conv_host->cout % 64 != 0 ||
+      shortcut_host->cout != conv_host->cout) {
+    set_error("af_conv_shortcut_ndhwc: needs cin %% 64 == 0 on both convs and equal cout %% 64 == 0");
+    return AF_ERR_INVALID;
+  }
+  int rc = conv_umma_init();
+  if (rc) return (af_status)rc;
+  ConvLayer L, L2;
+  float* bias = nullptr;
+  rc = upload_layer(*conv_host, true, L);
+  if (!rc) rc = upload_layer(*shortcut_host, true, L2);
+  if (!rc) {
+    std::vector<float> sum(conv_host->cout);
+    for (int i = 0; i < conv_host->cout; ++i) sum[i] = conv_host->bias[i] + shortcut_host->bias[i];
+    if (cudaMalloc(&bias, sum.size() * sizeof(float)) != cudaSuccess ||
+        cudaMemcpy(bias, sum.data(), sum.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("af_conv_shortcut_ndhwc: bias upload failed");
+      rc = AF_ERR_CUDA;
+    }
+  }
+  if (!rc) {
+    Dims in = {t, hgt, wid, L.cin_p};
+    const long long sW = in.C, sH = (long long)in.W * in.C, sT = sH * in.H, sB = sT * in.T;
+    FusedShortcut sc = {&L2, x2_dev, Dims{t, hgt2, wid2, L2.cin_p}, bias};
+    rc = run_conv(nullptr, L, x_dev, in, sB, sT, sH, sW, batch, nullptr, y_dev, relu != 0, (cudaStream_t)stream, 2, 0, 0, &sc);
+    if (!rc && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+      set_error("af_conv_shortcut_ndhwc: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = AF_ERR_CUDA;
+    }
+  }
+  if (bias) cudaFree(bias);
+  free_layer(L);
+  free_layer(L2);
   return (af_status)rc;
 }
 

@@ -25,6 +25,12 @@ struct ConvProblem {
   long long M;         // B*To*Ho*Wo
   int pool_t = 0;      // conv_umma pointwise only: fuse MaxPool3d k=s=[2,1,1] over frame pairs; y is then
                        // [B, To/2, Ho, Wo, Cout] (needs relu, To even, Ho*Wo % 64 == 0)
+  // conv_umma only: a second operand source accumulated into the same output tile — the block's projection
+  // shortcut (pointwise conv of stride [1,sh2,sw2] over the block input, resnet_helper.py:411-423) fused into
+  // its `c` conv: y = relu(conv(x) + conv2(x2) + bias), bias = both folded-BN biases summed by the caller.
+  const void* x2 = nullptr;     // dense NDHWC [B, T2, H2, W2, Cin2]
+  const void* w2 = nullptr;     // bf16 [Cout][Cin2]
+  int Cin2 = 0, T2 = 0, H2 = 0, W2 = 0, sh2 = 1, sw2 = 1;
   int pool_hw = 0;     // conv_rows only: fuse MaxPool3d k[1,3,3] s[1,2,2] p[0,1,1]; y is then the
                        // ZERO-INITIALISED pooled tensor [B*To, Ho/2, Wo/2, Cout] (needs relu)
 };

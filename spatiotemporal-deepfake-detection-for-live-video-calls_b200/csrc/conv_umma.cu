@@ -60,6 +60,9 @@ struct UmmaParams {
   int out_per_group;   // output staging slots per epilogue group (1 or 2)
   int pool_t;          // fused temporal max-pool: tile = 64 pixels x 2 consecutive frames (rows r, r+64)
   int hw;              // pixels per frame (pool_t only)
+  // second operand source (fused projection shortcut): a pointwise conv of stride [1,sh2,sw2] over another
+  // tensor, accumulated into the same TMEM tile after the primary taps (0 channel blocks = none)
+  int cblocks2, im2col2, sh2, sw2;
 };
 
 constexpr int MAX_STAGES = 8;
@@ -88,6 +91,7 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_r,
+                 const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_b2,
                  const UmmaParams p) {
   constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -113,6 +117,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int cblocks = p.Cin / BLOCK_K;
   const int num_kb = p.kt * p.kh * p.kw * cblocks;
+  const int num_kb_all = num_kb + p.cblocks2;        // primary taps, then the fused shortcut's channel blocks
   const int stages = p.stages;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
 
@@ -121,6 +126,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tma_prefetch_desc(&tm_b);
     tma_prefetch_desc(&tm_y);
     tma_prefetch_desc(&tm_r);
+    if (p.cblocks2) { tma_prefetch_desc(&tm_a2); tma_prefetch_desc(&tm_b2); }
     for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], (CHUNKS >= 2 ? 2 : 1) * EPI_THREADS); }
     for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
@@ -181,6 +187,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (++dx == p.kw) { dx = 0; if (++dy == p.kh) { dy = 0; ++dt; } }
           }
         }
+        // fused projection shortcut (resnet_helper.py:411-423,438-441): x2[b, to, ho*sh2, wo*sw2, :] . W2^T
+        for (int cb2 = 0; cb2 < p.cblocks2; ++cb2) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if (p.im2col2)
+              tma_load_im2col_5d(sa, &tm_a2, &full_bar[stage], cb2 * BLOCK_K, wo * p.sw2, ho * p.sh2, to, b, 0, 0, 0);
+            else
+              tma_load_2d(sa, &tm_a2, &full_bar[stage], cb2 * BLOCK_K, m0);
+            tma_load_2d(sb, &tm_b2, &full_bar[stage], cb2 * BLOCK_K, n0);
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -198,7 +220,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb_all; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
@@ -365,7 +387,7 @@ int g_max_smem = 0;
 
 template <int BLOCK_N>
 int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const CUtensorMap& tr,
-             UmmaParams up, cudaStream_t s) {
+             const CUtensorMap& ta2, const CUtensorMap& tb2, UmmaParams up, cudaStream_t s) {
   static bool configured[64] = {};            // the opt-in shared-memory size is a per-device function attribute
   auto kern = conv_umma_kernel<BLOCK_N>;
   int dev = 0;
@@ -393,7 +415,7 @@ int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  AFB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ty, tr, up));
+  AFB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ty, tr, ta2, tb2, up));
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;
@@ -412,6 +434,33 @@ int encode_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, 
               (unsigned long long)rows, (unsigned long long)cols, box_rows, (int)r);
     return AF_ERR_CUDA;
   }
+  return AF_OK;
+}
+
+
+// im2col-mode map over a dense NDHWC tensor: 128 output pixels x 64 channels per box; the hardware applies
+// the conv stride, the tap offset and the zero halo.
+int encode_im2col(CUtensorMap* map, const void* x, int B, int Ti, int Hi, int Wi, int Cin, int kt, int kh, int kw,
+                  int st, int sh, int sw, int pt, int ph, int pw) {
+  cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Ti, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)Wi * Cin * 2, (cuuint64_t)Hi * Wi * Cin * 2,
+                           (cuuint64_t)Ti * Hi * Wi * Cin * 2};
+  int lower[3] = {-pw, -ph, -pt};
+  int upper[3] = {pw - (kw - 1), ph - (kh - 1), pt - (kt - 1)};
+  if (g_corner_dhw) { int t0 = lower[0]; lower[0] = lower[2]; lower[2] = t0; t0 = upper[0]; upper[0] = upper[2]; upper[2] = t0; }
+  cuuint32_t es[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)st, 1};
+  CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, lower,
+                               upper, BLOCK_K, BLOCK_M, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeIm2col failed: %d (C=%d W=%d H=%d T=%d B=%d k=%dx%dx%d)", (int)r, Cin, Wi, Hi, Ti, B, kt,
+              kh, kw);
+    return AF_ERR_CUDA;
+  }
+  // CUTLASS (copy_traits_sm90_im2col.hpp) clears bit 21 of descriptor word 1 for tensors
+  // smaller than 128 KiB on drivers <= 13.1 to work around a driver encoding issue.
+  const unsigned long long bytes = (unsigned long long)B * Ti * Hi * Wi * Cin * 2ULL;
+  if (g_driver_version <= 13010 && bytes < 131072ULL) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ULL << 21);
   return AF_OK;
 }
 
@@ -451,6 +500,10 @@ bool conv_umma_supported(const ConvProblem& p) {
     const bool pointwise = p.kt == 1 && p.kh == 1 && p.kw == 1 && p.st == 1 && p.sh == 1 && p.sw == 1;
     if (!pointwise || !p.relu || (p.To & 1) || ((p.Ho * p.Wo) & 63)) return false;
   }
+  if (p.x2) {      // fused projection shortcut: same output grid through a pointwise stride-[1,sh2,sw2] conv of x2
+    if (p.pool_t || p.res || !p.w2 || p.Cin2 <= 0 || p.Cin2 % BLOCK_K != 0) return false;
+    if (p.T2 != p.To || (p.H2 - 1) / p.sh2 + 1 != p.Ho || (p.W2 - 1) / p.sw2 + 1 != p.Wo) return false;
+  }
   return true;
 }
 
@@ -459,13 +512,13 @@ namespace {
 // parameters and the four tensor maps.  The engine's buffers are fixed, so plans are memoised — encoding four
 // tensor maps per conv is most of the host cost of a batch-1 pass.
 struct UmmaPlan {
-  alignas(64) CUtensorMap ta, tb, ty, tr;
+  alignas(64) CUtensorMap ta, tb, ty, tr, ta2, tb2;
   UmmaParams up;
   int bn;
 };
 struct PlanKey {
-  const void *x, *w, *y, *res; const float* bias;
-  int v[20];
+  const void *x, *w, *y, *res, *x2, *w2; const float* bias;
+  int v[26];
   bool operator==(const PlanKey& o) const { return memcmp(this, &o, sizeof(PlanKey)) == 0; }
 };
 struct PlanKeyHash {
@@ -484,9 +537,9 @@ int build_plan(const ConvProblem& p, UmmaPlan& plan);
 int conv_umma_launch(const ConvProblem& p, cudaStream_t s) {
   PlanKey key;
   memset(&key, 0, sizeof(key));
-  key.x = p.x; key.w = p.w; key.y = p.y; key.res = p.res; key.bias = p.bias;
-  const int vals[20] = {p.B, p.Ti, p.Hi, p.Wi, p.Cin, p.To, p.Ho, p.Wo, p.Cout, p.kt, p.kh, p.kw, p.st, p.sh, p.sw,
-                        p.pt, p.ph, p.pw, p.relu, p.pool_t};
+  key.x = p.x; key.w = p.w; key.y = p.y; key.res = p.res; key.bias = p.bias; key.x2 = p.x2; key.w2 = p.w2;
+  const int vals[26] = {p.B, p.Ti, p.Hi, p.Wi, p.Cin, p.To, p.Ho, p.Wo, p.Cout, p.kt, p.kh, p.kw, p.st, p.sh, p.sw,
+                        p.pt, p.ph, p.pw, p.relu, p.pool_t, p.Cin2, p.T2, p.H2, p.W2, p.sh2, p.sw2};
   memcpy(key.v, vals, sizeof(vals));
   auto it = g_plans.find(key);
   if (it == g_plans.end()) {
@@ -498,9 +551,9 @@ int conv_umma_launch(const ConvProblem& p, cudaStream_t s) {
   }
   const UmmaPlan& pl = it->second;
   switch (pl.bn) {
-    case 256: return launch_t<256>(pl.ta, pl.tb, pl.ty, pl.tr, pl.up, s);
-    case 128: return launch_t<128>(pl.ta, pl.tb, pl.ty, pl.tr, pl.up, s);
-    default: return launch_t<64>(pl.ta, pl.tb, pl.ty, pl.tr, pl.up, s);
+    case 256: return launch_t<256>(pl.ta, pl.tb, pl.ty, pl.tr, pl.ta2, pl.tb2, pl.up, s);
+    case 128: return launch_t<128>(pl.ta, pl.tb, pl.ty, pl.tr, pl.ta2, pl.tb2, pl.up, s);
+    default: return launch_t<64>(pl.ta, pl.tb, pl.ty, pl.tr, pl.ta2, pl.tb2, pl.up, s);
   }
 }
 
@@ -528,25 +581,8 @@ int build_plan(const ConvProblem& p, UmmaPlan& plan) {
   up.num_n_tiles = p.Cout / bn;
 
   if (up.im2col) {
-    cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Ti, (cuuint64_t)p.B};
-    cuuint64_t strides[4] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Wi * p.Cin * 2, (cuuint64_t)p.Hi * p.Wi * p.Cin * 2,
-                             (cuuint64_t)p.Ti * p.Hi * p.Wi * p.Cin * 2};
-    int lower[3] = {-p.pw, -p.ph, -p.pt};
-    int upper[3] = {p.pw - (p.kw - 1), p.ph - (p.kh - 1), p.pt - (p.kt - 1)};
-    if (g_corner_dhw) { int t0 = lower[0]; lower[0] = lower[2]; lower[2] = t0; t0 = upper[0]; upper[0] = upper[2]; upper[2] = t0; }
-    cuuint32_t es[5] = {1, (cuuint32_t)p.sw, (cuuint32_t)p.sh, (cuuint32_t)p.st, 1};
-    CUresult r = g_encode_im2col(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(p.x), dims, strides, lower,
-                                 upper, BLOCK_K, BLOCK_M, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("cuTensorMapEncodeIm2col failed: %d (C=%d W=%d H=%d T=%d B=%d k=%dx%dx%d)", (int)r, p.Cin, p.Wi, p.Hi,
-                p.Ti, p.B, p.kt, p.kh, p.kw);
-      return AF_ERR_CUDA;
-    }
-    // CUTLASS (copy_traits_sm90_im2col.hpp) clears bit 21 of descriptor word 1 for tensors
-    // smaller than 128 KiB on drivers <= 13.1 to work around a driver encoding issue.
-    const unsigned long long bytes = (unsigned long long)p.B * p.Ti * p.Hi * p.Wi * p.Cin * 2ULL;
-    if (g_driver_version <= 13010 && bytes < 131072ULL) reinterpret_cast<uint64_t*>(&ta)[1] &= ~(1ULL << 21);
+    int rc = encode_im2col(&ta, p.x, p.B, p.Ti, p.Hi, p.Wi, p.Cin, p.kt, p.kh, p.kw, p.st, p.sh, p.sw, p.pt, p.ph, p.pw);
+    if (rc) return rc;
   } else {
     int rc = encode_2d(&ta, p.x, (uint64_t)p.M, (uint64_t)p.Cin, p.pool_t ? 64 : BLOCK_M, "A");
     if (rc) return rc;
@@ -563,6 +599,20 @@ int build_plan(const ConvProblem& p, UmmaPlan& plan) {
     rc = encode_2d(&ty, p.y, (uint64_t)p.M, (uint64_t)p.Cout, BLOCK_M, "Y");
     if (rc) return rc;
     rc = encode_2d(&tr, p.res ? p.res : p.y, (uint64_t)p.M, (uint64_t)p.Cout, BLOCK_M, "R");
+    if (rc) return rc;
+  }
+
+  // fused projection shortcut: pointwise conv of stride [1,sh2,sw2] over x2 [B,T2,H2,W2,Cin2], weights w2 [Cout][Cin2]
+  up.cblocks2 = 0; up.im2col2 = 0; up.sh2 = up.sw2 = 1;
+  plan.ta2 = plan.ta; plan.tb2 = plan.tb;
+  if (p.x2) {
+    up.cblocks2 = p.Cin2 / BLOCK_K;
+    up.sh2 = p.sh2; up.sw2 = p.sw2;
+    up.im2col2 = (p.sh2 != 1 || p.sw2 != 1) ? 1 : 0;
+    if (up.im2col2) rc = encode_im2col(&plan.ta2, p.x2, p.B, p.T2, p.H2, p.W2, p.Cin2, 1, 1, 1, 1, p.sh2, p.sw2, 0, 0, 0);
+    else rc = encode_2d(&plan.ta2, p.x2, (uint64_t)p.M, (uint64_t)p.Cin2, BLOCK_M, "A2");
+    if (rc) return rc;
+    rc = encode_2d(&plan.tb2, p.w2, (uint64_t)p.Cout, (uint64_t)p.Cin2, (uint32_t)bn, "W2");
     if (rc) return rc;
   }
 

@@ -215,3 +215,35 @@ def conv_ndhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride
                               C.c_void_p(y.data_ptr()), B, T, H, W, int(relu), prec, impl,
                               C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "af_conv_ndhwc")
     return y
+
+
+def _conv_desc(weight: torch.Tensor, bias: torch.Tensor, stride, pad):
+    w = weight.detach().float().cpu().contiguous().numpy()
+    b = bias.detach().float().cpu().contiguous().numpy()
+    d = _lib.AfConvDesc()
+    d.weight, d.bias = w.ctypes.data, b.ctypes.data
+    d.cout, d.cin, d.kt, d.kh, d.kw = w.shape
+    d.st, d.sh, d.sw = stride
+    d.pt, d.ph, d.pw = pad
+    return d, (w, b)
+
+
+def conv_shortcut_ndhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, x2: torch.Tensor,
+                        weight2: torch.Tensor, bias2: torch.Tensor, stride2, relu: bool = True) -> torch.Tensor:
+    """relu(conv1x1x1(x) + conv1x1x1_stride(x2) + both biases) in ONE tcgen05 GEMM — the first ResBlock of a
+    stage with its projection shortcut fused into the `c` conv (test/diagnostic entry af_conv_shortcut_ndhwc).
+    x: bf16 [B,T,Ho,Wo,cin]; x2: bf16 [B,T,H2,W2,cin2] with (H2-1)//sh+1 == Ho; weights [cout,cin,1,1,1]."""
+    L = lib()
+    for t in (x, x2):
+        assert t.is_cuda and t.is_contiguous() and t.dtype == torch.bfloat16
+    B, T, H, W, _ = x.shape
+    d1, keep1 = _conv_desc(weight, bias, (1, 1, 1), (0, 0, 0))
+    d2, keep2 = _conv_desc(weight2, bias2, stride2, (0, 0, 0))
+    y = torch.empty((B, T, H, W, d1.cout), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(L.af_conv_shortcut_ndhwc(C.c_void_p(x.data_ptr()), C.byref(d1), C.c_void_p(x2.data_ptr()), C.byref(d2),
+                                       C.c_void_p(y.data_ptr()), B, T, H, W, x2.shape[2], x2.shape[3], int(relu),
+                                       C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
+              "af_conv_shortcut_ndhwc")
+    del keep1, keep2
+    return y
