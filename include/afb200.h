@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AFB200_VERSION 100
+#define AFB200_VERSION 101
 
 typedef struct af_engine* af_handle;
 
@@ -62,7 +62,34 @@ typedef struct {
   int32_t branch1, a, b, c;
   int32_t temporal_pool_before; /* 1: MaxPool3d [2,1,1] on the block input
                                    (pathway0_pool, video_model_builder.py:474-480,566-568) */
+  int32_t spatial_pool;         /* 1: MaxPool3d((1,2,2)) behind the BatchNorm of conv b and of branch1 — what the
+                                   FTCN-TT plugin puts where the I3D has a spatial stride
+                                   (model/classifier/i3d_temporal_var_fix_dropout_tt_cfg.py:222-267); 0 for i3d_ori */
 } af_block_desc;
+
+/* One pre-norm transformer layer of the FTCN-TT head (model/classifier/time_transformer.py:75-88):
+ * x += to_out(attention(LayerNorm(x)));  x += fc2(GELU(fc1(LayerNorm(x)))).  Host pointers, fp32, nn.Linear layout. */
+typedef struct {
+  const float *ln1_w, *ln1_b;
+  const float* qkv_w;              /* [3*heads*dim_head][dim], no bias (time_transformer.py:37) */
+  const float *out_w, *out_b;      /* [dim][heads*dim_head], [dim] */
+  const float *ln2_w, *ln2_b;
+  const float *fc1_w, *fc1_b;      /* [mlp_dim][dim], [mlp_dim] */
+  const float *fc2_w, *fc2_b;      /* [dim][mlp_dim], [dim] */
+} af_tt_layer;
+
+/* TransformerHead + TimeTransformer (i3d_temporal_var_fix_dropout_tt_cfg.py:126-196, time_transformer.py:219-279):
+ * per-frame spatial means -> `tokens` vectors of `dim` channels, cls token + learned positions, `depth` layers,
+ * LayerNorm + Linear(dim->1) on the cls token. */
+typedef struct {
+  int32_t dim, tokens, heads, dim_head, mlp_dim, depth;
+  const af_tt_layer* layers;
+  const float* cls_token;      /* [dim] */
+  const float* pos_embedding;  /* [tokens+1][dim] */
+  const float *norm_w, *norm_b;
+  const float* fc_w;           /* [dim] */
+  float fc_b;
+} af_tt_head;
 
 /* The whole network: stem conv (+BN+ReLU) + MaxPool3d [1,3,3]/[1,2,2]/[0,1,1]
  * (stem_helper.py:173-178), the blocks, global average pool + Linear(F->1)
@@ -77,6 +104,11 @@ typedef struct {
   float fc_bias;
   int32_t feature_dim;     /* 2048 */
   int32_t clip_t, clip_s;  /* 32, 224 (cfg.clip_size, cfg.imsize; setting/i3d_ori.yaml:20,60) */
+  /* FTCN-TT plugin only (zero / NULL for i3d_ori): */
+  int32_t stem_pool2;        /* 1: MaxPool3d((1,2,2)) between the stem's BatchNorm and its ReLU; the stem conv is then
+                                k[5,1,1] s[1,1,1] (temporal_only_conv on s1.pathway0_stem) */
+  const af_tt_head* tt_head; /* non-NULL: transformer head on the per-frame means of the last stage instead of
+                                average-pool + Linear; fc_weight may then be NULL and feature_dim = tt_head->dim */
 } af_weights;
 
 /* Per-frame source description for the crop kernel: one decoded RGB (or BGR) u8

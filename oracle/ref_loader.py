@@ -14,6 +14,7 @@ minimum surface the reference touches:
   * fvcore.nn.weight_init.c2_msra_fill<- altfreezing/slowfast/utils/weight_init_helper.py:7
   * fvcore.common.file_io.PathManager <- altfreezing/slowfast/utils/logging.py:13
   * simplejson, termcolor             <- slowfast/utils/logging.py:12, altfreezing/utils/logger.py:32
+  * timm.models.layers.trunc_normal_  <- model/classifier/time_transformer.py:217 (FTCN-TT plugin only)
 """
 import copy
 import os
@@ -102,28 +103,38 @@ def _install_stubs():
     mod("fvcore.nn.weight_init", c2_msra_fill=c2_msra_fill)
     mod("simplejson")
     mod("termcolor", colored=lambda s, *a, **k: s)
+    # timm is only used for its truncated-normal initialiser (model/classifier/time_transformer.py:217,253)
+    mod("timm")
+    mod("timm.models")
+    mod("timm.models.layers", trunc_normal_=nn.init.trunc_normal_)
 
 
 _CLASSIFIER_CLS = None
+_CLASSIFIER_SETTING = None
 
 
-def reference_classifier():
-    """Build `PluginLoader.get_classifier("i3d_ori")()` exactly as
-    altfreezing/demo.py:398-404 does (cfg is a process-wide singleton and
-    freeze() is irreversible, so the class is cached)."""
-    global _CLASSIFIER_CLS
+def reference_classifier(setting: str = "i3d_ori.yaml"):
+    """Build `PluginLoader.get_classifier(cfg.classifier_type)()` exactly as
+    altfreezing/demo.py:398-404 does.  `setting` is the yaml under altfreezing/setting/:
+    "i3d_ori.yaml" (AltFreezing I3D) or "ftcn_tt.yaml" (the FTCN-TT plugin).  cfg is a
+    process-wide singleton and freeze() is irreversible, so one process can build one setting only."""
+    global _CLASSIFIER_CLS, _CLASSIFIER_SETTING
     if not reference_available():
         raise RuntimeError("reference tree not present: " + REFERENCE_ROOT)
+    if _CLASSIFIER_CLS is not None and _CLASSIFIER_SETTING != setting:
+        raise RuntimeError("the reference config is frozen on %s in this process; build %s in another process"
+                           % (_CLASSIFIER_SETTING, setting))
     if _CLASSIFIER_CLS is None:
         _install_stubs()
         if ALTFREEZING_DIR not in sys.path:
             sys.path.insert(0, ALTFREEZING_DIR)
         from config import config as cfg
         cfg.init_with_yaml()
-        cfg.update_with_yaml("i3d_ori.yaml")
+        cfg.update_with_yaml(setting)
         cfg.freeze()
         from utils.plugin_loader import PluginLoader
         _CLASSIFIER_CLS = PluginLoader.get_classifier(cfg.classifier_type)
+        _CLASSIFIER_SETTING = setting
     return _CLASSIFIER_CLS().eval()
 
 

@@ -25,14 +25,27 @@ class AfConvDesc(C.Structure):
 
 class AfBlockDesc(C.Structure):
     _fields_ = [("branch1", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("c", C.c_int32),
-                ("temporal_pool_before", C.c_int32)]
+                ("temporal_pool_before", C.c_int32), ("spatial_pool", C.c_int32)]
+
+
+class AfTTLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "out_w", "out_b", "ln2_w", "ln2_b",
+                                          "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+class AfTTHead(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("tokens", C.c_int32), ("heads", C.c_int32), ("dim_head", C.c_int32),
+                ("mlp_dim", C.c_int32), ("depth", C.c_int32), ("layers", C.POINTER(AfTTLayer)),
+                ("cls_token", C.c_void_p), ("pos_embedding", C.c_void_p), ("norm_w", C.c_void_p),
+                ("norm_b", C.c_void_p), ("fc_w", C.c_void_p), ("fc_b", C.c_float)]
 
 
 class AfWeights(C.Structure):
     _fields_ = [("n_convs", C.c_int32), ("convs", C.POINTER(AfConvDesc)),
                 ("stem", C.c_int32), ("n_blocks", C.c_int32), ("blocks", C.POINTER(AfBlockDesc)),
                 ("fc_weight", C.c_void_p), ("fc_bias", C.c_float), ("feature_dim", C.c_int32),
-                ("clip_t", C.c_int32), ("clip_s", C.c_int32)]
+                ("clip_t", C.c_int32), ("clip_s", C.c_int32),
+                ("stem_pool2", C.c_int32), ("tt_head", C.POINTER(AfTTHead))]
 
 
 class AfFrameDesc(C.Structure):

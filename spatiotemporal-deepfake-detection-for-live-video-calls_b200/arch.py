@@ -43,6 +43,7 @@ class ConvSpec:
     stride: Tuple[int, int, int]
     pad: Tuple[int, int, int]
     relu: bool           # ReLU applied right after BN (before any residual)
+    pool2: bool = False  # FTCN-TT: MaxPool3d((1,2,2)) between this conv's BN and what follows
 
 
 @dataclass(frozen=True)
@@ -82,9 +83,76 @@ def block_specs() -> List[BlockSpec]:
     return out
 
 
-def all_conv_specs() -> List[ConvSpec]:
-    specs = [stem_spec()]
+# ---------------------------------------------------------------------------------------------
+# FTCN-TT variant (altfreezing/model/classifier/i3d_temporal_var_fix_dropout_tt_cfg.py with
+# setting/ftcn_tt.yaml + root_setting.yaml: spatial_count 0, keep_stride_count 0, no_time_pool false,
+# transformer.stop_point 5, patch_type time, depth 1, dim -1 -> 1024):
+#   * temporal_only_conv (:207-289) rebuilds every conv whose spatial kernel is > 1 or whose spatial stride is 2
+#     as a k[kt,1,1] s[1,1,1] conv; a removed stride becomes MaxPool3d((1,2,2)) appended to that conv's BatchNorm
+#     (nn.Sequential(bn, pool) -> state_dict keys "...bn.0.*")
+#   * s5 is replaced by nn.Identity (:315-321); the head is TransformerHead(spatial 14, time 16, 1024) (:323-330)
+FTCN_STAGES = 3                      # s2..s4
+TT_TOKENS, TT_DIM, TT_HEADS, TT_DIM_HEAD, TT_MLP, TT_DEPTH = 16, 1024, 16, 64, 2048, 1
+TT_PREFIX = "resnet.head.time_T"
+
+VARIANTS = ("i3d", "ftcn_tt")
+
+
+def ftcn_stem_spec() -> ConvSpec:
+    p = "resnet.s1.pathway0_stem"
+    return ConvSpec(p + ".conv", p + ".bn.0", 3, STEM_WIDTH, (5, 1, 1), (1, 1, 1), (2, 0, 0), True, True)
+
+
+def ftcn_block_specs() -> List[BlockSpec]:
+    out = []
     for blk in block_specs():
+        if blk.stage > FTCN_STAGES + 1:
+            break
+        strided = blk.b.stride[1] == 2
+        b = ConvSpec(blk.b.name, blk.b.bn + (".0" if strided else ""), blk.b.cin, blk.b.cout, (1, 1, 1), (1, 1, 1),
+                     (0, 0, 0), True, strided)
+        br = blk.branch1
+        if br is not None:
+            br = ConvSpec(br.name, br.bn + (".0" if strided else ""), br.cin, br.cout, (1, 1, 1), (1, 1, 1), (0, 0, 0),
+                          False, strided)
+        out.append(BlockSpec(blk.stage, blk.index, blk.a, b, blk.c, br))
+    return out
+
+
+def tt_param_shapes():
+    """state_dict name -> shape of the transformer head (TimeTransformer, time_transformer.py:219-279)."""
+    inner = TT_HEADS * TT_DIM_HEAD
+    shapes = {TT_PREFIX + ".pos_embedding": (1, TT_TOKENS + 1, TT_DIM), TT_PREFIX + ".cls_token": (1, 1, TT_DIM)}
+    for i in range(TT_DEPTH):
+        q = "%s.transformer.layers.%d" % (TT_PREFIX, i)
+        shapes.update({
+            q + ".0.fn.norm.weight": (TT_DIM,), q + ".0.fn.norm.bias": (TT_DIM,),
+            q + ".0.fn.fn.to_qkv.weight": (3 * inner, TT_DIM),
+            q + ".0.fn.fn.to_out.0.weight": (TT_DIM, inner), q + ".0.fn.fn.to_out.0.bias": (TT_DIM,),
+            q + ".1.fn.norm.weight": (TT_DIM,), q + ".1.fn.norm.bias": (TT_DIM,),
+            q + ".1.fn.fn.net.0.weight": (TT_MLP, TT_DIM), q + ".1.fn.fn.net.0.bias": (TT_MLP,),
+            q + ".1.fn.fn.net.3.weight": (TT_DIM, TT_MLP), q + ".1.fn.fn.net.3.bias": (TT_DIM,),
+        })
+    shapes.update({TT_PREFIX + ".mlp_head.0.weight": (TT_DIM,), TT_PREFIX + ".mlp_head.0.bias": (TT_DIM,),
+                   TT_PREFIX + ".mlp_head.1.weight": (1, TT_DIM), TT_PREFIX + ".mlp_head.1.bias": (1,)})
+    return shapes
+
+
+def stem_spec_for(variant: str) -> ConvSpec:
+    return ftcn_stem_spec() if variant == "ftcn_tt" else stem_spec()
+
+
+def block_specs_for(variant: str) -> List[BlockSpec]:
+    return ftcn_block_specs() if variant == "ftcn_tt" else block_specs()
+
+
+def feature_dim_for(variant: str) -> int:
+    return TT_DIM if variant == "ftcn_tt" else FEATURE_DIM
+
+
+def all_conv_specs(variant: str = "i3d") -> List[ConvSpec]:
+    specs = [stem_spec_for(variant)]
+    for blk in block_specs_for(variant):
         if blk.branch1 is not None:
             specs.append(blk.branch1)
         specs += [blk.a, blk.b, blk.c]

@@ -15,7 +15,7 @@ import torch
 from torch import nn
 
 from .engine import Engine
-from .network import I3D8x8Params
+from .network import params_for
 from .weights import strip_checkpoint
 
 log = logging.getLogger("afb200")
@@ -27,10 +27,11 @@ class B200Engine(nn.Module):
     it again would duplicate every key in state_dict, SURVEY.md §8b gotcha (i))."""
 
     def __init__(self, network: nn.Module, precision: str = "bf16", max_batch: int = 32,
-                 clip_t: int = 32, clip_s: int = 224):
+                 clip_t: int = 32, clip_s: int = 224, variant: str = "i3d"):
         super().__init__()
         object.__setattr__(self, "_network", network)
         self.precision, self.max_batch, self.clip_t, self.clip_s = precision, max_batch, clip_t, clip_s
+        self.variant = variant          # "i3d" (i3d_ori plugin) or "ftcn_tt" (i3d_temporal_var_fix_dropout_tt_cfg plugin)
         self._engine: Optional[Engine] = None
         self._engine_device = None
         self._weights_version = None
@@ -52,7 +53,8 @@ class B200Engine(nn.Module):
             self.refold()
             idx = device.index if device.index is not None else torch.cuda.current_device()
             self._engine = Engine(self._network.state_dict(), device=idx, max_batch=self.max_batch,
-                                  precision=self.precision, clip_t=self.clip_t, clip_s=self.clip_s)
+                                  precision=self.precision, clip_t=self.clip_t, clip_s=self.clip_s,
+                                  variant=self.variant)
             self._engine_device, self._weights_version = device, ver
         return self._engine
 
@@ -68,25 +70,32 @@ class B200Engine(nn.Module):
             # feature.py:106-114 hooks the last nn.Linear: feed it the pooled features so the
             # hook observes the same input/output it would see in the reference network.
             _, feats = eng.forward(images, return_features=True)
-            logits = proj(feats.view(feats.shape[0], 1, 1, 1, -1)).view(feats.shape[0], -1)
+            if self.variant == "ftcn_tt":      # mlp_head.1 sees the LayerNorm'd cls token [B, dim]
+                logits = proj(feats).view(feats.shape[0], -1)
+            else:
+                logits = proj(feats.view(feats.shape[0], 1, 1, 1, -1)).view(feats.shape[0], -1)
         else:
             logits = eng.forward(images)
         return {"final_output": logits}
 
     def _projection(self):
         try:
+            if self.variant == "ftcn_tt":
+                return getattr(self._network.resnet.head.time_T.mlp_head, "1")
             return self._network.resnet.head.projection
         except AttributeError:
             return None
 
 
 class Classifier(nn.Module):
-    """Stand-alone equivalent of `PluginLoader.get_classifier("i3d_ori")` on B200."""
+    """Stand-alone equivalent of `PluginLoader.get_classifier("i3d_ori")` (variant "i3d") or of
+    `PluginLoader.get_classifier("i3d_temporal_var_fix_dropout_tt_cfg")` (variant "ftcn_tt") on B200."""
 
-    def __init__(self, precision: str = "bf16", max_batch: int = 32, clip_size: int = 32, imsize: int = 224):
+    def __init__(self, precision: str = "bf16", max_batch: int = 32, clip_size: int = 32, imsize: int = 224,
+                 variant: str = "i3d"):
         super().__init__()
-        self.network = I3D8x8Params()
-        engine = B200Engine(self.network, precision, max_batch, clip_size, imsize)
+        self.network = params_for(variant)
+        engine = B200Engine(self.network, precision, max_batch, clip_size, imsize, variant)
         object.__setattr__(self, "_warped_network", engine)
 
     def forward(self, *inputs, **kwargs):

@@ -173,6 +173,13 @@ struct af_engine {
   float* fc_w = nullptr;
   float fc_b = 0.f;
   int feat_dim = 0;
+  // FTCN-TT plugin: temporal-only stem with a 2x2 max-pool behind its BN, transformer head
+  bool stem_pool2 = false;
+  bool has_tt = false;
+  TTHeadDev tt;
+  std::vector<float*> tt_arrays;     // device copies the TTHeadDev pointers refer to
+  float* tt_ws = nullptr;            // transformer activations for max_batch clips
+  float* tok_ws = nullptr;           // per-frame mean features [max_batch * tokens, dim]
   int cb_front = 32, cb_back = 32;  // clips per chunk: stem..s2 / s3..head (tuned on B200)
   int conv_impl = 0;       // 0 auto, 1 force SIMT, 2 force UMMA where supported
   bool keep_stages = false;
@@ -358,7 +365,7 @@ static int run_blocks(af_engine* e, int b_begin, int b_end, const void*& x, Dims
     if (blk.branch1 >= 0) {
       const ConvLayer& L1 = e->convs[blk.branch1];
       const ConvLayer& Lc1 = e->convs[blk.c];
-      const bool fuse_sc = e->is_bf16 && e->conv_impl == 0 && !no_scfuse && bi < (int)e->fused_bias.size() &&
+      const bool fuse_sc = e->is_bf16 && e->conv_impl == 0 && !no_scfuse && !blk.spatial_pool && bi < (int)e->fused_bias.size() &&
                            e->fused_bias[bi] && L1.kt == 1 && L1.kh == 1 && L1.kw == 1 && L1.st == 1 &&
                            L1.cin_p % 64 == 0 && Lc1.kt == 1 && Lc1.kh == 1 && Lc1.kw == 1 && Lc1.st == 1 &&
                            Lc1.sh == 1 && Lc1.sw == 1;
@@ -377,6 +384,24 @@ static int run_blocks(af_engine* e, int b_begin, int b_end, const void*& x, Dims
     rc = dense_conv(e, blk.b, ya, da, B, nullptr, yb, true, s);
     if (rc) return rc;
     Dims db = conv_out(e->convs[blk.b], da);
+    if (blk.spatial_pool) {
+      // FTCN-TT: MaxPool3d((1,2,2)) behind b_bn and branch1_bn (ReLU and max commute, so the conv epilogue's
+      // ReLU stays where it is).  `ya` is dead after conv b and `yb` after its pooling, so they take the pooled maps.
+      OpTrace tr(s);
+      rc = maxpool_hw2_launch(yb, ya, (long long)B * db.T, db.H, db.W, db.C, e->is_bf16, s);
+      if (rc) return rc;
+      tr.done("maxpool 1x2x2 (b)", 0.0, (double)B * db.elems() * 1.25 * e->esz);
+      db.H /= 2; db.W /= 2;
+      if (shortcut == ysc) {
+        const Dims dsc = conv_out(e->convs[blk.branch1], d);
+        OpTrace tr2(s);
+        rc = maxpool_hw2_launch(ysc, yb, (long long)B * dsc.T, dsc.H, dsc.W, dsc.C, e->is_bf16, s);
+        if (rc) return rc;
+        tr2.done("maxpool 1x2x2 (branch1)", 0.0, (double)B * dsc.elems() * 1.25 * e->esz);
+        shortcut = yb;
+      }
+      void* t0 = ya; ya = yb; yb = t0;             // from here on `yb` names the pooled b output
+    }
     // fuse the next block's temporal max-pool into this `c` conv's epilogue when possible
     static const bool no_tfuse = getenv("AFB200_NO_FUSED_TPOOL") != nullptr;
     const ConvLayer& Lc = e->convs[blk.c];
@@ -427,7 +452,8 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
                      cudaStream_t s) {
   const ConvLayer& stem = e->convs[e->stem];
   const Dims din = {e->T, e->S, e->S, stem.cin_p};
-  const Dims dpre = conv_out(stem, din);
+  Dims dpre = conv_out(stem, din);
+  if (e->stem_pool2) { dpre.H /= 2; dpre.W /= 2; }      // FTCN-TT: MaxPool3d((1,2,2)) behind the stem's BN
   const Dims dpool = {dpre.T, (dpre.H + 2 - 3) / 2 + 1, (dpre.W + 2 - 3) / 2 + 1, dpre.C};
   const int nblk = (int)e->blocks.size();
   const int split = e->split < 0 ? nblk : e->split;
@@ -446,7 +472,16 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
       if (rc) return rc;
       bool fused_pool = false;
       bool stem_done = false;
-      if (e->stem_direct == 1 && e->conv_impl == 0 && (dpre.H % 2 == 0) && (dpre.W % 2 == 0)) {
+      if (e->stem_pool2) {
+        // FTCN-TT stem: conv k[5,1,1] + BN + max-pool 2x2 + ReLU + max-pool 3x3/2 in one kernel
+        OpTrace tr(s);
+        rc = ftcn_stem_launch(e->clip, f0, fB, stem.w_simt, stem.bias, e->fbuf[1], s);
+        if (rc) return rc;
+        tr.done("ftcn stem k5x1x1 +pool2 +pool3/2", 2.0 * (double)fB * e->T * e->S * e->S * 64 * 15,
+                (double)fB * ((double)e->T * e->S * e->S * 4 + dpool.elems()) * e->esz);
+        stem_done = true;
+        fused_pool = true;
+      } else if (e->stem_direct == 1 && e->conv_impl == 0 && (dpre.H % 2 == 0) && (dpre.W % 2 == 0)) {
         // stem conv + BN + ReLU + max-pool in ONE kernel, reading the padded clip directly
         OpTrace tr(s);
         AFB_CUDA(cudaMemsetAsync(e->fbuf[1], 0, (size_t)fB * dpool.elems() * e->esz, s));
@@ -516,12 +551,26 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
     int rc = run_blocks(e, split, nblk, x, d, gB, e->bbuf, g0, stage_no, s);
     if (rc) return rc;
     OpTrace trh(s);
-    rc = head_launch(x, gB, d.T * d.H * d.W, d.C, e->is_bf16, e->fc_w, e->fc_b, e->feat_ws + (long long)g0 * e->feat_dim,
-                     features ? features + (long long)g0 * e->feat_dim : nullptr, logits ? logits + g0 : nullptr,
-                     scores ? scores + g0 : nullptr, s);
-    if (rc) return rc;
-    trh.done("head avgpool+fc", 0.0, (double)gB * d.elems() * e->esz);
-    if (e->frame_feat_out) {     // per-frame spatial means [gB*T', C]: the same pooling kernel over H*W positions
+    if (e->has_tt) {
+      // TransformerHead: AvgPool3d((1,H,W)) per frame -> tokens [gB, T', C] -> TimeTransformer
+      if (d.T != e->tt.tokens || d.C != e->tt.dim) { set_error("tt head: trunk gives %d x %d, head takes %d x %d", d.T, d.C, e->tt.tokens, e->tt.dim); return AF_ERR_INVALID; }
+      rc = spatial_mean_launch(x, gB * d.T, d.H * d.W, d.C, e->is_bf16, e->tok_ws, s);
+      if (!rc)
+        rc = tt_head_launch(e->tt, e->tok_ws, gB, e->tt_ws, features ? features + (long long)g0 * e->feat_dim : nullptr,
+                            logits ? logits + g0 : nullptr, scores ? scores + g0 : nullptr, s);
+      if (rc) return rc;
+      trh.done("head frame means + transformer", 0.0, (double)gB * d.elems() * e->esz);
+    } else {
+      rc = head_launch(x, gB, d.T * d.H * d.W, d.C, e->is_bf16, e->fc_w, e->fc_b, e->feat_ws + (long long)g0 * e->feat_dim,
+                       features ? features + (long long)g0 * e->feat_dim : nullptr, logits ? logits + g0 : nullptr,
+                       scores ? scores + g0 : nullptr, s);
+      if (rc) return rc;
+      trh.done("head avgpool+fc", 0.0, (double)gB * d.elems() * e->esz);
+    }
+    if (e->frame_feat_out && e->has_tt) {         // the transformer's tokens ARE the per-frame means
+      AFB_CUDA(cudaMemcpyAsync(e->frame_feat_out + (long long)g0 * d.T * e->feat_dim, e->tok_ws,
+                               (size_t)gB * d.T * d.C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    } else if (e->frame_feat_out) {     // per-frame spatial means [gB*T', C]: the same pooling kernel over H*W positions
       rc = head_launch(x, gB * d.T, d.H * d.W, d.C, e->is_bf16, e->fc_w, e->fc_b,
                        e->frame_feat_out + (long long)g0 * d.T * e->feat_dim, nullptr, nullptr, nullptr, s);
       if (rc) return rc;
@@ -534,7 +583,8 @@ static int plan_workspace(af_engine* e) {
   // walk the network once for one clip to size the scratch buffers
   const ConvLayer& stem = e->convs[e->stem];
   Dims d = conv_out(stem, Dims{e->T, e->S, e->S, stem.cin_p});
-  long long fmax = d.elems();
+  if (e->stem_pool2) { d.H /= 2; d.W /= 2; }
+  long long fmax = e->stem_pool2 ? 0 : d.elems();      // the FTCN-TT stem kernel never materialises its conv output
   if (e->has_stem_u) {
     const long long u = (long long)e->T * (e->S / 2 + 3) * (e->S / 2) * 64;
     if (u > fmax) fmax = u;
@@ -552,9 +602,13 @@ static int plan_workspace(af_engine* e) {
     if (blk.temporal_pool_before) { d.T /= 2; if (d.elems() > mx) mx = d.elems(); }
     Dims da = conv_out(e->convs[blk.a], d);
     Dims db = conv_out(e->convs[blk.b], da);
-    Dims dc = conv_out(e->convs[blk.c], db);
-    for (long long v : {d.elems(), da.elems(), db.elems(), dc.elems()})
+    long long sc_elems = 0;
+    if (blk.branch1 >= 0) sc_elems = conv_out(e->convs[blk.branch1], d).elems();
+    for (long long v : {d.elems(), da.elems(), db.elems(), sc_elems})
       if (v > mx) mx = v;
+    if (blk.spatial_pool) { db.H /= 2; db.W /= 2; }
+    Dims dc = conv_out(e->convs[blk.c], db);
+    if (dc.elems() > mx) mx = dc.elems();
     if (dc.C != e->convs[blk.c].cout) { set_error("internal dims"); return AF_ERR_INVALID; }
     d = dc;
   }
@@ -602,6 +656,9 @@ af_status af_destroy(af_handle h) {
     if (fb) cudaFree(fb);
   free_workspace(h);
   if (h->fc_w) cudaFree(h->fc_w);
+  for (float* p : h->tt_arrays) cudaFree(p);
+  if (h->tt_ws) cudaFree(h->tt_ws);
+  if (h->tok_ws) cudaFree(h->tok_ws);
   if (h->clip_raw) cudaFree(h->clip_raw);
   if (h->feat_ws) cudaFree(h->feat_ws);
   if (h->u8_stage) cudaFree(h->u8_stage);
@@ -613,6 +670,51 @@ af_status af_destroy(af_handle h) {
   for (auto& r : h->ev_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto ev : h->ev_pool) cudaEventDestroy(ev);
   delete h;
+  return AF_OK;
+}
+
+// Device copy of the FTCN-TT transformer head's parameters.
+static int upload_tt_head(af_engine* e, const af_tt_head& h) {
+  if (h.dim <= 0 || h.tokens <= 0 || h.heads <= 0 || h.dim_head <= 0 || h.mlp_dim <= 0 || h.depth <= 0 || !h.layers ||
+      !h.cls_token || !h.pos_embedding || !h.norm_w || !h.norm_b || !h.fc_w) {
+    set_error("af_create: incomplete transformer head");
+    return AF_ERR_INVALID;
+  }
+  auto up = [&](const float* host, size_t n, const float** dev) -> int {
+    if (!host) { set_error("af_create: transformer head has a null array"); return AF_ERR_INVALID; }
+    float* d = nullptr;
+    AFB_CUDA(cudaMalloc(&d, n * sizeof(float)));
+    e->tt_arrays.push_back(d);
+    AFB_CUDA(cudaMemcpy(d, host, n * sizeof(float), cudaMemcpyHostToDevice));
+    *dev = d;
+    return AF_OK;
+  };
+  TTHeadDev& t = e->tt;
+  t.dim = h.dim; t.tokens = h.tokens; t.heads = h.heads; t.dim_head = h.dim_head; t.mlp_dim = h.mlp_dim; t.fc_b = h.fc_b;
+  const size_t D = h.dim, inner = (size_t)h.heads * h.dim_head, mlp = h.mlp_dim;
+  int rc = up(h.cls_token, D, &t.cls_token);
+  if (!rc) rc = up(h.pos_embedding, (size_t)(h.tokens + 1) * D, &t.pos_embedding);
+  if (!rc) rc = up(h.norm_w, D, &t.norm_w);
+  if (!rc) rc = up(h.norm_b, D, &t.norm_b);
+  if (!rc) rc = up(h.fc_w, D, &t.fc_w);
+  for (int i = 0; i < h.depth && !rc; ++i) {
+    const af_tt_layer& L = h.layers[i];
+    TTLayerDev dl = {};
+    rc = up(L.ln1_w, D, &dl.ln1_w);
+    if (!rc) rc = up(L.ln1_b, D, &dl.ln1_b);
+    if (!rc) rc = up(L.qkv_w, 3 * inner * D, &dl.qkv_w);
+    if (!rc) rc = up(L.out_w, D * inner, &dl.out_w);
+    if (!rc) rc = up(L.out_b, D, &dl.out_b);
+    if (!rc) rc = up(L.ln2_w, D, &dl.ln2_w);
+    if (!rc) rc = up(L.ln2_b, D, &dl.ln2_b);
+    if (!rc) rc = up(L.fc1_w, mlp * D, &dl.fc1_w);
+    if (!rc) rc = up(L.fc1_b, mlp, &dl.fc1_b);
+    if (!rc) rc = up(L.fc2_w, D * mlp, &dl.fc2_w);
+    if (!rc) rc = up(L.fc2_b, D, &dl.fc2_b);
+    if (!rc) t.layers.push_back(dl);
+  }
+  if (rc) return rc;
+  e->has_tt = true;
   return AF_OK;
 }
 
@@ -635,7 +737,21 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
     int rc = upload_layer(w->convs[i], e->is_bf16, e->convs[i]);
     if (rc) return (af_status)rc;
   }
-  if (e->is_bf16 && (e->S % 2 == 0)) {
+  e->stem_pool2 = w->stem_pool2 != 0;
+  if (e->stem_pool2) {
+    const af_conv_desc& sc = w->convs[w->stem];
+    if (sc.cin != 3 || sc.cout != 64 || sc.kt != 5 || sc.kh != 1 || sc.kw != 1 || sc.st != 1 || sc.sh != 1 || sc.sw != 1 ||
+        sc.pt != 2 || sc.ph != 0 || sc.pw != 0 || e->S % 4 != 0) {
+      set_error("af_create: stem_pool2 needs the FTCN-TT stem (3->64, k[5,1,1], s1, p[2,0,0]) and clip_s %% 4 == 0");
+      return AF_ERR_INVALID;
+    }
+  }
+  for (int bi = 0; bi < w->n_blocks; ++bi)
+    if (w->blocks[bi].spatial_pool && w->blocks[bi].branch1 < 0) {
+      set_error("af_create: block %d has spatial_pool but no projection shortcut", bi);
+      return AF_ERR_INVALID;
+    }
+  if (e->is_bf16 && (e->S % 2 == 0) && !e->stem_pool2) {
     int rc = upload_stem_unfolded(w->convs[w->stem], e->stem_u);
     if (rc == AF_OK) e->has_stem_u = true;
     else if (rc != AF_ERR_INVALID) return (af_status)rc;
@@ -656,8 +772,13 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
     AFB_CUDA(cudaMalloc(&e->fused_bias[bi], n * sizeof(float)));
     AFB_CUDA(cudaMemcpy(e->fused_bias[bi], sum.data(), n * sizeof(float), cudaMemcpyHostToDevice));
   }
-  AFB_CUDA(cudaMalloc(&e->fc_w, w->feature_dim * sizeof(float)));
-  AFB_CUDA(cudaMemcpy(e->fc_w, w->fc_weight, w->feature_dim * sizeof(float), cudaMemcpyHostToDevice));
+  if (w->tt_head) {
+    int rc = upload_tt_head(e, *w->tt_head);
+    if (rc) return (af_status)rc;
+  } else {
+    AFB_CUDA(cudaMalloc(&e->fc_w, w->feature_dim * sizeof(float)));
+    AFB_CUDA(cudaMemcpy(e->fc_w, w->fc_weight, w->feature_dim * sizeof(float), cudaMemcpyHostToDevice));
+  }
   // padded clip buffer: T+4 frames, S+6 rows, S+8 columns, 4 channels; pads stay zero forever
   const long long Tp = e->T + 4, Hp = e->S + 6, Wp = e->S + 8;
   const size_t clip_bytes = (size_t)e->max_batch * Tp * Hp * Wp * 4 * e->esz;
@@ -674,6 +795,10 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
   if (rc) return (af_status)rc;
   AFB_CUDA(cudaMalloc(&e->feat_ws, (size_t)e->max_batch * e->feat_dim * sizeof(float)));
   AFB_CUDA(cudaMalloc(&e->out_stage, (size_t)2 * e->max_batch * sizeof(float)));
+  if (e->has_tt) {
+    AFB_CUDA(cudaMalloc(&e->tt_ws, (size_t)tt_head_workspace_floats(e->tt, e->max_batch) * sizeof(float)));
+    AFB_CUDA(cudaMalloc(&e->tok_ws, (size_t)e->max_batch * e->tt.tokens * e->tt.dim * sizeof(float)));
+  }
   return AF_OK;
 }
 
@@ -699,6 +824,7 @@ af_status af_create(af_handle* out, int32_t device, const af_weights* w, int32_t
   e->esz = e->is_bf16 ? 2 : 4;
   e->T = w->clip_t; e->S = w->clip_s; e->max_batch = max_batch;
   e->stem = w->stem; e->fc_b = w->fc_bias; e->feat_dim = w->feature_dim;
+  if (!w->tt_head && !w->fc_weight) { set_error("af_create: fc_weight is NULL and there is no transformer head"); delete e; return AF_ERR_INVALID; }
   af_status rc = create_impl(e, w);
   if (rc != AF_OK) { af_destroy(e); return rc; }
   *out = e;

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace afb {
 
 typedef __nv_bfloat16 bf16;
@@ -85,6 +87,8 @@ int maxpool_temporal_launch(const void* x, void* y, int B, int T, int H, int W, 
 int head_launch(const void* x, int B, int P, int C, bool is_bf16, const float* fc_w, float fc_b,
                 float* features_ws, float* features_out, float* logits, float* scores,
                 cudaStream_t s);
+// mean over P positions: x [N, P, C] -> out fp32 [N, C]
+int spatial_mean_launch(const void* x, int N, int P, int C, bool is_bf16, float* out, cudaStream_t s);
 int ndhwc_to_ncthw_f32_launch(const void* x, float* y, int B, int T, int H, int W, int C,
                               bool is_bf16, cudaStream_t s);
 // crop_pack.cu
@@ -104,5 +108,23 @@ struct ClipGeom { double tfm[6]; int left_top[2]; int canvas_wh[2]; };
 int crop_launch(const FrameDesc* frames, const ClipGeom* geom, int B, int T, int S, int bgr,
                 uint8_t* out_u8, const ClipLayout* dst, const float mean[3], const float stdv[3],
                 cudaStream_t s);
+
+// ftcn.cu (FTCN-TT plugin: fused temporal-only stem, 2x2 max-pool, transformer head; all pointers device memory)
+struct TTLayerDev {
+  const float *ln1_w, *ln1_b, *qkv_w, *out_w, *out_b, *ln2_w, *ln2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+};
+struct TTHeadDev {
+  int dim = 0, tokens = 0, heads = 0, dim_head = 0, mlp_dim = 0;
+  std::vector<TTLayerDev> layers;
+  const float *cls_token = nullptr, *pos_embedding = nullptr, *norm_w = nullptr, *norm_b = nullptr, *fc_w = nullptr;
+  float fc_b = 0.f;
+};
+int ftcn_stem_launch(const ClipLayout& clip, int clip0, int B, const float* w_tap_c_cout, const float* bias, void* y,
+                     cudaStream_t s);
+int maxpool_hw2_launch(const void* x, void* y, long long BT, int H, int W, int C, bool is_bf16, cudaStream_t s);
+long long tt_head_workspace_floats(const TTHeadDev& h, int B);
+// tokens fp32 [B, h.tokens, h.dim] -> logits / sigmoid scores [B], optional normalised cls features [B, h.dim]
+int tt_head_launch(const TTHeadDev& h, const float* tokens, int B, float* ws, float* features_out, float* logits,
+                   float* scores, cudaStream_t s);
 
 }  // namespace afb

@@ -1,0 +1,372 @@
+// Kernels that only the FTCN-TT plugin needs (altfreezing/model/classifier/i3d_temporal_var_fix_dropout_tt_cfg.py):
+// the same slowfast ResNet-50 trunk with every spatial kernel collapsed to 1x1 and every spatial stride replaced by
+// a MaxPool3d((1,2,2)) behind the conv's BatchNorm (temporal_only_conv, :207-289), stopped after s4 (:315-321), and a
+// one-layer pre-norm transformer over the 16 per-frame mean features (TransformerHead :126-196,
+// time_transformer.py:29-88,219-279) instead of the average-pool + Linear head.
+//
+//   ftcn_stem_kernel     Conv3d(3->64, k[5,1,1]) + folded BN + MaxPool3d(1,2,2) + ReLU + MaxPool3d k[1,3,3] s[1,2,2]
+//                        p[0,1,1] in one pass over the padded NDHWC4 clip (the 224x224x64 conv output never exists)
+//   maxpool_hw2_kernel   MaxPool3d((1,2,2)) on NDHWC
+//   tt_* kernels         the transformer head in fp32 (17 tokens x 1024 channels per clip)
+// The trunk's kt x 1 x 1 convs run on the engine's ordinary conv kernels (conv_umma / conv_tsweep / conv_simt).
+#include <math.h>
+
+#include "../../include/afb200.h"
+#include "common.cuh"
+
+namespace afb {
+namespace {
+
+// ------------------------------------------------------------------------------------------------ stem
+constexpr int FS_OX = 8, FS_OY = 4;                    // final (56x56-level) outputs per block
+constexpr int FS_MX = 2 * FS_OX + 1, FS_MY = 2 * FS_OY + 1;   // 112-level map region incl. the 3x3/2 pool halo: 17 x 9
+constexpr int FS_IX = 2 * FS_MX, FS_IY = 2 * FS_MY;    // input pixels under it: 34 x 18
+constexpr int FS_C = 64;
+constexpr int FS_SMEM = 5 * FS_IY * FS_IX * 16 + FS_MY * FS_MX * FS_C * 4;
+
+template <typename T> __device__ __forceinline__ float4 load_px4(const T* p);
+template <> __device__ __forceinline__ float4 load_px4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 load_px4<bf16>(const bf16* p) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&t.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+  return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+}
+template <typename T> __device__ __forceinline__ void store1(T* p, float v);
+template <> __device__ __forceinline__ void store1<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void store1<bf16>(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// clip: padded NDHWC4 (element strides sB,sT,sH,sW; `clip` points at logical (b=0,t=0,y=0,x=0); >= 2 zero frames
+// and >= 3 zero rows / columns around every clip).  w: [5][4][64] fp32 (tap, channel, cout).  y: [B*T, S/4, S/4, 64].
+template <typename T>
+__global__ void __launch_bounds__(256) ftcn_stem_kernel(const T* __restrict__ clip, long long sB, long long sT, long long sH,
+                                                        long long sW, int T_, int S, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, T* __restrict__ y) {
+  extern __shared__ float4 fs_smem[];
+  float4* in_s = fs_smem;                                                   // [5][FS_IY][FS_IX]
+  float* map_s = reinterpret_cast<float*>(fs_smem + 5 * FS_IY * FS_IX);     // [FS_MY*FS_MX][64]
+  const int bt = blockIdx.z, b = bt / T_, t = bt - b * T_;
+  const int ox0 = blockIdx.x * FS_OX, oy0 = blockIdx.y * FS_OY;
+  const int mx0 = 2 * ox0 - 1, my0 = 2 * oy0 - 1;                           // map origin (may be -1)
+  const int ix0 = 2 * mx0, iy0 = 2 * my0;                                   // input origin (may be -2: inside the pads)
+  const T* src = clip + b * sB + (long long)(t - 2) * sT;
+  for (int i = threadIdx.x; i < 5 * FS_IY * FS_IX; i += 256) {
+    const int x = i % FS_IX, r = i / FS_IX, yy = r % FS_IY, f = r / FS_IY;
+    const int gx = ix0 + x, gy = iy0 + yy;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gx < S && gy < S) v = load_px4<T>(src + f * sT + (long long)gy * sH + (long long)gx * sW);
+    in_s[i] = v;
+  }
+  const int c = threadIdx.x & 63, lane4 = threadIdx.x >> 6;
+  float wr[5][3];
+#pragma unroll
+  for (int f = 0; f < 5; ++f)
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) wr[f][ch] = __ldg(w + (f * 4 + ch) * FS_C + c);
+  const float bc = __ldg(bias + c);
+  __syncthreads();
+  const int M2 = S / 2;
+  for (int pos = lane4; pos < FS_MY * FS_MX; pos += 4) {
+    const int my = pos / FS_MX, mx = pos - my * FS_MX;
+    float m = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                      // MaxPool3d((1,2,2)) over the conv + BN outputs
+      const int px = (2 * my + (q >> 1)) * FS_IX + 2 * mx + (q & 1);
+      float a = bc;
+#pragma unroll
+      for (int f = 0; f < 5; ++f) {
+        const float4 v = in_s[f * FS_IY * FS_IX + px];
+        a = fmaf(v.x, wr[f][0], a);
+        a = fmaf(v.y, wr[f][1], a);
+        a = fmaf(v.z, wr[f][2], a);
+      }
+      m = fmaxf(m, a);
+    }
+    // ReLU, then positions outside the 112x112 map must not win the 3x3 max: after ReLU 0 is neutral
+    const bool inside = (unsigned)(my0 + my) < (unsigned)M2 && (unsigned)(mx0 + mx) < (unsigned)M2;
+    map_s[pos * FS_C + c] = inside ? fmaxf(m, 0.f) : 0.f;
+  }
+  __syncthreads();
+  const int O = S / 4;
+#pragma unroll
+  for (int j = 0; j < (FS_OX * FS_OY) / 4; ++j) {
+    const int o = lane4 * ((FS_OX * FS_OY) / 4) + j, oy = o / FS_OX, ox = o - oy * FS_OX;
+    if (oy0 + oy >= O || ox0 + ox >= O) continue;
+    float m = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) m = fmaxf(m, map_s[((2 * oy + dy) * FS_MX + 2 * ox + dx) * FS_C + c]);
+    store1<T>(y + (((long long)bt * O + oy0 + oy) * O + ox0 + ox) * FS_C + c, m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 2x2 max-pool
+template <typename T> struct V16;
+template <> struct V16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ uint4 vmax(uint4 a, uint4 b) {
+    float4 x = *reinterpret_cast<float4*>(&a), z = *reinterpret_cast<float4*>(&b);
+    x.x = fmaxf(x.x, z.x); x.y = fmaxf(x.y, z.y); x.z = fmaxf(x.z, z.z); x.w = fmaxf(x.w, z.w);
+    return *reinterpret_cast<uint4*>(&x);
+  }
+};
+template <> struct V16<bf16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ uint4 vmax(uint4 a, uint4 b) {
+    __nv_bfloat162* x = reinterpret_cast<__nv_bfloat162*>(&a);
+    const __nv_bfloat162* z = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = __hmax2(x[i], z[i]);
+    return a;
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_hw2_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C,
+                                                          long long total) {
+  constexpr int V = V16<T>::N;
+  const int cv = C / V, Ho = H / 2, Wo = W / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int c = (int)(r % cv) * V; r /= cv;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho); r /= Ho;
+    const T* p = x + ((r * H + 2 * ho) * W + 2 * wo) * C + c;
+    uint4 m = *reinterpret_cast<const uint4*>(p);
+    m = V16<T>::vmax(m, *reinterpret_cast<const uint4*>(p + C));
+    m = V16<T>::vmax(m, *reinterpret_cast<const uint4*>(p + (long long)W * C));
+    m = V16<T>::vmax(m, *reinterpret_cast<const uint4*>(p + (long long)W * C + C));
+    *reinterpret_cast<uint4*>(y + ((r * Ho + ho) * Wo + wo) * C + c) = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ transformer head
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();                                    // red may still be read from a previous call
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+  return t;
+}
+
+// x[b, 0, :] = cls + pos[0];  x[b, 1+i, :] = tok[b, i, :] + pos[1+i]          (TimeTransformer.forward :262-266)
+__global__ void tt_embed_kernel(const float* __restrict__ tok, const float* __restrict__ cls, const float* __restrict__ pos,
+                                float* __restrict__ x, int n, int D) {
+  const int row = blockIdx.x, b = row / (n + 1), i = row - b * (n + 1);
+  const float* src = i == 0 ? cls : tok + ((long long)b * n + (i - 1)) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) x[(long long)row * D + d] = src[d] + pos[(long long)i * D + d];
+}
+
+// nn.LayerNorm(D), eps 1e-5, biased variance; one block per row (rows `stride_rows` apart in the input)
+__global__ void tt_layernorm_kernel(const float* __restrict__ x, long long in_row_stride, const float* __restrict__ g,
+                                    const float* __restrict__ be, float* __restrict__ y, int D) {
+  __shared__ float red[32];
+  const float* xr = x + (long long)blockIdx.x * in_row_stride;
+  float s = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) s += xr[d];
+  const float mean = block_sum(s, red) / (float)D;
+  float q = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) { const float t = xr[d] - mean; q = fmaf(t, t, q); }
+  const float rstd = rsqrtf(block_sum(q, red) / (float)D + 1e-5f);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) y[(long long)blockIdx.x * D + d] = (xr[d] - mean) * rstd * g[d] + be[d];
+}
+
+// Y[M,N] = X[M,K] . W[N,K]^T (+ bias) (-> exact GELU) (+ R[M,N]).  32 x 64 output tile per block, K in steps of 16.
+constexpr int TL_BM = 32, TL_BN = 64, TL_BK = 16;
+__global__ void __launch_bounds__(256) tt_linear_kernel(const float* __restrict__ X, const float* __restrict__ W,
+                                                        const float* __restrict__ bias, const float* __restrict__ R,
+                                                        float* __restrict__ Y, int M, int N, int K, int gelu) {
+  __shared__ float xs[TL_BK][TL_BM + 1], ws[TL_BK][TL_BN + 1];
+  const int m0 = blockIdx.y * TL_BM, n0 = blockIdx.x * TL_BN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 16 x 16 threads; each 2 rows x 4 columns
+  float acc[2][4] = {};
+  for (int k0 = 0; k0 < K; k0 += TL_BK) {
+    for (int i = threadIdx.x; i < TL_BM * TL_BK; i += 256) {
+      const int kk = i & 15, r = i >> 4;
+      xs[kk][r] = (m0 + r < M) ? X[(long long)(m0 + r) * K + k0 + kk] : 0.f;
+    }
+    for (int i = threadIdx.x; i < TL_BN * TL_BK; i += 256) {
+      const int kk = i & 15, r = i >> 4;
+      ws[kk][r] = (n0 + r < N) ? W[(long long)(n0 + r) * K + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TL_BK; ++kk) {
+      const float a0 = xs[kk][ty * 2], a1 = xs[kk][ty * 2 + 1];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float bv = ws[kk][tx * 4 + j];
+        acc[0][j] = fmaf(a0, bv, acc[0][j]);
+        acc[1][j] = fmaf(a1, bv, acc[1][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + ty * 2 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (gelu) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));     // nn.GELU(approximate='none')
+      if (R) v += R[(long long)m * N + n];
+      Y[(long long)m * N + n] = v;
+    }
+  }
+}
+
+// softmax(q k^T * scale) v for one (clip, head): qkv [B, n1, 3*H*dh] in to_qkv's (q | k | v), (h d) order
+// (time_transformer.py:49-64) -> out [B, n1, H*dh].  n1 <= 32, dh = 64.
+constexpr int TA_MAXN = 32, TA_DH = 64;
+__global__ void __launch_bounds__(128) tt_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int n1,
+                                                           int heads, float scale) {
+  __shared__ float q[TA_MAXN][TA_DH + 1], k[TA_MAXN][TA_DH + 1], v[TA_MAXN][TA_DH + 1], p[TA_MAXN][TA_MAXN + 1];
+  const int b = blockIdx.x / heads, h = blockIdx.x - b * heads;
+  const int inner = heads * TA_DH;
+  for (int i = threadIdx.x; i < n1 * TA_DH; i += 128) {
+    const int r = i / TA_DH, d = i - r * TA_DH;
+    const float* row = qkv + ((long long)b * n1 + r) * 3 * inner + h * TA_DH + d;
+    q[r][d] = row[0]; k[r][d] = row[inner]; v[r][d] = row[2 * inner];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n1 * n1; i += 128) {
+    const int r = i / n1, c = i - r * n1;
+    float s = 0.f;
+#pragma unroll 16
+    for (int d = 0; d < TA_DH; ++d) s = fmaf(q[r][d], k[c][d], s);
+    p[r][c] = s * scale;
+  }
+  __syncthreads();
+  if (threadIdx.x < n1) {
+    const int r = threadIdx.x;
+    float mx = -INFINITY;
+    for (int c = 0; c < n1; ++c) mx = fmaxf(mx, p[r][c]);
+    float sum = 0.f;
+    for (int c = 0; c < n1; ++c) { const float e = expf(p[r][c] - mx); p[r][c] = e; sum += e; }
+    const float inv = 1.f / sum;
+    for (int c = 0; c < n1; ++c) p[r][c] *= inv;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n1 * TA_DH; i += 128) {
+    const int r = i / TA_DH, d = i - r * TA_DH;
+    float s = 0.f;
+    for (int c = 0; c < n1; ++c) s = fmaf(p[r][c], v[c][d], s);
+    out[((long long)b * n1 + r) * inner + h * TA_DH + d] = s;
+  }
+}
+
+// mlp_head on the cls token: LayerNorm -> Linear(D -> 1) (time_transformer.py:247,270-273); optional sigmoid and a
+// copy of the normalised cls vector (the input of the last nn.Linear, which altfreezing/feature.py:106-114 hooks).
+__global__ void tt_final_kernel(const float* __restrict__ x, long long row_stride, const float* __restrict__ g,
+                                const float* __restrict__ be, const float* __restrict__ w, float bias, int D,
+                                float* __restrict__ feat_out, float* __restrict__ logits, float* __restrict__ scores) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float* xr = x + (long long)b * row_stride;
+  float s = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) s += xr[d];
+  const float mean = block_sum(s, red) / (float)D;
+  float q = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) { const float t = xr[d] - mean; q = fmaf(t, t, q); }
+  const float rstd = rsqrtf(block_sum(q, red) / (float)D + 1e-5f);
+  float dot = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float nv = (xr[d] - mean) * rstd * g[d] + be[d];
+    if (feat_out) feat_out[(long long)b * D + d] = nv;
+    dot = fmaf(nv, w[d], dot);
+  }
+  const float l = block_sum(dot, red) + bias;
+  if (threadIdx.x == 0) {
+    if (logits) logits[b] = l;
+    if (scores) scores[b] = 1.f / (1.f + expf(-l));
+  }
+}
+
+inline int flat_grid(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+int ftcn_stem_launch(const ClipLayout& clip, int clip0, int B, const float* w_tap_c_cout, const float* bias, void* y,
+                     cudaStream_t s) {
+  if (clip.S % 4 || B <= 0) { set_error("ftcn_stem: clip size %d not a multiple of 4", clip.S); return AF_ERR_INVALID; }
+  static bool configured[64] = {};
+  int dev = 0;
+  AFB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    AFB_CUDA(cudaFuncSetAttribute(ftcn_stem_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
+    AFB_CUDA(cudaFuncSetAttribute(ftcn_stem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  const int O = clip.S / 4;
+  dim3 grid((O + FS_OX - 1) / FS_OX, (O + FS_OY - 1) / FS_OY, B * clip.T);
+  if (clip.is_bf16)
+    ftcn_stem_kernel<bf16><<<grid, 256, FS_SMEM, s>>>((const bf16*)clip.base + (long long)clip0 * clip.sB, clip.sB, clip.sT,
+                                                      clip.sH, clip.sW, clip.T, clip.S, w_tap_c_cout, bias, (bf16*)y);
+  else
+    ftcn_stem_kernel<float><<<grid, 256, FS_SMEM, s>>>((const float*)clip.base + (long long)clip0 * clip.sB, clip.sB, clip.sT,
+                                                       clip.sH, clip.sW, clip.T, clip.S, w_tap_c_cout, bias, (float*)y);
+  ++g_launches;
+  AFB_CUDA(cudaGetLastError());
+  return AF_OK;
+}
+
+int maxpool_hw2_launch(const void* x, void* y, long long BT, int H, int W, int C, bool is_bf16, cudaStream_t s) {
+  const int V = is_bf16 ? 8 : 4;
+  if ((H & 1) || (W & 1) || C % V) { set_error("maxpool_hw2: H=%d W=%d C=%d unsupported", H, W, C); return AF_ERR_INVALID; }
+  const long long total = BT * (H / 2) * (W / 2) * (C / V);
+  if (is_bf16) maxpool_hw2_kernel<bf16><<<flat_grid(total, 256), 256, 0, s>>>((const bf16*)x, (bf16*)y, H, W, C, total);
+  else maxpool_hw2_kernel<float><<<flat_grid(total, 256), 256, 0, s>>>((const float*)x, (float*)y, H, W, C, total);
+  ++g_launches;
+  AFB_CUDA(cudaGetLastError());
+  return AF_OK;
+}
+
+int tt_head_launch(const TTHeadDev& h, const float* tokens, int B, float* ws, float* features_out, float* logits,
+                   float* scores, cudaStream_t s) {
+  const int n1 = h.tokens + 1, D = h.dim, inner = h.heads * h.dim_head, M = B * n1;
+  if (n1 > TA_MAXN || h.dim_head != TA_DH) { set_error("tt_head: %d tokens / dim_head %d unsupported", h.tokens, h.dim_head); return AF_ERR_INVALID; }
+  // workspace carve-up (floats): x [M,D] | ln [M,D] | qkv [M,3*inner] | att [M,inner] | hid [M,mlp]
+  float* x = ws;
+  float* ln = x + (long long)M * D;
+  float* qkv = ln + (long long)M * D;
+  float* att = qkv + (long long)M * 3 * inner;
+  float* hid = att + (long long)M * inner;
+  auto linear = [&](const float* X, const float* W, const float* bias, const float* R, float* Y, int N, int K, int gelu) {
+    dim3 grid((N + TL_BN - 1) / TL_BN, (M + TL_BM - 1) / TL_BM);
+    tt_linear_kernel<<<grid, 256, 0, s>>>(X, W, bias, R, Y, M, N, K, gelu);
+    ++g_launches;
+  };
+  tt_embed_kernel<<<M, 256, 0, s>>>(tokens, h.cls_token, h.pos_embedding, x, h.tokens, D);
+  ++g_launches;
+  for (const TTLayerDev& L : h.layers) {
+    tt_layernorm_kernel<<<M, 256, 0, s>>>(x, D, L.ln1_w, L.ln1_b, ln, D);
+    linear(ln, L.qkv_w, nullptr, nullptr, qkv, 3 * inner, D, 0);
+    tt_attention_kernel<<<B * h.heads, 128, 0, s>>>(qkv, att, n1, h.heads, 1.0f / sqrtf((float)h.dim_head));
+    linear(att, L.out_w, L.out_b, x, x, D, inner, 0);                 // x = to_out(att) + x   (Residual, :8-12)
+    tt_layernorm_kernel<<<M, 256, 0, s>>>(x, D, L.ln2_w, L.ln2_b, ln, D);
+    linear(ln, L.fc1_w, L.fc1_b, nullptr, hid, h.mlp_dim, D, 1);
+    linear(hid, L.fc2_w, L.fc2_b, x, x, D, h.mlp_dim, 0);             // x = ff(ln) + x
+    g_launches += 3;
+  }
+  tt_final_kernel<<<B, 256, 0, s>>>(x, (long long)n1 * D, h.norm_w, h.norm_b, h.fc_w, h.fc_b, D, features_out, logits, scores);
+  ++g_launches;
+  AFB_CUDA(cudaGetLastError());
+  return AF_OK;
+}
+
+long long tt_head_workspace_floats(const TTHeadDev& h, int B) {
+  const long long M = (long long)B * (h.tokens + 1), inner = (long long)h.heads * h.dim_head;
+  return M * (2LL * h.dim + 4 * inner + h.mlp_dim);
+}
+
+}  // namespace afb

@@ -225,6 +225,17 @@ int head_launch(const void* x, int B, int P, int C, bool is_bf16, const float* f
   return AF_OK;
 }
 
+int spatial_mean_launch(const void* x, int N, int P, int C, bool is_bf16, float* out, cudaStream_t s) {
+  const int V = is_bf16 ? 8 : 4;
+  if (C % (V * 32)) { set_error("spatial_mean: C=%d not a multiple of %d", C, V * 32); return AF_ERR_INVALID; }
+  dim3 grid(C / (V * 32), N), block(32, 8);
+  if (is_bf16) head_pool_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, out, P, C);
+  else head_pool_kernel<float><<<grid, block, 0, s>>>((const float*)x, out, P, C);
+  ++g_launches;
+  AFB_CUDA(cudaGetLastError());
+  return AF_OK;
+}
+
 int ndhwc_to_ncthw_f32_launch(const void* x, float* y, int B, int T, int H, int W, int C,
                               bool is_bf16, cudaStream_t s) {
   const long long P = (long long)T * H * W;

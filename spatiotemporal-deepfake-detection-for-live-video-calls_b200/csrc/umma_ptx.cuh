@@ -105,6 +105,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_ex(uint32_t addr, uint32_t sb
   d |= (uint64_t)layout << 61;
   return d;
 }
+// Measured on B200 (round 1): an operand may start at any 128-byte multiple inside a TMA-written SWIZZLE_128B
+// box, with SBO not a multiple of 1024 (e.g. a 10-pixel-wide halo box, tile starting dy rows / dx pixels in):
+// results are exact with the base-offset field (bits [49,52)) left 0 — the hardware de-swizzles on absolute
+// shared-memory address bits [7,10), exactly as TMA swizzled when writing.  Setting base offset = (addr>>7)&7
+// on top of that gives wrong results.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
   uint64_t d = 0;
   d |= (uint64_t)((addr & 0x3FFFF) >> 4);

@@ -34,7 +34,7 @@ def _fptr(a: np.ndarray):
 
 class Engine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0, max_batch: int = 32,
-                 precision: str = "bf16", clip_t: int = 32, clip_s: int = 224):
+                 precision: str = "bf16", clip_t: int = 32, clip_s: int = 224, variant: str = "i3d"):
         if not torch.cuda.is_available():
             raise _lib.Afb200Error("afb200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self._L = lib()
@@ -42,7 +42,9 @@ class Engine:
         self.max_batch, self.clip_t, self.clip_s = max_batch, clip_t, clip_s
         self.precision = precision
         self._h = C.c_void_p()
-        fw = FoldedWeights(state_dict, clip_t, clip_s)
+        self.variant = variant
+        fw = FoldedWeights(state_dict, clip_t, clip_s, variant)
+        self.feature_dim = int(fw.struct.feature_dim)
         prec = {"bf16": AF_PREC_BF16, "fp32": AF_PREC_FP32}[precision]
         torch.cuda.init()
         with torch.cuda.device(self.device):
@@ -77,7 +79,7 @@ class Engine:
 
     def forward(self, x: torch.Tensor, return_features: bool = False):
         """x: normalised clip tensor [B,3,T,S,S] on this engine's device (any strides;
-        fp32 / bf16 / fp16).  Returns fp32 logits [B,1] (and features [B,2048])."""
+        fp32 / bf16 / fp16).  Returns fp32 logits [B,1] (and features [B,feature_dim])."""
         if x.dim() != 5 or x.shape[1] != 3 or x.shape[2] != self.clip_t or x.shape[3] != self.clip_s \
                 or x.shape[4] != self.clip_s:
             raise ValueError("afb200 engine takes [B,3,%d,%d,%d] clips, got %s" %
@@ -88,7 +90,7 @@ class Engine:
             x = x.float()
         B = x.shape[0]
         logits = torch.empty((B, 1), dtype=torch.float32, device=self.device)
-        feats = torch.empty((B, 2048), dtype=torch.float32, device=self.device) if return_features else None
+        feats = torch.empty((B, self.feature_dim), dtype=torch.float32, device=self.device) if return_features else None
         strides = (C.c_int64 * 5)(*x.stride())
         with torch.cuda.device(self.device):
             for b0 in range(0, B, self.max_batch):
@@ -109,7 +111,7 @@ class Engine:
             x = x.float()
         B = x.shape[0]
         logits = torch.empty((B, 1), dtype=torch.float32, device=self.device)
-        feats = torch.empty((B, self.clip_t // 2, 2048), dtype=torch.float32, device=self.device)
+        feats = torch.empty((B, self.clip_t // 2, self.feature_dim), dtype=torch.float32, device=self.device)
         strides = (C.c_int64 * 5)(*x.stride())
         with torch.cuda.device(self.device):
             for b0 in range(0, B, self.max_batch):
@@ -125,7 +127,7 @@ class Engine:
         B = clips.shape[0]
         logits = torch.empty(B, dtype=torch.float32, device=self.device)
         scores = torch.empty(B, dtype=torch.float32, device=self.device)
-        feats = torch.empty((B, 2048), dtype=torch.float32, device=self.device) if return_features else None
+        feats = torch.empty((B, self.feature_dim), dtype=torch.float32, device=self.device) if return_features else None
         with torch.cuda.device(self.device):
             for b0 in range(0, B, self.max_batch):
                 nb = min(self.max_batch, B - b0)
@@ -165,7 +167,7 @@ class Engine:
         (see crop.pack_descriptors).  Returns (logits [B], scores [B])."""
         logits = torch.empty(batch, dtype=torch.float32, device=self.device)
         scores = torch.empty(batch, dtype=torch.float32, device=self.device)
-        feats = torch.empty((batch, 2048), dtype=torch.float32, device=self.device) if return_features else None
+        feats = torch.empty((batch, self.feature_dim), dtype=torch.float32, device=self.device) if return_features else None
         with torch.cuda.device(self.device):
             check(self._L.af_crop_infer(self._h, C.c_void_p(frames_dev.data_ptr()), C.c_void_p(geom_dev.data_ptr()),
                                         batch, int(bgr), _fptr(self.mean255), _fptr(self.std255),

@@ -57,5 +57,51 @@ class I3D8x8Params(nn.Module):
         raise RuntimeError("I3D8x8Params holds weights only; run it through afb200.B200Engine")
 
 
-def reference_key_set() -> Dict[str, tuple]:
-    return {k: tuple(v.shape) for k, v in I3D8x8Params().state_dict().items()}
+class _ParamHolder(_Holder):
+    """A leaf that owns one tensor per given attribute name (LayerNorm / bias-free Linear stand-ins)."""
+
+    def __init__(self, **shapes):
+        super().__init__()
+        for name, shape in shapes.items():
+            setattr(self, name, nn.Parameter(torch.zeros(shape), requires_grad=False))
+
+
+class FTCNTTParams(nn.Module):
+    """The 275 tensors of the reference FTCN-TT network (model/classifier/i3d_temporal_var_fix_dropout_tt_cfg.py:
+    295-333 with setting/ftcn_tt.yaml) under the reference's names — BatchNorms that temporal_only_conv wrapped into
+    nn.Sequential(bn, MaxPool3d) carry the extra ".0" — so its checkpoints load unchanged.  The head's final
+    nn.Linear (mlp_head.1) is a real nn.Linear for altfreezing/feature.py:106-114's hook."""
+
+    def __init__(self):
+        super().__init__()
+        for spec in arch.all_conv_specs("ftcn_tt"):
+            _attach(self, spec.name, _conv_holder(spec))
+            _attach(self, spec.bn, _bn_holder(spec.cout))
+        groups: Dict[str, Dict[str, tuple]] = {}
+        for name, shape in arch.tt_param_shapes().items():
+            owner, leaf = name.rsplit(".", 1)
+            groups.setdefault(owner, {})[leaf] = shape
+        for owner, shapes in groups.items():
+            if owner.endswith("mlp_head.1"):
+                _attach(self, owner, nn.Linear(arch.TT_DIM, 1, bias=True))
+            elif owner == arch.TT_PREFIX:          # pos_embedding / cls_token live on time_T itself, next to children
+                holder = self
+                for part in owner.split("."):
+                    if not hasattr(holder, part):
+                        setattr(holder, part, _Holder())
+                    holder = getattr(holder, part)
+                for leaf, shape in shapes.items():
+                    setattr(holder, leaf, nn.Parameter(torch.zeros(shape), requires_grad=False))
+            else:
+                _attach(self, owner, _ParamHolder(**shapes))
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("FTCNTTParams holds weights only; run it through afb200.B200Engine")
+
+
+def params_for(variant: str) -> nn.Module:
+    return FTCNTTParams() if variant == "ftcn_tt" else I3D8x8Params()
+
+
+def reference_key_set(variant: str = "i3d") -> Dict[str, tuple]:
+    return {k: tuple(v.shape) for k, v in params_for(variant).state_dict().items()}

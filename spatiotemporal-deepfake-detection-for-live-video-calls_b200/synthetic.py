@@ -20,9 +20,10 @@ IMAGENET_MEAN = (0.485, 0.456, 0.406)   # altfreezing/demo.py:84-87
 IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
-def synthetic_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
-    """A full 320-key state_dict of the reference `I3D8x8` network
-     with MSRA(fan_out) conv weights and non-degenerate BN."""
+def synthetic_state_dict(seed: int = 0, variant: str = "i3d") -> Dict[str, torch.Tensor]:
+    """A full state_dict of the reference network (320 keys for the `I3D8x8` of i3d_ori; 275 for
+    the FTCN-TT plugin) with MSRA(fan_out) conv weights, non-degenerate BN and, for FTCN-TT, a transformer head
+    drawn like TimeTransformer._init_weights (normal 0.02 Linear weights) but with non-trivial biases/LayerNorms."""
     g = torch.Generator().manual_seed(int(seed))
     sd: Dict[str, torch.Tensor] = {}
 
@@ -32,7 +33,7 @@ def synthetic_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
     def rand(lo, hi, *shape):
         return lo + (hi - lo) * torch.rand(*shape, generator=g, dtype=torch.float32)
 
-    for cv in arch.all_conv_specs():
+    for cv in arch.all_conv_specs(variant):
         kt, kh, kw = cv.kernel
         fan_out = cv.cout * kt * kh * kw
         sd[cv.name + ".weight"] = randn(cv.cout, cv.cin, kt, kh, kw) * math.sqrt(2.0 / fan_out)
@@ -42,8 +43,19 @@ def synthetic_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
         sd[cv.bn + ".running_mean"] = randn(cv.cout) * 0.05
         sd[cv.bn + ".running_var"] = rand(0.8, 1.2, cv.cout)
         sd[cv.bn + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
-    sd["resnet.head.projection.weight"] = randn(1, arch.FEATURE_DIM) * 0.05
-    sd["resnet.head.projection.bias"] = torch.full((1,), 0.1)
+    if variant == "ftcn_tt":
+        for name, shape in arch.tt_param_shapes().items():
+            if name.endswith("norm.weight") or name.endswith("mlp_head.0.weight"):
+                sd[name] = rand(0.8, 1.2, *shape)
+            elif name.endswith(".bias"):
+                sd[name] = randn(*shape) * 0.05
+            elif name.endswith("pos_embedding") or name.endswith("cls_token"):
+                sd[name] = randn(*shape) * 0.5
+            else:                                   # Linear weights
+                sd[name] = randn(*shape) * (0.05 if name.endswith("mlp_head.1.weight") else 0.03)
+    else:
+        sd["resnet.head.projection.weight"] = randn(1, arch.FEATURE_DIM) * 0.05
+        sd["resnet.head.projection.bias"] = torch.full((1,), 0.1)
     return sd
 
 
