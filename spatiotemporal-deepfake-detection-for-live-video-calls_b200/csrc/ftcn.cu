@@ -31,9 +31,15 @@ template <> __device__ __forceinline__ float4 load_px4<bf16>(const bf16* p) {
   const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&t.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
   return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
 }
-template <typename T> __device__ __forceinline__ void store1(T* p, float v);
-template <> __device__ __forceinline__ void store1<float>(float* p, float v) { *p = v; }
-template <> __device__ __forceinline__ void store1<bf16>(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <> __device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 t;
+  t.x = *reinterpret_cast<const uint32_t*>(&lo);
+  t.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = t;
+}
 
 // clip: padded NDHWC4 (element strides sB,sT,sH,sW; `clip` points at logical (b=0,t=0,y=0,x=0); >= 2 zero frames
 // and >= 3 zero rows / columns around every clip).  w: [5][4][64] fp32 (tap, channel, cout).  y: [B*T, S/4, S/4, 64].
@@ -56,47 +62,54 @@ __global__ void __launch_bounds__(256) ftcn_stem_kernel(const T* __restrict__ cl
     if (gx < S && gy < S) v = load_px4<T>(src + f * sT + (long long)gy * sH + (long long)gx * sW);
     in_s[i] = v;
   }
-  const int c = threadIdx.x & 63, lane4 = threadIdx.x >> 6;
-  float wr[5][3];
+  // thread = 4 consecutive output channels x one of 16 position lanes: every 16-byte shared-memory read of an input
+  // pixel feeds 12 FMAs (the first version, one channel per thread, was bound by those reads at 13 TFLOP/s)
+  const int cg = (threadIdx.x & 15) * 4, pl = threadIdx.x >> 4;
+  float4 wr[5][3];
 #pragma unroll
   for (int f = 0; f < 5; ++f)
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) wr[f][ch] = __ldg(w + (f * 4 + ch) * FS_C + c);
-  const float bc = __ldg(bias + c);
+    for (int ch = 0; ch < 3; ++ch) wr[f][ch] = __ldg(reinterpret_cast<const float4*>(w + (f * 4 + ch) * FS_C + cg));
+  const float4 bc = __ldg(reinterpret_cast<const float4*>(bias + cg));
   __syncthreads();
   const int M2 = S / 2;
-  for (int pos = lane4; pos < FS_MY * FS_MX; pos += 4) {
+  for (int pos = pl; pos < FS_MY * FS_MX; pos += 16) {
     const int my = pos / FS_MX, mx = pos - my * FS_MX;
-    float m = -INFINITY;
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {                      // MaxPool3d((1,2,2)) over the conv + BN outputs
       const int px = (2 * my + (q >> 1)) * FS_IX + 2 * mx + (q & 1);
-      float a = bc;
+      float4 a = bc;
 #pragma unroll
       for (int f = 0; f < 5; ++f) {
         const float4 v = in_s[f * FS_IY * FS_IX + px];
-        a = fmaf(v.x, wr[f][0], a);
-        a = fmaf(v.y, wr[f][1], a);
-        a = fmaf(v.z, wr[f][2], a);
+        a.x = fmaf(v.x, wr[f][0].x, a.x); a.y = fmaf(v.x, wr[f][0].y, a.y); a.z = fmaf(v.x, wr[f][0].z, a.z); a.w = fmaf(v.x, wr[f][0].w, a.w);
+        a.x = fmaf(v.y, wr[f][1].x, a.x); a.y = fmaf(v.y, wr[f][1].y, a.y); a.z = fmaf(v.y, wr[f][1].z, a.z); a.w = fmaf(v.y, wr[f][1].w, a.w);
+        a.x = fmaf(v.z, wr[f][2].x, a.x); a.y = fmaf(v.z, wr[f][2].y, a.y); a.z = fmaf(v.z, wr[f][2].z, a.z); a.w = fmaf(v.z, wr[f][2].w, a.w);
       }
-      m = fmaxf(m, a);
+      m.x = fmaxf(m.x, a.x); m.y = fmaxf(m.y, a.y); m.z = fmaxf(m.z, a.z); m.w = fmaxf(m.w, a.w);
     }
     // ReLU, then positions outside the 112x112 map must not win the 3x3 max: after ReLU 0 is neutral
     const bool inside = (unsigned)(my0 + my) < (unsigned)M2 && (unsigned)(mx0 + mx) < (unsigned)M2;
-    map_s[pos * FS_C + c] = inside ? fmaxf(m, 0.f) : 0.f;
+    if (!inside) m = make_float4(0.f, 0.f, 0.f, 0.f);
+    m.x = fmaxf(m.x, 0.f); m.y = fmaxf(m.y, 0.f); m.z = fmaxf(m.z, 0.f); m.w = fmaxf(m.w, 0.f);
+    *reinterpret_cast<float4*>(map_s + pos * FS_C + cg) = m;
   }
   __syncthreads();
   const int O = S / 4;
 #pragma unroll
-  for (int j = 0; j < (FS_OX * FS_OY) / 4; ++j) {
-    const int o = lane4 * ((FS_OX * FS_OY) / 4) + j, oy = o / FS_OX, ox = o - oy * FS_OX;
+  for (int j = 0; j < (FS_OX * FS_OY) / 16; ++j) {
+    const int o = pl * ((FS_OX * FS_OY) / 16) + j, oy = o / FS_OX, ox = o - oy * FS_OX;
     if (oy0 + oy >= O || ox0 + ox >= O) continue;
-    float m = 0.f;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) m = fmaxf(m, map_s[((2 * oy + dy) * FS_MX + 2 * ox + dx) * FS_C + c]);
-    store1<T>(y + (((long long)bt * O + oy0 + oy) * O + ox0 + ox) * FS_C + c, m);
+      for (int dx = 0; dx < 3; ++dx) {
+        const float4 v = *reinterpret_cast<const float4*>(map_s + ((2 * oy + dy) * FS_MX + 2 * ox + dx) * FS_C + cg);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    store4<T>(y + (((long long)bt * O + oy0 + oy) * O + ox0 + ox) * FS_C + cg, m);
   }
 }
 
@@ -174,40 +187,45 @@ __global__ void tt_layernorm_kernel(const float* __restrict__ x, long long in_ro
   for (int d = threadIdx.x; d < D; d += blockDim.x) y[(long long)blockIdx.x * D + d] = (xr[d] - mean) * rstd * g[d] + be[d];
 }
 
-// Y[M,N] = X[M,K] . W[N,K]^T (+ bias) (-> exact GELU) (+ R[M,N]).  32 x 64 output tile per block, K in steps of 16.
-constexpr int TL_BM = 32, TL_BN = 64, TL_BK = 16;
+// Y[M,N] = X[M,K] . W[N,K]^T (+ bias) (-> exact GELU) (+ R[M,N]).  64 x 64 output tile per block (4 x 4 per thread),
+// K in steps of 16.
+constexpr int TL_BM = 64, TL_BN = 64, TL_BK = 16;
 __global__ void __launch_bounds__(256) tt_linear_kernel(const float* __restrict__ X, const float* __restrict__ W,
                                                         const float* __restrict__ bias, const float* __restrict__ R,
                                                         float* __restrict__ Y, int M, int N, int K, int gelu) {
-  __shared__ float xs[TL_BK][TL_BM + 1], ws[TL_BK][TL_BN + 1];
+  __shared__ __align__(16) float xs[TL_BK][TL_BM + 4], ws[TL_BK][TL_BN + 4];
   const int m0 = blockIdx.y * TL_BM, n0 = blockIdx.x * TL_BN;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 16 x 16 threads; each 2 rows x 4 columns
-  float acc[2][4] = {};
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 16 x 16 threads; each 4 rows x 4 columns
+  float acc[4][4] = {};
   for (int k0 = 0; k0 < K; k0 += TL_BK) {
-    for (int i = threadIdx.x; i < TL_BM * TL_BK; i += 256) {
-      const int kk = i & 15, r = i >> 4;
-      xs[kk][r] = (m0 + r < M) ? X[(long long)(m0 + r) * K + k0 + kk] : 0.f;
+    for (int i = threadIdx.x; i < TL_BM * TL_BK / 4; i += 256) {      // 16-byte loads along K, transposed into smem
+      const int k4 = (i & 3) * 4, r = i >> 2;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < M) v = *reinterpret_cast<const float4*>(X + (long long)(m0 + r) * K + k0 + k4);
+      xs[k4][r] = v.x; xs[k4 + 1][r] = v.y; xs[k4 + 2][r] = v.z; xs[k4 + 3][r] = v.w;
     }
-    for (int i = threadIdx.x; i < TL_BN * TL_BK; i += 256) {
-      const int kk = i & 15, r = i >> 4;
-      ws[kk][r] = (n0 + r < N) ? W[(long long)(n0 + r) * K + k0 + kk] : 0.f;
+    for (int i = threadIdx.x; i < TL_BN * TL_BK / 4; i += 256) {
+      const int k4 = (i & 3) * 4, r = i >> 2;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + r < N) v = *reinterpret_cast<const float4*>(W + (long long)(n0 + r) * K + k0 + k4);
+      ws[k4][r] = v.x; ws[k4 + 1][r] = v.y; ws[k4 + 2][r] = v.z; ws[k4 + 3][r] = v.w;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < TL_BK; ++kk) {
-      const float a0 = xs[kk][ty * 2], a1 = xs[kk][ty * 2 + 1];
+      const float4 a = *reinterpret_cast<const float4*>(&xs[kk][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&ws[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float bv = ws[kk][tx * 4 + j];
-        acc[0][j] = fmaf(a0, bv, acc[0][j]);
-        acc[1][j] = fmaf(a1, bv, acc[1][j]);
-      }
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bw[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int m = m0 + ty * 2 + i;
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
     if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
