@@ -397,7 +397,12 @@ stem_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // ===================================================== TMA producer
     if (elect_one()) {                              // weights are constants: no need to wait for the prior grid
       mbar_expect_tx(w_full, SW_W_BYTES);
-      for (int i = 0; i < 35; ++i) tma_load_2d(smem_w + i * W_TILE_BYTES, &tm_w, w_full, 0, i * RB_N);
+      // tile (dt,dy) of W35 lands at slot dy*5 + (4-dt): the tiles of taps dt and dt-1 (same dy) are then adjacent, so
+      // one N=128 MMA can feed two consecutive output frames from the same input box (see the MMA issuer)
+      for (int i = 0; i < 35; ++i) {
+        const int dt = i / 7, dy = i - dt * 7;
+        tma_load_2d(smem_w + (dy * 5 + 4 - dt) * W_TILE_BYTES, &tm_w, w_full, 0, i * RB_N);
+      }
     }
     __syncwarp();
     pdl_wait_prior_grid();
@@ -423,7 +428,7 @@ stem_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     pdl_wait_prior_grid();
-    constexpr uint32_t idesc = make_idesc(RB_N);
+    constexpr uint32_t idesc = make_idesc(RB_N), idesc2 = make_idesc(2 * RB_N);
     mbar_wait(w_full, 0);
     tc_fence_after();
     const uint32_t w_base = smem_u32(smem_w);
@@ -440,16 +445,38 @@ stem_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const uint32_t a_addr = smem_u32(smem_a + stage * p.a_stage_bytes);
         if (elect_one()) {
           const int g_lo = f > 4 ? f - 4 : 0, g_hi = f < RB_G - 1 ? f : RB_G - 1;
-          for (int g = g_lo; g <= g_hi; ++g) {      // output frame g of the unit sees this input frame as tap dt = f - g
+          // Output frame g of the unit sees this input frame as tap dt = f - g.  Two consecutive output frames
+          // (g, g+1) use taps (dt, dt-1) of the SAME activation box: their weight tiles are adjacent in smem and their
+          // accumulators adjacent in TMEM, so one 128x128x16 MMA does both and reads the A operand once -- an
+          // N=64 MMA is bound by its shared-memory operand reads (6 KB per 32 tensor clocks), the paired one is not.
+          int g = g_lo;
+          while (g <= g_hi) {
             const int dt = f - g;
             const uint32_t d_tmem = tmem_base + (as * RB_G + g) * RB_N;
-            const uint32_t w_addr = w_base + dt * 7 * W_TILE_BYTES;
+            if (g + 1 <= g_hi) {
+              const bool init = dt == 1;            // frame g+1 receives its first contribution (tap 0) here
 #pragma unroll
-            for (int dy = 0; dy < 7; ++dy) {
-              const uint64_t adesc = make_smem_desc_ex(a_addr + dy * A_TAP_BYTES, 1024, LAYOUT);
-              const uint64_t bdesc = make_smem_desc_ex(w_addr + dy * W_TILE_BYTES, SBO_B, LAYOUT);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, (dt | dy) != 0 ? 1u : 0u);
-              umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              for (int dy = 0; dy < 7; ++dy) {
+                const uint64_t adesc = make_smem_desc_ex(a_addr + dy * A_TAP_BYTES, 1024, LAYOUT);
+                const uint64_t bdesc = make_smem_desc_ex(w_base + (dy * 5 + 4 - dt) * W_TILE_BYTES, SBO_B, LAYOUT);
+                if (dy == 0 && init) {              // the pair's predicate is shared: open g+1's accumulator separately
+                  umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+                  umma_bf16(d_tmem + RB_N, adesc, bdesc + (W_TILE_BYTES >> 4), idesc, 0u);
+                } else {
+                  umma_bf16(d_tmem, adesc, bdesc, idesc2, 1u);
+                }
+                umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc2, 1u);
+              }
+              g += 2;
+            } else {
+#pragma unroll
+              for (int dy = 0; dy < 7; ++dy) {
+                const uint64_t adesc = make_smem_desc_ex(a_addr + dy * A_TAP_BYTES, 1024, LAYOUT);
+                const uint64_t bdesc = make_smem_desc_ex(w_base + (dy * 5 + 4 - dt) * W_TILE_BYTES, SBO_B, LAYOUT);
+                umma_bf16(d_tmem, adesc, bdesc, idesc, (dt | dy) != 0 ? 1u : 0u);
+                umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              }
+              g += 1;
             }
           }
           umma_commit(&empty_bar[stage]);
