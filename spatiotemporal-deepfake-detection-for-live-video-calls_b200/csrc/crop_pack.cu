@@ -14,6 +14,8 @@
 //   x = (float(u8) - 255*mean_c) / (255*std_c)      (altfreezing/demo.py:84-87,317-319)
 // in IEEE fp32 and writes the engine's padded NDHWC4 clip directly (bf16 or fp32), so the
 // aligned u8 clip never round-trips through HBM.
+#include <string.h>
+
 #include "common.cuh"
 #include "../../include/afb200.h"
 
@@ -21,14 +23,6 @@ namespace afb {
 namespace {
 
 __device__ __forceinline__ int cv_round(double v) { return __double2int_rn(v); }
-
-__device__ __forceinline__ int bilinear_w(int fa, int fb) {
-  // float32((1 - a/32)) * float32((1 - b/32)) style entries of OpenCV's BilinearTab_i,
-  // scaled by 2^15 and saturated to int16.
-  const float v = __fmul_rn(fa * (1.0f / 32.0f), fb * (1.0f / 32.0f));
-  const int w = __float2int_rn(__fmul_rn(v, 32768.0f));
-  return w > 32767 ? 32767 : w;
-}
 
 template <typename T> __device__ __forceinline__ void store_px4(T* p, float a, float b, float c);
 template <> __device__ __forceinline__ void store_px4<float>(float* p, float a, float b, float c) {
@@ -46,20 +40,38 @@ struct Norm { float mean[3], stdv[3]; };
 
 __device__ __forceinline__ float norm1(float v, float m, float s) { return __fdiv_rn(__fsub_rn(v, m), s); }
 
+// 6 consecutive bytes (two RGB pixels) starting at an arbitrary address, fetched as two aligned 8-byte words.
+// Only used where the 16-byte window is known to lie inside the frame buffer.
+__device__ __forceinline__ uint2 load6(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint2* q = reinterpret_cast<const uint2*>(a & ~(uintptr_t)7);
+  const uint2 lo = __ldg(q), hi = __ldg(q + 1);
+  const uint32_t sh = (uint32_t)(a & 7) * 8;
+  // 128-bit window {lo.x, lo.y, hi.x, hi.y} shifted right by sh bits (sh in {0,8,..,56}); keep the low 48 bits
+  const uint32_t w0 = sh < 32 ? lo.x : lo.y, w1 = sh < 32 ? lo.y : hi.x, w2 = sh < 32 ? hi.x : hi.y;
+  const uint32_t s2 = sh & 31;
+  return make_uint2(__funnelshift_r(w0, w1, s2), __funnelshift_r(w1, w2, s2));
+}
+
+// Per block (32 columns x 8 rows of one frame): the f64 part of OpenCV's coordinate maths is done once per column
+// (adelta, bdelta) and once per row (X0, Y0) by 40 threads and shared through smem, together with the frame's
+// descriptor reduced to "valid canvas window" form.  lut: fp32 [3][256] = (v - mean_c) / std_c for every u8 value
+// (built by norm_lut_kernel with the same IEEE division the callers' pack step performs).
 template <typename T, bool kToClip>
 __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__ frames,
                                                    const ClipGeom* __restrict__ geom, int T_, int S,
                                                    int bgr, uint8_t* __restrict__ out_u8, T* dst,
                                                    long long sB, long long sT, long long sH,
-                                                   long long sW, Norm nrm) {
-  // Per block (32 columns x 8 rows of one frame): the f64 part of OpenCV's coordinate maths is done
-  // once per column (adelta, bdelta) and once per row (X0, Y0) by 40 threads and shared through smem.
+                                                   long long sW, const float* __restrict__ lut) {
   __shared__ int s_ad[32], s_bd[32], s_x0[8], s_y0[8];
+  __shared__ int s_win[6];             // valid canvas window [x_lo, x_hi) x [y_lo, y_hi), strict-interior rows [yi_lo, yi_hi)
+  __shared__ const uint8_t* s_org;     // address of canvas pixel (0,0) in the frame
+  __shared__ long long s_pitch;
   const int bt = blockIdx.z;
   const int b = bt / T_, t = bt - b * T_;
-  const ClipGeom g = geom[b];
   const int tid = threadIdx.y * 32 + threadIdx.x;
   if (tid < 40) {
+    const ClipGeom g = geom[b];
     // cv::invertAffineTransform (f64)
     double D = __dsub_rn(__dmul_rn(g.tfm[0], g.tfm[4]), __dmul_rn(g.tfm[1], g.tfm[3]));
     D = D != 0.0 ? __ddiv_rn(1.0, D) : 0.0;
@@ -76,51 +88,80 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
       s_x0[tid - 32] = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(A12, yy), b1), 1024.0)) + 16;
       s_y0[tid - 32] = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(A22, yy), b2), 1024.0)) + 16;
     }
+  } else if (tid == 40) {
+    // canvas pixel (cx,cy) is frame pixel (cx+ltx, cy+lty); it exists iff it is inside the canvas AND inside this
+    // frame's own big box clipped to the frame (faster_crop_align_xray.py:77-83)
+    const ClipGeom g = geom[b];
+    const FrameDesc f = frames[bt];
+    const int ltx = g.left_top[0], lty = g.left_top[1];
+    const int bx1 = max(f.box[0], 0), by1 = max(f.box[1], 0);
+    const int bx2 = min(f.box[2], f.width), by2 = min(f.box[3], f.height);
+    s_win[0] = max(0, bx1 - ltx); s_win[1] = min(g.canvas_wh[0], bx2 - ltx);
+    s_win[2] = max(0, by1 - lty); s_win[3] = min(g.canvas_wh[1], by2 - lty);
+    // rows whose 16-byte fetch windows cannot leave the frame buffer: frame rows 1 .. height-2
+    s_win[4] = max(s_win[2], 1 - lty); s_win[5] = min(s_win[3], f.height - 1 - lty);
+    s_org = f.data + (long long)lty * f.pitch + (long long)ltx * 3;
+    s_pitch = f.pitch;
   }
   __syncthreads();
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = blockIdx.y * 8 + threadIdx.y;
   if (x >= S || y >= S) return;
-  const FrameDesc f = frames[bt];
-  const int adelta = s_ad[threadIdx.x], bdelta = s_bd[threadIdx.x];
-  const int X0 = s_x0[threadIdx.y], Y0 = s_y0[threadIdx.y];
-  const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+  const int X = (s_x0[threadIdx.y] + s_ad[threadIdx.x]) >> 5, Y = (s_y0[threadIdx.y] + s_bd[threadIdx.x]) >> 5;
   int sx = X >> 5, sy = Y >> 5;
   sx = max(-32768, min(32767, sx));
   sy = max(-32768, min(32767, sy));
   const int fx = X & 31, fy = Y & 31;
-  const int w00 = bilinear_w(32 - fy, 32 - fx), w01 = bilinear_w(32 - fy, fx);
-  const int w10 = bilinear_w(fy, 32 - fx), w11 = bilinear_w(fy, fx);
-
-  const int bx1 = max(f.box[0], 0), by1 = max(f.box[1], 0);
-  const int bx2 = min(f.box[2], f.width), by2 = min(f.box[3], f.height);
-  int acc[3] = {0, 0, 0};
+  // OpenCV's BilinearTab_i entry: rint(float(a/32) * float(b/32) * 32768) saturated to int16.  Both factors and the
+  // product are exact in fp32, so this is the integer 32*a*b (<= 32768) with the one saturating case a = b = 32.
+  const int w00 = min((32 - fy) * (32 - fx) * 32, 32767), w01 = (32 - fy) * fx * 32;
+  const int w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+  const int xlo = s_win[0], xhi = s_win[1], ylo = s_win[2], yhi = s_win[3];
+  const uint8_t* org = s_org;
+  const long long pitch = s_pitch;
+  int acc[3] = {0, 0, 0};                 // in memory channel order; BGR frames are swapped at the end
+  if (sx >= xlo && sx + 1 < xhi && sy >= s_win[4] && sy + 1 < s_win[5] && pitch >= 16) {
+    // all four taps exist: two 6-byte fetches
+    const uint8_t* p = org + (long long)sy * pitch + (long long)sx * 3;
+    const uint2 r0 = load6(p), r1 = load6(p + pitch);
+    const int a0 = r0.x & 255, a1 = (r0.x >> 8) & 255, a2 = (r0.x >> 16) & 255;
+    const int b0 = r0.x >> 24, b1 = r0.y & 255, b2 = (r0.y >> 8) & 255;
+    const int d0 = r1.x & 255, d1 = (r1.x >> 8) & 255, d2 = (r1.x >> 16) & 255;
+    const int e0 = r1.x >> 24, e1 = r1.y & 255, e2 = (r1.y >> 8) & 255;
+    acc[0] = w00 * a0 + w01 * b0 + w10 * d0 + w11 * e0;
+    acc[1] = w00 * a1 + w01 * b1 + w10 * d1 + w11 * e1;
+    acc[2] = w00 * a2 + w01 * b2 + w10 * d2 + w11 * e2;
+  } else {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int cx = sx + (k & 1), cy = sy + (k >> 1);
-    const int wgt = k == 0 ? w00 : k == 1 ? w01 : k == 2 ? w10 : w11;
-    const int px = cx + g.left_top[0], py = cy + g.left_top[1];
-    const bool ok = cx >= 0 && cx < g.canvas_wh[0] && cy >= 0 && cy < g.canvas_wh[1] &&
-                    px >= bx1 && px < bx2 && py >= by1 && py < by2;
-    if (ok && wgt != 0) {
-      const uint8_t* p = f.data + (long long)py * f.pitch + (long long)px * 3;
-      acc[0] += wgt * (int)p[bgr ? 2 : 0];
-      acc[1] += wgt * (int)p[1];
-      acc[2] += wgt * (int)p[bgr ? 0 : 2];
+    for (int k = 0; k < 4; ++k) {
+      const int cx = sx + (k & 1), cy = sy + (k >> 1);
+      const int wgt = k == 0 ? w00 : k == 1 ? w01 : k == 2 ? w10 : w11;
+      if (cx >= xlo && cx < xhi && cy >= ylo && cy < yhi && wgt != 0) {
+        const uint8_t* p = org + (long long)cy * pitch + (long long)cx * 3;
+        acc[0] += wgt * (int)p[0];
+        acc[1] += wgt * (int)p[1];
+        acc[2] += wgt * (int)p[2];
+      }
     }
   }
   int o[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) o[c] = max(0, min(255, (acc[c] + 16384) >> 15));
+  if (bgr) { const int t0 = o[0]; o[0] = o[2]; o[2] = t0; }
 
   if (kToClip) {
     T* q = dst + b * sB + t * sT + y * sH + x * sW;
-    store_px4<T>(q, norm1((float)o[0], nrm.mean[0], nrm.stdv[0]), norm1((float)o[1], nrm.mean[1], nrm.stdv[1]),
-                 norm1((float)o[2], nrm.mean[2], nrm.stdv[2]));
+    store_px4<T>(q, __ldg(lut + o[0]), __ldg(lut + 256 + o[1]), __ldg(lut + 512 + o[2]));
   } else {
     uint8_t* q = out_u8 + (((long long)bt * S + y) * S + x) * 3;
     q[0] = (uint8_t)o[0]; q[1] = (uint8_t)o[1]; q[2] = (uint8_t)o[2];
   }
+}
+
+// lut[c][v] = (float(v) - mean_c) / std_c in IEEE fp32 (demo.py:84-87,317-319), one entry per u8 value
+__global__ void norm_lut_kernel(Norm nrm, float* __restrict__ lut) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 768) lut[i] = norm1((float)(i & 255), nrm.mean[i >> 8], nrm.stdv[i >> 8]);
 }
 
 // u8 [B,T,S,S,3] aligned clips -> normalised padded NDHWC4 clip (A4 of SURVEY.md §8a).
@@ -202,6 +243,34 @@ inline int flat_grid(long long total, int block) {
 
 }  // namespace
 
+// Normalisation tables live in device memory per (device, mean, std); a table is built the first time its
+// constants are seen (callers use one or two sets: demo.py's and the services' rounding of 255*mean).
+struct NormLutCache { float* dev[4] = {}; Norm key[4] = {}; int used = 0, next = 0; };
+static NormLutCache g_norm_lut[64];
+
+static int norm_lut_for(const Norm& n, cudaStream_t s, const float** out) {
+  int dev = 0;
+  AFB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { set_error("crop: device index %d out of range", dev); return AF_ERR_INVALID; }
+  NormLutCache& c = g_norm_lut[dev];
+  for (int i = 0; i < c.used; ++i)
+    if (memcmp(&c.key[i], &n, sizeof(Norm)) == 0) { *out = c.dev[i]; return AF_OK; }
+  int slot = c.used < 4 ? c.used : c.next;
+  if (c.used == 4) {
+    AFB_CUDA(cudaDeviceSynchronize());       // a launch in flight may still read the table being replaced
+    c.next = (c.next + 1) & 3;
+  }
+  if (!c.dev[slot]) AFB_CUDA(cudaMalloc(&c.dev[slot], 768 * sizeof(float)));
+  norm_lut_kernel<<<3, 256, 0, s>>>(n, c.dev[slot]);
+  ++g_launches;
+  AFB_CUDA(cudaGetLastError());
+  AFB_CUDA(cudaStreamSynchronize(s));        // other streams may use the table as soon as this call returns
+  c.key[slot] = n;
+  if (c.used < 4) ++c.used;
+  *out = c.dev[slot];
+  return AF_OK;
+}
+
 int crop_launch(const FrameDesc* frames, const ClipGeom* geom, int B, int T, int S, int bgr,
                 uint8_t* out_u8, const ClipLayout* dst, const float mean[3], const float stdv[3],
                 cudaStream_t s) {
@@ -210,14 +279,19 @@ int crop_launch(const FrameDesc* frames, const ClipGeom* geom, int B, int T, int
   Norm n = {{0, 0, 0}, {1, 1, 1}};
   if (mean && stdv)
     for (int c = 0; c < 3; ++c) { n.mean[c] = mean[c]; n.stdv[c] = stdv[c]; }
+  const float* lut = nullptr;
+  if (dst != nullptr) {
+    int rc = norm_lut_for(n, s, &lut);
+    if (rc) return rc;
+  }
   if (dst == nullptr) {
-    crop_kernel<float, false><<<grid, block, 0, s>>>(frames, geom, T, S, bgr, out_u8, nullptr, 0, 0, 0, 0, n);
+    crop_kernel<float, false><<<grid, block, 0, s>>>(frames, geom, T, S, bgr, out_u8, nullptr, 0, 0, 0, 0, nullptr);
   } else if (dst->is_bf16) {
     crop_kernel<bf16, true><<<grid, block, 0, s>>>(frames, geom, T, S, bgr, nullptr, (bf16*)dst->base, dst->sB,
-                                                   dst->sT, dst->sH, dst->sW, n);
+                                                   dst->sT, dst->sH, dst->sW, lut);
   } else {
     crop_kernel<float, true><<<grid, block, 0, s>>>(frames, geom, T, S, bgr, nullptr, (float*)dst->base, dst->sB,
-                                                    dst->sT, dst->sH, dst->sW, n);
+                                                    dst->sT, dst->sH, dst->sW, lut);
   }
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
