@@ -235,6 +235,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         cpu_reference_step(sd, inputs, n)
         dt = time.perf_counter() - t0
+        torch.set_num_threads(1)      # park the OpenMP team: its spinning workers would slow the launch thread below
         cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "%d clips, batch 1 each (cv2.warpAffine crop + normalise + fp32 forward of the oracle port), after 1 warm-up clip" % n}
 
