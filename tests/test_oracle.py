@@ -162,11 +162,33 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert afb200.lib().af_last_error() is not None
 
 
-def test_struct_layouts_match_header():
-    assert ctypes.sizeof(afb200._lib.AfConvDesc) == 16 + 11 * 4 + 4
-    assert ctypes.sizeof(afb200._lib.AfBlockDesc) == 20
-    assert ctypes.sizeof(afb200._lib.AfFrameDesc) == 40
-    assert ctypes.sizeof(afb200._lib.AfClipGeom) == 64
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every struct in include/afb200.h as gcc sees them == the ctypes mirrors in _lib.py."""
+    import shutil
+    import subprocess
+    L = afb200._lib
+    structs = {"af_conv_desc": L.AfConvDesc, "af_block_desc": L.AfBlockDesc, "af_tt_layer": L.AfTTLayer,
+               "af_tt_head": L.AfTTHead, "af_weights": L.AfWeights, "af_frame_desc": L.AfFrameDesc,
+               "af_clip_geom": L.AfClipGeom}
+    assert ctypes.sizeof(L.AfConvDesc) == 16 + 11 * 4 + 4 and ctypes.sizeof(L.AfBlockDesc) == 24
+    assert ctypes.sizeof(L.AfFrameDesc) == 40 and ctypes.sizeof(L.AfClipGeom) == 64
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "afb200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
 
 
 def test_folded_weights_struct(state_dict):
