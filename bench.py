@@ -21,6 +21,7 @@ import sys
 import threading
 import time
 
+_emit = print          # replaced by _QuietStdout.emit when run as a script
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -174,7 +175,7 @@ def run_reference(args):
                              "sample": "%d steps x %d clip (cv2.warpAffine crop + fp32 torch forward of the oracle port)" % (args.steps, clips_per_step)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------- our arm
@@ -367,14 +368,38 @@ def run_ours(args):
                              "whole_step_frac_of_tensor_roofline": value / world * FLOPS_PER_CLIP / (peak * 1e12)},
                 "cpu_baseline": cpu_baseline, "clocks": clocks, "p50_batch1_latency_ms": p50, "p99_batch1_latency_ms": p99,
                 "k1_src_bytes_per_clip": src_bytes / B}
-        print(json.dumps(line), flush=True)
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+class _QuietStdout:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the
+    first communicator when NCCL_DEBUG is set in the environment), so everything but our own line goes to stderr:
+    file descriptor 1 points at stderr while the benchmark runs and is restored for the final print."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self._saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    with _QuietStdout() as out:
+        _emit = out.emit
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_ours(a)
