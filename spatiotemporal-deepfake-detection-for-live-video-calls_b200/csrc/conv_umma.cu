@@ -576,6 +576,13 @@ int build_plan(const ConvProblem& p, UmmaPlan& plan) {
   for (int cand : {256, 128}) {
     if (p.Cout % cand == 0 && (long long)up.num_m_tiles * (p.Cout / cand) >= 2LL * g_num_sms) { bn = cand; break; }
   }
+  // Residual layers with a very short K (s2 / s3 `c` convs: K = 64 / 128) are pure HBM streams: narrower tiles give
+  // them two output slots per epilogue group and a deeper operand ring (measured on B200, 32 clips: K=64 5.4 -> 6.5 TB/s
+  // at BLOCK_N 64, K=128 5.45 -> 5.7 TB/s at BLOCK_N 128; wider K is better off at 256)
+  if (p.res && !p.x2 && pointwise) {
+    if (p.Cin <= 64) bn = 64;
+    else if (p.Cin <= 128 && bn > 128) bn = 128;
+  }
   static const char* fbn = getenv("AFB200_BLOCK_N");
   if (fbn) { int v = atoi(fbn); if ((v == 64 || v == 128 || v == 256) && p.Cout % v == 0) bn = v; }
   up.num_n_tiles = p.Cout / bn;
