@@ -300,24 +300,41 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         clip_bytes = 32 * 224 * 224 * 3
-        host = torch.empty((B, 32, 224, 224, 3), dtype=torch.uint8).pin_memory()
-        host.random_(0, 256)
-        h_logits = torch.empty(B, dtype=torch.float32).pin_memory()
-        h_scores = torch.empty(B, dtype=torch.float32).pin_memory()
-        for _ in range(2):
-            eng.infer_u8_host_ptr(host.data_ptr(), B, h_logits.data_ptr(), h_scores.data_ptr())
+        # two pinned input batches, used alternately: every step uploads its own clips and reads its own scores back;
+        # the pipelined service call (af_submit_u8_host / af_wait = ClassifierSvc.infer_scores_stream) lets the upload
+        # of step i+1 overlap the compute of step i
+        hosts = [torch.empty((B, 32, 224, 224, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        for h_ in hosts:
+            h_.random_(0, 256)
+        for i in range(2):
+            eng.wait(eng.submit_u8_host_ptr(hosts[i].data_ptr(), B), B)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         n_e2e = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            eng.infer_u8_host_ptr(host.data_ptr(), B, h_logits.data_ptr(), h_scores.data_ptr())
+        pending = eng.submit_u8_host_ptr(hosts[0].data_ptr(), B)
+        for i in range(1, n_e2e):
+            nxt = eng.submit_u8_host_ptr(hosts[i & 1].data_ptr(), B)
+            scores_h, _ = eng.wait(pending, B)
+            pending = nxt
+        scores_h, _ = eng.wait(pending, B)
         torch.cuda.synchronize()
         dt = parallel.max_over_ranks(time.perf_counter() - t0, dev)
         e2e = {"value": n_total * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": B * clip_bytes,
                "d2h_bytes_per_step": 8 * B, "steps": n_e2e,
-               "api": "af_infer_u8_host (ClassifierSvc.infer_scores boundary): pinned u8 [B,32,224,224,3] -> scores"}
+               "api": "af_submit_u8_host + af_wait (ClassifierSvc.infer_scores_stream: pinned u8 [B,32,224,224,3] -> scores "
+                      "on the host, two batches in flight)"}
+        # the one-call-at-a-time form of the same boundary (ClassifierSvc.infer_scores), for comparison
+        h_logits = torch.empty(B, dtype=torch.float32).pin_memory()
+        h_scores = torch.empty(B, dtype=torch.float32).pin_memory()
+        eng.infer_u8_host_ptr(hosts[0].data_ptr(), B, h_logits.data_ptr(), h_scores.data_ptr())
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            eng.infer_u8_host_ptr(hosts[i & 1].data_ptr(), B, h_logits.data_ptr(), h_scores.data_ptr())
+        torch.cuda.synchronize()
+        dt = parallel.max_over_ranks(time.perf_counter() - t0, dev)
+        e2e["blocking_call_value"] = n_total * n_e2e / dt
 
     # p50 batch-1 latency (crop + trunk + score on host), rank 0 only
     p50 = p99 = None

@@ -186,6 +186,17 @@ af_status af_infer_u8_host(af_handle h, const uint8_t* clips_host, int32_t batch
                            const float mean255[3], const float std255[3], float* logits_host,
                            float* scores_host, void* stream);
 
+/* Pipelined form of af_infer_u8_host for callers that score batch after batch (the flush loops of
+ * altfreezing/TEST2.py:393-439 and test/af_realtime.py:318-360, batch_eval-style offline scoring): af_submit_u8_host
+ * starts the upload of `clips_host` on an internal copy stream, queues pack + trunk + the read-back of logits and
+ * scores behind it on `stream`, and returns at once with a ticket (0 or 1); af_wait blocks until that submission's
+ * results are on the host and copies them out.  Two submissions may be outstanding, so the upload of batch i+1
+ * overlaps the compute of batch i.  `clips_host` must stay valid until af_wait returns (pinned memory for a truly
+ * asynchronous copy); results of a ticket must be collected before the slot is submitted to again. */
+af_status af_submit_u8_host(af_handle h, const uint8_t* clips_host, int32_t batch, const float mean255[3],
+                            const float std255[3], void* stream, int32_t* ticket);
+af_status af_wait(af_handle h, int32_t ticket, float* logits_host, float* scores_host);
+
 /* FasterCropAlignXRay.process_single for a batch of clips, bit-exact with
  * cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) (faster_crop_align_xray.py:77-88):
  * gathers straight from the decoded frames (frames[b*T+t]), masks to each frame's big

@@ -58,7 +58,7 @@ class AfClipGeom(C.Structure):
 
 
 EXPORTS = ("af_last_error", "af_version", "af_launch_count", "af_create", "af_destroy", "af_set_option",
-           "af_forward", "af_forward_frames", "af_infer_u8", "af_infer_u8_host", "af_crop_u8", "af_crop_infer",
+           "af_forward", "af_forward_frames", "af_infer_u8", "af_infer_u8_host", "af_submit_u8_host", "af_wait", "af_crop_u8", "af_crop_infer",
            "af_conv_ndhwc", "af_conv_shortcut_ndhwc", "af_get_stage", "af_get_stat")
 
 _lib = None
@@ -97,6 +97,10 @@ def lib():
     L.af_infer_u8.argtypes = [vp, vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), f32p, f32p, f32p, vp]
     L.af_infer_u8_host.restype = i32
     L.af_infer_u8_host.argtypes = [vp, vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), f32p, f32p, vp]
+    L.af_submit_u8_host.restype = i32
+    L.af_submit_u8_host.argtypes = [vp, vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), vp, C.POINTER(i32)]
+    L.af_wait.restype = i32
+    L.af_wait.argtypes = [vp, i32, f32p, f32p]
     L.af_crop_u8.restype = i32
     L.af_crop_u8.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     L.af_crop_infer.restype = i32

@@ -203,6 +203,15 @@ struct af_engine {
   cudaStream_t copy_stream = nullptr;          // H2D of host clips, overlapped with the trunk
   std::vector<cudaEvent_t> copy_events;
   float* out_stage = nullptr;  // [2*max_batch] logits, scores (device staging for *_host calls)
+  // pipelined host API (af_submit_u8_host / af_wait): two slots, each with its own staging and events
+  struct HostSlot {
+    uint8_t* u8_dev = nullptr;      // [max_batch] u8 clips
+    float* out_dev = nullptr;       // [2*max_batch] logits, scores
+    float* out_pinned = nullptr;    // same, pinned host memory
+    cudaEvent_t copied = nullptr, done = nullptr;
+    int batch = 0;                  // > 0 while a submission is outstanding
+  } host_slot[2];
+  int next_slot = 0;
   // event-based conv timing (option profile_events)
   bool profile_events = false;
   struct EvRec { cudaEvent_t e0, e1; int kind; double flops, bytes; };
@@ -665,6 +674,13 @@ af_status af_destroy(af_handle h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (auto ev : h->copy_events) cudaEventDestroy(ev);
   if (h->out_stage) cudaFree(h->out_stage);
+  for (auto& hs : h->host_slot) {
+    if (hs.u8_dev) cudaFree(hs.u8_dev);
+    if (hs.out_dev) cudaFree(hs.out_dev);
+    if (hs.out_pinned) cudaFreeHost(hs.out_pinned);
+    if (hs.copied) cudaEventDestroy(hs.copied);
+    if (hs.done) cudaEventDestroy(hs.done);
+  }
   for (int i = 0; i < 5; ++i)
     if (h->stage_buf[i]) cudaFree(h->stage_buf[i]);
   for (auto& r : h->ev_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -989,6 +1005,63 @@ af_status af_infer_u8_host(af_handle h, const uint8_t* clips_host, int32_t batch
   if (scores_host)
     AFB_CUDA(cudaMemcpyAsync(scores_host, h->out_stage + h->max_batch, batch * sizeof(float), cudaMemcpyDeviceToHost, s));
   AFB_CUDA(cudaStreamSynchronize(s));
+  return AF_OK;
+}
+
+af_status af_submit_u8_host(af_handle h, const uint8_t* clips_host, int32_t batch, const float mean255[3],
+                            const float std255[3], void* stream, int32_t* ticket) {
+  af_status rc = check_batch(h, batch, "af_submit_u8_host");
+  if (rc) return rc;
+  if (!clips_host || !mean255 || !std255 || !ticket) { set_error("af_submit_u8_host: null pointer"); return AF_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  AFB_CUDA(cudaSetDevice(h->device));
+  const int slot = h->next_slot;
+  af_engine::HostSlot& hs = h->host_slot[slot];
+  if (hs.batch > 0) {
+    set_error("af_submit_u8_host: both slots are outstanding; call af_wait on ticket %d first", slot);
+    return AF_ERR_INVALID;
+  }
+  const size_t clip_bytes = (size_t)h->T * h->S * h->S * 3;
+  if (!hs.u8_dev) {
+    AFB_CUDA(cudaMalloc(&hs.u8_dev, (size_t)h->max_batch * clip_bytes));
+    AFB_CUDA(cudaMalloc(&hs.out_dev, (size_t)2 * h->max_batch * sizeof(float)));
+    AFB_CUDA(cudaMallocHost(&hs.out_pinned, (size_t)2 * h->max_batch * sizeof(float)));
+    AFB_CUDA(cudaEventCreateWithFlags(&hs.copied, cudaEventDisableTiming));
+    AFB_CUDA(cudaEventCreateWithFlags(&hs.done, cudaEventDisableTiming));
+  }
+  if (!h->copy_stream) AFB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  // The upload runs on the copy stream, so it overlaps whatever the compute stream is still doing for the previous
+  // submission; the slot's previous user finished before its af_wait returned, so the staging buffer is free.
+  AFB_CUDA(cudaMemcpyAsync(hs.u8_dev, clips_host, (size_t)batch * clip_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  AFB_CUDA(cudaEventRecord(hs.copied, h->copy_stream));
+  AFB_CUDA(cudaStreamWaitEvent(s, hs.copied, 0));
+  {
+    const long long before = g_launches;
+    Feeder feed = [&](int f0, int fB, cudaStream_t st) {
+      return pack_u8_launch(hs.u8_dev + (size_t)f0 * clip_bytes, fB, mean255, std255, clip_at(h, f0), st);
+    };
+    int r = run_trunk(h, batch, feed, hs.out_dev, hs.out_dev + h->max_batch, nullptr, s);
+    h->launches += g_launches - before;
+    if (r) return (af_status)r;
+  }
+  AFB_CUDA(cudaMemcpyAsync(hs.out_pinned, hs.out_dev, (size_t)2 * h->max_batch * sizeof(float), cudaMemcpyDeviceToHost, s));
+  AFB_CUDA(cudaEventRecord(hs.done, s));
+  hs.batch = batch;
+  h->next_slot = slot ^ 1;
+  *ticket = slot;
+  return AF_OK;
+}
+
+af_status af_wait(af_handle h, int32_t ticket, float* logits_host, float* scores_host) {
+  if (!h || ticket < 0 || ticket > 1) { set_error("af_wait: invalid handle or ticket"); return AF_ERR_INVALID; }
+  af_engine::HostSlot& hs = h->host_slot[ticket];
+  if (hs.batch <= 0) { set_error("af_wait: ticket %d is not outstanding", ticket); return AF_ERR_INVALID; }
+  AFB_CUDA(cudaSetDevice(h->device));
+  const int batch = hs.batch;
+  hs.batch = 0;                                   // the slot is free again even if the wait reports an error
+  AFB_CUDA(cudaEventSynchronize(hs.done));
+  if (logits_host) memcpy(logits_host, hs.out_pinned, batch * sizeof(float));
+  if (scores_host) memcpy(scores_host, hs.out_pinned + h->max_batch, batch * sizeof(float));
   return AF_OK;
 }
 

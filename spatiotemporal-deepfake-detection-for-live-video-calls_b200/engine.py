@@ -161,6 +161,24 @@ class Engine:
                                            _fptr(self.std255), C.c_void_p(logits_ptr), C.c_void_p(scores_ptr),
                                            self._stream()), "af_infer_u8_host")
 
+    def submit_u8_host_ptr(self, host_ptr: int, batch: int) -> int:
+        """Pipelined scoring (af_submit_u8_host): queue upload + pack + trunk + read-back of `batch` u8 clips at
+        `host_ptr` (pinned memory) and return a ticket at once; at most two tickets may be outstanding."""
+        t = C.c_int32(-1)
+        with torch.cuda.device(self.device):
+            check(self._L.af_submit_u8_host(self._h, C.c_void_p(host_ptr), batch, _fptr(self.mean255), _fptr(self.std255),
+                                            self._stream(), C.byref(t)), "af_submit_u8_host")
+        return int(t.value)
+
+    def wait(self, ticket: int, batch: int):
+        """Block until `ticket`'s results are on the host -> (scores, logits) float32 [batch]."""
+        logits = np.empty(batch, np.float32)
+        scores = np.empty(batch, np.float32)
+        with torch.cuda.device(self.device):
+            check(self._L.af_wait(self._h, int(ticket), C.c_void_p(logits.ctypes.data), C.c_void_p(scores.ctypes.data)),
+                  "af_wait")
+        return scores, logits
+
     def crop_infer(self, frames_dev: torch.Tensor, geom_dev: torch.Tensor, batch: int, bgr: bool = False,
                    return_features: bool = False):
         """frames_dev: u8 tensor holding af_frame_desc[batch*T]; geom_dev: af_clip_geom[batch]

@@ -41,6 +41,25 @@ class ClassifierSvc:
         self._last_scores, self._last_logits = scores.copy(), logits
         return scores
 
+    def infer_scores_stream(self, batches):
+        """Generator form for callers that score batch after batch (TEST2.py:393-439's flush loop over a whole
+        video, batch_eval-style offline scoring): yields the same float32[B] per input batch, but the upload of batch
+        i+1 overlaps the compute of batch i (af_submit_u8_host / af_wait).  Batches of at most max_batch clips."""
+        pending = None                      # (ticket, batch size, pinned tensor kept alive)
+        for arr in batches:
+            arr = np.ascontiguousarray(arr, dtype=np.uint8)
+            if arr.ndim != 5 or arr.shape[1:] != (self.clip_size, self.imsize, self.imsize, 3) or \
+                    arr.shape[0] > self.engine.max_batch:
+                raise ValueError("infer_scores_stream expects u8 [B<=%d,%d,%d,%d,3], got %s" %
+                                 (self.engine.max_batch, self.clip_size, self.imsize, self.imsize, arr.shape))
+            pin = torch.from_numpy(arr).pin_memory()
+            ticket = self.engine.submit_u8_host_ptr(pin.data_ptr(), arr.shape[0])
+            if pending is not None:
+                yield self.engine.wait(pending[0], pending[1])[0]
+            pending = (ticket, arr.shape[0], pin)
+        if pending is not None:
+            yield self.engine.wait(pending[0], pending[1])[0]
+
 
 class CropAlignSvc:
     def __init__(self, imsize: int = 224, device: int = 0):

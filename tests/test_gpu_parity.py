@@ -374,6 +374,29 @@ def test_service_infer_scores(dev, state_dict, clips_u8, oracle_out):
         svc.infer_scores(clips_u8[:, :8])
 
 
+def test_pipelined_host_api_matches_blocking_call(dev, state_dict, clips_u8):
+    """af_submit_u8_host / af_wait (two batches in flight) == af_infer_u8_host, batch by batch, incl. a ragged one."""
+    svc = afb200.ClassifierSvc(state_dict, device=0, precision="bf16", max_batch=3)
+    batches = [clips_u8[:3], clips_u8[1:4], clips_u8[3:4], clips_u8[:2]]
+    want = [svc.infer_scores(b).copy() for b in batches]
+    got = list(svc.infer_scores_stream(batches))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and np.array_equal(g, w)
+    # a third submission without collecting the first is refused, not queued over live results
+    eng = svc.engine
+    pin = torch.from_numpy(np.ascontiguousarray(clips_u8[:1])).pin_memory()
+    t0 = eng.submit_u8_host_ptr(pin.data_ptr(), 1)
+    t1 = eng.submit_u8_host_ptr(pin.data_ptr(), 1)
+    with pytest.raises(afb200.Afb200Error):
+        eng.submit_u8_host_ptr(pin.data_ptr(), 1)
+    s0, _ = eng.wait(t0, 1)
+    s1, _ = eng.wait(t1, 1)
+    assert np.array_equal(s0, s1) and np.array_equal(s0, want[0][:1])
+    with pytest.raises(afb200.Afb200Error):
+        eng.wait(t0, 1)
+
+
 def test_linearity_property_of_conv_at_full_size(dev):
     """Size-independent property at a full BASELINE layer size (s2 1x3x3, one clip):
     conv(x1 + x2) == conv(x1) + conv(x2) without bias/ReLU, up to bf16 rounding."""
