@@ -265,6 +265,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    eng.set_option("ridge_x1000", int(1e3 * peaks["bf16_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)))
     eng.set_option("reset_stats", 1)
     eng.set_option("profile_events", 1)
     launches0 = eng.launch_count
@@ -289,6 +290,8 @@ def run_ours(args):
     clocks = sampler.stop(t_load0, time.time()) if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "warm-up + timed region + %d untimed steps of the same load" % extra
+    tb_ms, tb_flops, tb_n = (eng.get_stat("conv_tensor_bound_" + k) for k in ("ms", "flops", "launches"))
+    hb_ms, hb_bytes, hb_n = (eng.get_stat("conv_hbm_bound_" + k) for k in ("ms", "bytes", "launches"))
     conv_ms = eng.get_stat("conv_umma_ms")
     conv_flops = eng.get_stat("conv_umma_flops")
     conv_n = eng.get_stat("conv_umma_launches")
@@ -382,7 +385,19 @@ def run_ours(args):
                              "share_of_step": conv_ms / ms if ms > 0 else None,
                              "peak_source": "%s bf16_tflops_sustained (MEASURED_PEAKS.json)" % peaks["source"],
                              "simt_conv_ms_per_step": simt_ms / args.steps,
-                             "whole_step_frac_of_tensor_roofline": value / world * FLOPS_PER_CLIP / (peak * 1e12)},
+                             "whole_step_frac_of_tensor_roofline": value / world * FLOPS_PER_CLIP / (peak * 1e12),
+                             # the same launches split by the roofline that bounds each (algorithmic FLOP/byte of the
+                             # launch vs the ridge peak_tflops / peak_hbm): how close each class runs to ITS limit
+                             "classes": {
+                                 "tensor_bound": {"launches_per_step": tb_n / args.steps, "ms_per_step": tb_ms / args.steps,
+                                                  "achieved": tb_flops / (tb_ms * 1e9) if tb_ms > 0 else None,
+                                                  "peak": peak, "unit": "TFLOP/s",
+                                                  "frac": tb_flops / (tb_ms * 1e9) / peak if tb_ms > 0 else None},
+                                 "hbm_bound": {"launches_per_step": hb_n / args.steps, "ms_per_step": hb_ms / args.steps,
+                                               "achieved": hb_bytes / (hb_ms * 1e6) if hb_ms > 0 else None,
+                                               "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                               "frac": hb_bytes / (hb_ms * 1e6) / peaks["hbm_gbs"] if hb_ms > 0 else None,
+                                               "bytes": "algorithmic (input + output + residual + weights of each launch)"}}},
                 "cpu_baseline": cpu_baseline, "clocks": clocks, "p50_batch1_latency_ms": p50, "p99_batch1_latency_ms": p99,
                 "k1_src_bytes_per_clip": src_bytes / B}
         _emit(json.dumps(line))

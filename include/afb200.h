@@ -148,7 +148,11 @@ af_status af_destroy(af_handle h);
  * below synchronise the device and aggregate them since the last "reset_stats" option call:
  *   "conv_umma_ms" / "conv_umma_launches" / "conv_umma_flops"   tcgen05 conv kernel
  *   "conv_simt_ms" / "conv_simt_launches" / "conv_simt_flops"   CUDA-core conv kernel
- *   "conv_bytes"                                                algorithmic activation+weight bytes of all convs */
+ *   "conv_bytes"                                                algorithmic activation+weight bytes of all convs
+ * The tcgen05 launches are also split by which roofline bounds them — algorithmic FLOP/byte of the launch against the
+ * ridge set with option "ridge_x1000" (1000 x peak FLOP/s / peak byte/s; default 208):
+ *   "conv_tensor_bound_ms" / "_flops" / "_launches"             launches above the ridge
+ *   "conv_hbm_bound_ms" / "_bytes" / "_flops" / "_launches"     launches below it */
 af_status af_get_stat(af_handle h, const char* name, double* value);
 
 /* Tuning knobs (chunk sizes of the batch schedule); name/value pairs, optional. */

@@ -217,7 +217,11 @@ struct af_engine {
   struct EvRec { cudaEvent_t e0, e1; int kind; double flops, bytes; };
   std::vector<EvRec> ev_recs;
   std::vector<cudaEvent_t> ev_pool;
-  double stat_ms[2] = {0, 0}, stat_flops[2] = {0, 0}, stat_launches[2] = {0, 0}, stat_bytes = 0;
+  // kind 0: tcgen05 launch whose algorithmic intensity is above the roofline ridge (tensor-bound), 1: CUDA-core conv,
+  // 2: tcgen05 launch below the ridge (HBM-bound)
+  double stat_ms[3] = {0, 0, 0}, stat_flops[3] = {0, 0, 0}, stat_launches[3] = {0, 0, 0}, stat_kbytes[3] = {0, 0, 0};
+  double stat_bytes = 0;
+  double ridge_flop_per_byte = 208.0;   // measured sustained bf16 TFLOP/s / measured HBM TB/s (option "ridge_x1000")
   // kept stages (fp32 NCTHW) for parity tests
   float* stage_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   Dims stage_dims[5];
@@ -278,7 +282,8 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
   const double K2d = sc ? (double)sc->L->cin_p : 0.0;
   const double conv_flops = 2.0 * (double)p.M * L.cout * (Kd + K2d);
   const double conv_bytes = ((double)B * in.elems() + (sc ? (double)B * sc->in.elems() : 0.0) +
-                             (double)p.M * L.cout * (res ? 2 : 1) + (Kd + K2d) * L.cout) * (is_bf16 ? 2.0 : 4.0);
+                             (double)p.M * L.cout * ((res ? 1.0 : 0.0) + (pool_t ? 0.5 : pool_hw ? 0.25 : 1.0)) +
+                             (Kd + K2d) * L.cout) * (is_bf16 ? 2.0 : 4.0);
   ProfRec prec(e, s);
   p.w = L.w_umma;
   if (pool_hw && !(is_bf16 && (impl == 0 || impl == 3) && conv_rows_supported(p))) {
@@ -312,7 +317,7 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
     p.w = L.w_simt;
     rc = conv_simt_launch(p, is_bf16, s);
   }
-  prec.done(which[0] == 'u' ? 0 : 1, conv_flops, conv_bytes);
+  prec.done(which[0] != 'u' ? 1 : (conv_flops >= (e ? e->ridge_flop_per_byte : 208.0) * conv_bytes ? 0 : 2), conv_flops, conv_bytes);
   if (OpTrace::enabled()) {
     char nm[128];
     snprintf(nm, sizeof(nm), "conv %s k%dx%dx%d s%d M=%lld N=%d K=%d%s%s", which, L.kt, L.kh, L.kw, L.sh, p.M, L.cout,
@@ -854,12 +859,13 @@ af_status af_set_option(af_handle h, const char* name, int64_t value) {
   if (n == "conv_impl") { h->conv_impl = (int)value; return AF_OK; }
   if (n == "sm_limit") { h->sm_limit = (int)value; return AF_OK; }
   if (n == "profile_events") { h->profile_events = value != 0; return AF_OK; }
+  if (n == "ridge_x1000") { h->ridge_flop_per_byte = (double)value / 1000.0; return AF_OK; }
   if (n == "reset_stats") {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (auto& r : h->ev_recs) { h->ev_pool.push_back(r.e0); h->ev_pool.push_back(r.e1); }
     h->ev_recs.clear();
-    for (int k = 0; k < 2; ++k) h->stat_ms[k] = h->stat_flops[k] = h->stat_launches[k] = 0;
+    for (int k = 0; k < 3; ++k) h->stat_ms[k] = h->stat_flops[k] = h->stat_launches[k] = h->stat_kbytes[k] = 0;
     h->stat_bytes = 0;
     return AF_OK;
   }
@@ -884,15 +890,23 @@ af_status af_get_stat(af_handle h, const char* name, double* value) {
   for (auto& r : h->ev_recs) {          // fold finished event pairs into the running sums
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
-      h->stat_ms[r.kind] += ms; h->stat_flops[r.kind] += r.flops; h->stat_launches[r.kind] += 1; h->stat_bytes += r.bytes;
+      h->stat_ms[r.kind] += ms; h->stat_flops[r.kind] += r.flops; h->stat_launches[r.kind] += 1; h->stat_kbytes[r.kind] += r.bytes;
+      h->stat_bytes += r.bytes;
     }
     h->ev_pool.push_back(r.e0); h->ev_pool.push_back(r.e1);
   }
   h->ev_recs.clear();
   std::string n(name);
-  if (n == "conv_umma_ms") *value = h->stat_ms[0];
-  else if (n == "conv_umma_flops") *value = h->stat_flops[0];
-  else if (n == "conv_umma_launches") *value = h->stat_launches[0];
+  if (n == "conv_umma_ms") *value = h->stat_ms[0] + h->stat_ms[2];
+  else if (n == "conv_umma_flops") *value = h->stat_flops[0] + h->stat_flops[2];
+  else if (n == "conv_umma_launches") *value = h->stat_launches[0] + h->stat_launches[2];
+  else if (n == "conv_tensor_bound_ms") *value = h->stat_ms[0];
+  else if (n == "conv_tensor_bound_flops") *value = h->stat_flops[0];
+  else if (n == "conv_tensor_bound_launches") *value = h->stat_launches[0];
+  else if (n == "conv_hbm_bound_ms") *value = h->stat_ms[2];
+  else if (n == "conv_hbm_bound_bytes") *value = h->stat_kbytes[2];
+  else if (n == "conv_hbm_bound_flops") *value = h->stat_flops[2];
+  else if (n == "conv_hbm_bound_launches") *value = h->stat_launches[2];
   else if (n == "conv_simt_ms") *value = h->stat_ms[1];
   else if (n == "conv_simt_flops") *value = h->stat_flops[1];
   else if (n == "conv_simt_launches") *value = h->stat_launches[1];
