@@ -198,7 +198,8 @@ struct af_engine {
   void* fbuf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   void* bbuf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   void* gbuf = nullptr;      // group input of the back part [cb_back, ...]
-  float* feat_ws = nullptr;  // [max_batch, feat_dim]
+  float* feat_ws = nullptr;  // [max_batch * HEAD slices, feat_dim] pooled-feature partial sums (pool_head.cu)
+  int feat_slices = 16;
   uint8_t* u8_stage = nullptr;
   cudaStream_t copy_stream = nullptr;          // H2D of host clips, overlapped with the trunk
   std::vector<cudaEvent_t> copy_events;
@@ -575,7 +576,8 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
       if (rc) return rc;
       trh.done("head frame means + transformer", 0.0, (double)gB * d.elems() * e->esz);
     } else {
-      rc = head_launch(x, gB, d.T * d.H * d.W, d.C, e->is_bf16, e->fc_w, e->fc_b, e->feat_ws + (long long)g0 * e->feat_dim,
+      rc = head_launch(x, gB, d.T * d.H * d.W, d.C, e->is_bf16, e->fc_w, e->fc_b,
+                       e->feat_ws + (long long)g0 * e->feat_slices * e->feat_dim,
                        features ? features + (long long)g0 * e->feat_dim : nullptr, logits ? logits + g0 : nullptr,
                        scores ? scores + g0 : nullptr, s);
       if (rc) return rc;
@@ -585,8 +587,7 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
       AFB_CUDA(cudaMemcpyAsync(e->frame_feat_out + (long long)g0 * d.T * e->feat_dim, e->tok_ws,
                                (size_t)gB * d.T * d.C * sizeof(float), cudaMemcpyDeviceToDevice, s));
     } else if (e->frame_feat_out) {     // per-frame spatial means [gB*T', C]: the same pooling kernel over H*W positions
-      rc = head_launch(x, gB * d.T, d.H * d.W, d.C, e->is_bf16, e->fc_w, e->fc_b,
-                       e->frame_feat_out + (long long)g0 * d.T * e->feat_dim, nullptr, nullptr, nullptr, s);
+      rc = spatial_mean_launch(x, gB * d.T, d.H * d.W, d.C, e->is_bf16, e->frame_feat_out + (long long)g0 * d.T * e->feat_dim, s);
       if (rc) return rc;
     }
   }
@@ -814,7 +815,7 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
   if (e->cb_front > e->cb_back) e->cb_front = e->cb_back;
   rc = alloc_workspace(e);
   if (rc) return (af_status)rc;
-  AFB_CUDA(cudaMalloc(&e->feat_ws, (size_t)e->max_batch * e->feat_dim * sizeof(float)));
+  AFB_CUDA(cudaMalloc(&e->feat_ws, (size_t)e->max_batch * e->feat_slices * e->feat_dim * sizeof(float)));
   AFB_CUDA(cudaMalloc(&e->out_stage, (size_t)2 * e->max_batch * sizeof(float)));
   if (e->has_tt) {
     AFB_CUDA(cudaMalloc(&e->tt_ws, (size_t)tt_head_workspace_floats(e->tt, e->max_batch) * sizeof(float)));
@@ -859,6 +860,7 @@ af_status af_set_option(af_handle h, const char* name, int64_t value) {
   if (n == "conv_impl") { h->conv_impl = (int)value; return AF_OK; }
   if (n == "sm_limit") { h->sm_limit = (int)value; return AF_OK; }
   if (n == "profile_events") { h->profile_events = value != 0; return AF_OK; }
+  if (n == "dump_timeline") { conv_umma_timeline_dump((int)value); return AF_OK; }
   if (n == "ridge_x1000") { h->ridge_flop_per_byte = (double)value / 1000.0; return AF_OK; }
   if (n == "reset_stats") {
     cudaSetDevice(h->device);

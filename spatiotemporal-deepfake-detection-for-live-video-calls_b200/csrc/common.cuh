@@ -69,6 +69,7 @@ int conv_simt_launch(const ConvProblem& p, bool is_bf16, cudaStream_t s);
 bool conv_umma_supported(const ConvProblem& p);
 int conv_umma_launch(const ConvProblem& p, cudaStream_t s);
 int conv_umma_init();
+void conv_umma_timeline_dump(int n);
 // conv_rows.cu (row-halo tcgen05 kernel for Cout=64 layers with vertical taps)
 bool conv_rows_supported(const ConvProblem& p);
 int conv_rows_launch(const ConvProblem& p, cudaStream_t s);
@@ -84,6 +85,7 @@ int maxpool_spatial_launch(const void* x, void* y, int B, int T, int H, int W, i
                            cudaStream_t s);   // k[1,3,3] s[1,2,2] p[0,1,1]
 int maxpool_temporal_launch(const void* x, void* y, int B, int T, int H, int W, int C, bool is_bf16,
                             cudaStream_t s);  // k[2,1,1] s[2,1,1]
+int head_pool_slices(int P);      // partial-sum slices head_launch uses for P positions (sizes features_ws)
 int head_launch(const void* x, int B, int P, int C, bool is_bf16, const float* fc_w, float fc_b,
                 float* features_ws, float* features_out, float* logits, float* scores,
                 cudaStream_t s);

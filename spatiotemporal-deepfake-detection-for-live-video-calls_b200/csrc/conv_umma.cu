@@ -27,6 +27,7 @@
 // Programmatic dependent launch overlaps each kernel's prologue with its predecessor's tail.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstring>
 #include <unordered_map>
 
@@ -63,6 +64,7 @@ struct UmmaParams {
   // second operand source (fused projection shortcut): a pointwise conv of stride [1,sh2,sw2] over another
   // tensor, accumulated into the same TMEM tile after the primary taps (0 channel blocks = none)
   int cblocks2, im2col2, sh2, sw2;
+  unsigned long long* dbg;   // AFB200_TIMELINE=1: CTA 0 stamps %globaltimer at its phase boundaries (bring-up aid)
 };
 
 constexpr int MAX_STAGES = 8;
@@ -87,6 +89,14 @@ template <int CHUNKS> struct EpiIter {
   }
 };
 
+__device__ __forceinline__ void stamp(const UmmaParams& p, int slot) {
+  if (p.dbg && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.dbg[slot] = t;
+  }
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -97,6 +107,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr int CHUNKS = BLOCK_N / 64;
   pdl_launch_dependents();
+  if (threadIdx.x == 0) stamp(p, 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const bool has_res = p.res != nullptr;
@@ -141,7 +152,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  if (threadIdx.x == 0) stamp(p, 1);
   pdl_wait_prior_grid();      // everything above overlapped the previous kernel's tail
+  if (threadIdx.x == 0) stamp(p, 2);
 
   if (warp == 0) {
     // ===================================================== TMA producer (all lanes walk the loop,
@@ -223,6 +236,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int kb = 0; kb < num_kb_all; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (it == 0 && kb == 0 && lane == 0) stamp(p, 3);
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(a_addr);
           const uint64_t bdesc = make_smem_desc(a_addr + A_STAGE_BYTES);
@@ -239,6 +253,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         if (elect_one()) umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
         __syncwarp();
+        if (lane == 0) stamp(p, 4);                     // (last tile's value survives)
       }
     }
   } else {
@@ -357,7 +372,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (has_res && pre.valid()) { issue_res(pre, slot); pre.next(); }   // refill the slot just drained
       }
     }
+    if (et == 0 && eg == 0) stamp(p, 5);
     if (et == 0) tma_store_wait<0>();
+    if (et == 0 && eg == 0) stamp(p, 6);
   }
 
   tc_fence_before();
@@ -366,6 +383,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
+  if (threadIdx.x == 0) stamp(p, 7);
 }
 
 // ---------------------------------------------------------------- host side
@@ -384,6 +402,10 @@ int g_driver_version = 0;
 bool g_corner_dhw = false;    // AFB200_IM2COL_CORNERS=dhw flips the corner array order (bring-up knob)
 
 int g_max_smem = 0;
+unsigned long long* g_timeline = nullptr;      // AFB200_TIMELINE=1
+struct TimelineInfo { int grid, tiles, kblocks, bn; };
+TimelineInfo g_timeline_info[256];
+long long g_timeline_n = 0;
 
 template <int BLOCK_N>
 int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const CUtensorMap& tr,
@@ -415,6 +437,12 @@ int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  up.dbg = nullptr;
+  if (g_timeline) {                      // ring of 256 launches x 8 stamps, dumped by conv_umma_timeline_dump()
+    up.dbg = g_timeline + (size_t)(g_timeline_n % 256) * 8;
+    g_timeline_info[g_timeline_n % 256] = {grid, tiles, up.kt * up.kh * up.kw * (up.Cin / BLOCK_K) + up.cblocks2, BLOCK_N};
+    ++g_timeline_n;
+  }
   AFB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ty, tr, ta2, tb2, up));
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
@@ -482,9 +510,35 @@ int conv_umma_init() {
   AFB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   AFB_CUDA(cudaDriverGetVersion(&g_driver_version));
   AFB_CUDA(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const char* tl = getenv("AFB200_TIMELINE");
+  if (tl && tl[0] == '1' && !g_timeline) {
+    AFB_CUDA(cudaMalloc(&g_timeline, 256 * 8 * sizeof(unsigned long long)));
+    AFB_CUDA(cudaMemset(g_timeline, 0, 256 * 8 * sizeof(unsigned long long)));
+  }
   const char* c = getenv("AFB200_IM2COL_CORNERS");
   g_corner_dhw = c && c[0] == 'd';
   return AF_OK;
+}
+
+// AFB200_TIMELINE=1: print, for the last `n` conv_umma launches, CTA 0's phase boundaries in microseconds relative to
+// the previous launch's end: entry, prologue done, prior grid done, first operands landed, last MMA issued, last store
+// issued, stores drained, exit.
+void conv_umma_timeline_dump(int n) {
+  if (!g_timeline) return;
+  cudaDeviceSynchronize();
+  static unsigned long long host[256 * 8];
+  cudaMemcpy(host, g_timeline, sizeof(host), cudaMemcpyDeviceToHost);
+  long long first = g_timeline_n - n < 0 ? 0 : g_timeline_n - n;
+  unsigned long long prev_end = 0;
+  for (long long i = first; i < g_timeline_n; ++i) {
+    const unsigned long long* t = host + (size_t)(i % 256) * 8;
+    const TimelineInfo& f = g_timeline_info[i % 256];
+    const double base = prev_end ? (double)prev_end : (double)t[0];
+    fprintf(stderr, "[timeline] bn=%3d grid=%3d tiles=%4d kb=%3d | entry %+7.2f prol %+7.2f dep %+7.2f data %+7.2f mma %+7.2f st %+7.2f drain %+7.2f exit %+7.2f | dur %6.2f us\n",
+            f.bn, f.grid, f.tiles, f.kblocks, (t[0] - base) / 1e3, (t[1] - base) / 1e3, (t[2] - base) / 1e3, (t[3] - base) / 1e3,
+            (t[4] - base) / 1e3, (t[5] - base) / 1e3, (t[6] - base) / 1e3, (t[7] - base) / 1e3, (t[7] - t[0]) / 1e3);
+    prev_end = t[7];
+  }
 }
 
 bool conv_umma_supported(const ConvProblem& p) {

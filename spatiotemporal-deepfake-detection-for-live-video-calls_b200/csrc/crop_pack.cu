@@ -16,6 +16,8 @@
 // aligned u8 clip never round-trips through HBM.
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "../../include/afb200.h"
 
@@ -247,11 +249,13 @@ inline int flat_grid(long long total, int block) {
 // constants are seen (callers use one or two sets: demo.py's and the services' rounding of 255*mean).
 struct NormLutCache { float* dev[4] = {}; Norm key[4] = {}; int used = 0, next = 0; };
 static NormLutCache g_norm_lut[64];
+static std::mutex g_norm_lut_mutex;      // engines on different host threads share the per-device tables
 
 static int norm_lut_for(const Norm& n, cudaStream_t s, const float** out) {
   int dev = 0;
   AFB_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) { set_error("crop: device index %d out of range", dev); return AF_ERR_INVALID; }
+  std::lock_guard<std::mutex> lock(g_norm_lut_mutex);
   NormLutCache& c = g_norm_lut[dev];
   for (int i = 0; i < c.used; ++i)
     if (memcmp(&c.key[i], &n, sizeof(Norm)) == 0) { *out = c.dev[i]; return AF_OK; }

@@ -91,20 +91,25 @@ __global__ void maxpool_temporal_kernel(const T* __restrict__ x, T* __restrict__
   }
 }
 
-// Average over P positions for a slab of channels: grid (C/(V*32), B), block (32, 8).
-// threadIdx.x -> channel vector, threadIdx.y -> position phase.
+// Sum over a slice of the P positions for a slab of channels: grid (C/(V*32), B, PZ), block (32, 8).
+// threadIdx.x -> channel vector, threadIdx.y -> position phase, blockIdx.z -> position slice.  With PZ == 1 the block
+// writes the mean; with PZ > 1 it writes its partial sum to feat[(b*PZ + z)*C + c] and head_fc_kernel adds the PZ
+// partials in a fixed order and divides (a single clip is then pooled by 8*PZ blocks instead of 8: the head was the
+// slowest kernel of the batch-1 pass).  PZ depends only on P, never on the batch, so results are batch-invariant.
+constexpr int HEAD_PZ = 16;
 template <typename T>
-__global__ void head_pool_kernel(const T* __restrict__ x, float* __restrict__ feat, int P, int C) {
+__global__ void head_pool_kernel(const T* __restrict__ x, float* __restrict__ feat, int P, int C, int PZ) {
   constexpr int V = Vec<T>::N;
   __shared__ float part[8][32 * V];
-  const int b = blockIdx.y;
+  const int b = blockIdx.y, z = blockIdx.z;
   const int c = (blockIdx.x * 32 + threadIdx.x) * V;
+  const int per = (P + PZ - 1) / PZ, p_lo = z * per, p_hi = min(P, p_lo + per);
   float s[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) s[k] = 0.f;
   if (c < C) {
     const T* xb = x + (long long)b * P * C + c;
-    for (int p = threadIdx.y; p < P; p += 8) {
+    for (int p = p_lo + threadIdx.y; p < p_hi; p += 8) {
       Vec<T> t;
       t.load(xb + (long long)p * C);
 #pragma unroll
@@ -120,20 +125,25 @@ __global__ void head_pool_kernel(const T* __restrict__ x, float* __restrict__ fe
       float t = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) t += part[j][threadIdx.x * V + k];
-      feat[(long long)b * C + c + k] = t / (float)P;
+      feat[((long long)b * PZ + z) * C + c + k] = PZ == 1 ? t / (float)P : t;
     }
   }
 }
 
-// logits[b] = dot(feat[b], w) + bias ; optional sigmoid; optional copy of the features.
-__global__ void head_fc_kernel(const float* __restrict__ feat, const float* __restrict__ w, float bias,
+// logits[b] = dot(feat[b], w) + bias ; optional sigmoid; optional copy of the features.  feat holds PZ partial sums
+// per clip (PZ > 1: summed here in slice order and divided by P) or the finished mean (PZ == 1).
+__global__ void head_fc_kernel(const float* __restrict__ feat, int PZ, float P, const float* __restrict__ w, float bias,
                                int C, float* __restrict__ feat_out, float* __restrict__ logits,
                                float* __restrict__ scores) {
   __shared__ float red[32];
   const int b = blockIdx.x;
   float s = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float f = feat[(long long)b * C + c];
+    float f = feat[(long long)b * PZ * C + c];
+    if (PZ > 1) {
+      for (int z = 1; z < PZ; ++z) f += feat[((long long)b * PZ + z) * C + c];
+      f = f / P;
+    }
     if (feat_out) feat_out[(long long)b * C + c] = f;
     s = fmaf(f, w[c], s);
   }
@@ -211,15 +221,19 @@ int maxpool_temporal_launch(const void* x, void* y, int B, int T, int H, int W, 
   return AF_OK;
 }
 
+int head_pool_slices(int P) { return P >= 8 * HEAD_PZ ? HEAD_PZ : 1; }
+
+// features_ws: [B * head_pool_slices(P), C] floats
 int head_launch(const void* x, int B, int P, int C, bool is_bf16, const float* fc_w, float fc_b,
                 float* features_ws, float* features_out, float* logits, float* scores,
                 cudaStream_t s) {
   const int V = is_bf16 ? 8 : 4;
   if (C % (V * 32)) { set_error("head: C=%d not a multiple of %d", C, V * 32); return AF_ERR_INVALID; }
-  dim3 grid(C / (V * 32), B), block(32, 8);
-  if (is_bf16) head_pool_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, features_ws, P, C);
-  else head_pool_kernel<float><<<grid, block, 0, s>>>((const float*)x, features_ws, P, C);
-  head_fc_kernel<<<B, 256, 0, s>>>(features_ws, fc_w, fc_b, C, features_out, logits, scores);
+  const int PZ = head_pool_slices(P);
+  dim3 grid(C / (V * 32), B, PZ), block(32, 8);
+  if (is_bf16) head_pool_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, features_ws, P, C, PZ);
+  else head_pool_kernel<float><<<grid, block, 0, s>>>((const float*)x, features_ws, P, C, PZ);
+  head_fc_kernel<<<B, 256, 0, s>>>(features_ws, PZ, (float)P, fc_w, fc_b, C, features_out, logits, scores);
   g_launches += 2;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;
@@ -229,8 +243,8 @@ int spatial_mean_launch(const void* x, int N, int P, int C, bool is_bf16, float*
   const int V = is_bf16 ? 8 : 4;
   if (C % (V * 32)) { set_error("spatial_mean: C=%d not a multiple of %d", C, V * 32); return AF_ERR_INVALID; }
   dim3 grid(C / (V * 32), N), block(32, 8);
-  if (is_bf16) head_pool_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, out, P, C);
-  else head_pool_kernel<float><<<grid, block, 0, s>>>((const float*)x, out, P, C);
+  if (is_bf16) head_pool_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, out, P, C, 1);
+  else head_pool_kernel<float><<<grid, block, 0, s>>>((const float*)x, out, P, C, 1);
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;
