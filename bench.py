@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--variant", default="i3d", choices=["i3d", "ftcn_tt"],
+                    help="i3d: the AltFreezing I3D (BASELINE.json's metric); ftcn_tt: the reference's second classifier "
+                         "plugin (SURVEY 8f row 4) through the same pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunk-front", type=int, default=0)
@@ -101,14 +104,15 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU legs (oracle port)
-def cpu_reference_step(sd, clip_inputs, n_clips):
+def cpu_reference_step(sd, clip_inputs, n_clips, variant="i3d"):
     """The reference's CPU path for n_clips clips, batch 1 each (demo.py:309-328):
     crop/align (cv2.warpAffine, the reference's own dependency; numpy emulation if cv2 is
     absent) -> normalise -> fp32 forward (oracle port of the reference network)."""
     import numpy as np
     import torch
     from afb200 import synthetic
-    from oracle import crop_oracle, i3d_oracle
+    from oracle import crop_oracle, ftcn_oracle, i3d_oracle
+    net_forward = ftcn_oracle.forward if variant == "ftcn_tt" else i3d_oracle.forward
     try:
         import cv2
     except Exception:
@@ -125,7 +129,7 @@ def cpu_reference_step(sd, clip_inputs, n_clips):
             imgs.append(cv2.warpAffine(canvas, tfm, (224, 224)) if cv2 is not None
                         else crop_oracle.warp_affine_u8(canvas, tfm, 224))
         x = synthetic.normalise_clip(np.stack(imgs))
-        out.append(float(torch.sigmoid(i3d_oracle.forward(sd, x))[0, 0]))
+        out.append(float(torch.sigmoid(net_forward(sd, x))[0, 0]))
     return out
 
 
@@ -155,21 +159,21 @@ def run_reference(args):
     from afb200 import synthetic
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = synthetic.synthetic_state_dict(0)
+    sd = synthetic.synthetic_state_dict(0, args.variant)
     inputs = make_cpu_clip_inputs(1)
     clips_per_step = 1
     for _ in range(args.warmup):
-        cpu_reference_step(sd, inputs, clips_per_step)
+        cpu_reference_step(sd, inputs, clips_per_step, args.variant)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(sd, inputs, clips_per_step)
+        cpu_reference_step(sd, inputs, clips_per_step, args.variant)
     dt = time.perf_counter() - t0
     value = clips_per_step * args.steps / dt
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "AltFreezing I3D ResNet-50 clip classification: crop/warp/normalise + trunk, "
-                                   "32x224x224 clips (reference CPU path, batch 1 per step: demo.py loop)",
+            "config": {"workload": "%s clip classification: crop/warp/normalise + trunk, "
+                                   "32x224x224 clips (reference CPU path, batch 1 per step: demo.py loop)" % _net_name(args.variant),
                        "clips_per_step": clips_per_step},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d steps x %d clip (cv2.warpAffine crop + fp32 torch forward of the oracle port)" % (args.steps, clips_per_step)},
@@ -224,17 +228,17 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     peaks = measured_peaks()
     B = args.batch
-    sd = synthetic.synthetic_state_dict(0)
+    sd = synthetic.synthetic_state_dict(0, args.variant)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         inputs = make_cpu_clip_inputs(1)
-        cpu_reference_step(sd, inputs, 1)
+        cpu_reference_step(sd, inputs, 1, args.variant)
         n = 4
         t0 = time.perf_counter()
-        cpu_reference_step(sd, inputs, n)
+        cpu_reference_step(sd, inputs, n, args.variant)
         dt = time.perf_counter() - t0
         torch.set_num_threads(1)      # park the OpenMP team: its spinning workers would slow the launch thread below
         cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
@@ -243,7 +247,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)      # started early so nvidia-smi is already streaming when the load begins
     if rank == 0:
         sampler.start()
-    eng = afb200.Engine(sd, device=local_rank, max_batch=B, precision=args.precision)
+    eng = afb200.Engine(sd, device=local_rank, max_batch=B, precision=args.precision, variant=args.variant)
     if args.chunk_front:
         eng.set_option("chunk_front", args.chunk_front)
     if args.chunk_back:
@@ -369,8 +373,8 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": "AltFreezing I3D ResNet-50 %s, batch %d synthetic 32x224x224 clips per GPU, "
-                                       "GPU crop/warp/normalise kernel from 720p frames resident in HBM (BASELINE configs[1])" % (args.precision, B),
+                "config": {"workload": "%s %s, batch %d synthetic 32x224x224 clips per GPU, "
+                                       "GPU crop/warp/normalise kernel from 720p frames resident in HBM (BASELINE configs[1])" % (_net_name(args.variant), args.precision, B),
                            "clips_per_step_per_gpu": B, "parallelism": "clip-sharded x%d, scores all-gathered" % world,
                            "l2": "inputs and activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
                            "weights": "seeded synthetic (no checkpoint ships with the reference)"},
@@ -385,7 +389,8 @@ def run_ours(args):
                              "share_of_step": conv_ms / ms if ms > 0 else None,
                              "peak_source": "%s bf16_tflops_sustained (MEASURED_PEAKS.json)" % peaks["source"],
                              "simt_conv_ms_per_step": simt_ms / args.steps,
-                             "whole_step_frac_of_tensor_roofline": value / world * FLOPS_PER_CLIP / (peak * 1e12),
+                             "whole_step_frac_of_tensor_roofline": (value / world * FLOPS_PER_CLIP / (peak * 1e12)
+                                                                    if args.variant == "i3d" else None),
                              # the same launches split by the roofline that bounds each (algorithmic FLOP/byte of the
                              # launch vs the ridge peak_tflops / peak_hbm): how close each class runs to ITS limit
                              "classes": {
@@ -403,6 +408,10 @@ def run_ours(args):
         _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _net_name(variant):
+    return "FTCN-TT (temporal-only ResNet-50 + transformer head)" if variant == "ftcn_tt" else "AltFreezing I3D ResNet-50"
 
 
 class _QuietStdout:

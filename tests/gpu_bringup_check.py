@@ -1,5 +1,5 @@
 """Bring-up diagnostics on a B200: runs every kernel against torch/oracle references and
-prints a table instead of stopping at the first failure.  Usage: python tools/gpu_check.py [sections]"""
+prints a table instead of stopping at the first failure.  Usage: python tests/gpu_bringup_check.py [sections]"""
 import os
 import sys
 import time

@@ -1,6 +1,6 @@
 """Throughput of the FTCN-TT plugin path on one B200: u8 aligned clips resident in HBM ->
-normalise/pack -> temporal-only trunk -> transformer head -> scores.  Prints one JSON line.  With --cpu also times
-the oracle port (fp32 torch on the host cores) on one clip."""
+normalise/pack -> temporal-only trunk -> transformer head -> scores.  Prints one JSON line.  (The CPU baseline of
+this plugin is timed by `bench.py --variant ftcn_tt`, the one place outside tests/ that may run oracle/.)"""
 import argparse, json, os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,7 +11,6 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
-ap.add_argument("--cpu", action="store_true")
 a = ap.parse_args()
 sd = synthetic.synthetic_state_dict(0, "ftcn_tt")
 eng = afb200.Engine(sd, max_batch=a.batch, precision="bf16", variant="ftcn_tt")
@@ -35,12 +34,4 @@ for _ in range(30):
 out = {"metric": "clips_per_s_32x224x224", "variant": "ftcn_tt", "value": a.batch / ms * 1e3, "unit": "clips/s",
        "ms_per_step": ms, "batch": a.batch, "steps": a.steps, "dtype": "bf16", "data": "synthetic",
        "gpu_launches": eng.launch_count - n0 - 0, "p50_batch1_latency_ms": sorted(lat[5:])[len(lat[5:]) // 2]}
-if a.cpu:
-    from oracle import ftcn_oracle
-    torch.set_num_threads(os.cpu_count() or 1)
-    x = synthetic.normalise_clip(synthetic.synthetic_clip_u8(0))
-    ftcn_oracle.forward(sd, x)
-    t0 = time.perf_counter(); ftcn_oracle.forward(sd, x); ftcn_oracle.forward(sd, x)
-    out["cpu_baseline"] = {"value": 2 / (time.perf_counter() - t0), "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
-                           "sample": "2 clips, batch 1 (fp32 torch forward of the oracle port)"}
 print(json.dumps(out))
