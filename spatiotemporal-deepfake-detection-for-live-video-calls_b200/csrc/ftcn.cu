@@ -22,7 +22,7 @@ constexpr int FS_OX = 8, FS_OY = 4;                    // final (56x56-level) ou
 constexpr int FS_MX = 2 * FS_OX + 1, FS_MY = 2 * FS_OY + 1;   // 112-level map region incl. the 3x3/2 pool halo: 17 x 9
 constexpr int FS_IX = 2 * FS_MX, FS_IY = 2 * FS_MY;    // input pixels under it: 34 x 18
 constexpr int FS_C = 64;
-constexpr int FS_SMEM = 5 * FS_IY * FS_IX * 16 + FS_MY * FS_MX * FS_C * 4;
+template <typename T> constexpr int fs_smem_bytes() { return 5 * FS_IY * FS_IX * 16 + FS_MY * FS_MX * FS_C * 4 + 5 * FS_IY * FS_IX * 4 * (int)sizeof(T); }
 
 template <typename T> __device__ __forceinline__ float4 load_px4(const T* p);
 template <> __device__ __forceinline__ float4 load_px4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -41,29 +41,32 @@ template <> __device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = t;
 }
 
+__device__ __forceinline__ void cp_async_px(void* smem_dst, const void* gsrc, int bytes, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int src_bytes = valid ? bytes : 0;                  // 0 source bytes = zero fill
+  if (bytes == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
 // clip: padded NDHWC4 (element strides sB,sT,sH,sW; `clip` points at logical (b=0,t=0,y=0,x=0); >= 2 zero frames
 // and >= 3 zero rows / columns around every clip).  w: [5][4][64] fp32 (tap, channel, cout).  y: [B*T, S/4, S/4, 64].
+// Persistent blocks (2 per SM) walk tiles of 8 x 4 final outputs of one frame.  Per tile: the 5-frame input patch
+// arrives by cp.async into a raw staging buffer WHILE the previous tile is computed, is widened to fp32 once, then
+// thread = 4 consecutive output channels x one of 16 position lanes (every 16-byte smem read feeds 12 FMAs) builds
+// the 2x2-max-pooled, ReLU'd 17 x 9 map tile in smem and the 3x3/2 max-pool writes the 32 outputs.
+// (Round-1 history: one channel per thread 13 TFLOP/s, bound by the smem reads; 4 channels per thread with a
+// synchronous fill 22 TFLOP/s, bound by the fill phase at 2 blocks/SM; reading pixels straight from global 15.)
 template <typename T>
-__global__ void __launch_bounds__(256) ftcn_stem_kernel(const T* __restrict__ clip, long long sB, long long sT, long long sH,
-                                                        long long sW, int T_, int S, const float* __restrict__ w,
-                                                        const float* __restrict__ bias, T* __restrict__ y) {
+__global__ void __launch_bounds__(256, 2) ftcn_stem_kernel(const T* __restrict__ clip, long long sB, long long sT, long long sH,
+                                                           long long sW, int T_, int S, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, T* __restrict__ y, int tiles_x,
+                                                           int tiles_y, int n_tiles) {
   extern __shared__ float4 fs_smem[];
-  float4* in_s = fs_smem;                                                   // [5][FS_IY][FS_IX]
+  float4* in_s = fs_smem;                                                   // [5][FS_IY][FS_IX] fp32 pixels
   float* map_s = reinterpret_cast<float*>(fs_smem + 5 * FS_IY * FS_IX);     // [FS_MY*FS_MX][64]
-  const int bt = blockIdx.z, b = bt / T_, t = bt - b * T_;
-  const int ox0 = blockIdx.x * FS_OX, oy0 = blockIdx.y * FS_OY;
-  const int mx0 = 2 * ox0 - 1, my0 = 2 * oy0 - 1;                           // map origin (may be -1)
-  const int ix0 = 2 * mx0, iy0 = 2 * my0;                                   // input origin (may be -2: inside the pads)
-  const T* src = clip + b * sB + (long long)(t - 2) * sT;
-  for (int i = threadIdx.x; i < 5 * FS_IY * FS_IX; i += 256) {
-    const int x = i % FS_IX, r = i / FS_IX, yy = r % FS_IY, f = r / FS_IY;
-    const int gx = ix0 + x, gy = iy0 + yy;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gx < S && gy < S) v = load_px4<T>(src + f * sT + (long long)gy * sH + (long long)gx * sW);
-    in_s[i] = v;
-  }
-  // thread = 4 consecutive output channels x one of 16 position lanes: every 16-byte shared-memory read of an input
-  // pixel feeds 12 FMAs (the first version, one channel per thread, was bound by those reads at 13 TFLOP/s)
+  T* raw_s = reinterpret_cast<T*>(map_s + FS_MY * FS_MX * FS_C);            // [5][FS_IY][FS_IX][4] as stored in the clip
   const int cg = (threadIdx.x & 15) * 4, pl = threadIdx.x >> 4;
   float4 wr[5][3];
 #pragma unroll
@@ -71,45 +74,71 @@ __global__ void __launch_bounds__(256) ftcn_stem_kernel(const T* __restrict__ cl
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) wr[f][ch] = __ldg(reinterpret_cast<const float4*>(w + (f * 4 + ch) * FS_C + cg));
   const float4 bc = __ldg(reinterpret_cast<const float4*>(bias + cg));
-  __syncthreads();
-  const int M2 = S / 2;
-  for (int pos = pl; pos < FS_MY * FS_MX; pos += 16) {
-    const int my = pos / FS_MX, mx = pos - my * FS_MX;
-    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {                      // MaxPool3d((1,2,2)) over the conv + BN outputs
-      const int px = (2 * my + (q >> 1)) * FS_IX + 2 * mx + (q & 1);
-      float4 a = bc;
-#pragma unroll
-      for (int f = 0; f < 5; ++f) {
-        const float4 v = in_s[f * FS_IY * FS_IX + px];
-        a.x = fmaf(v.x, wr[f][0].x, a.x); a.y = fmaf(v.x, wr[f][0].y, a.y); a.z = fmaf(v.x, wr[f][0].z, a.z); a.w = fmaf(v.x, wr[f][0].w, a.w);
-        a.x = fmaf(v.y, wr[f][1].x, a.x); a.y = fmaf(v.y, wr[f][1].y, a.y); a.z = fmaf(v.y, wr[f][1].z, a.z); a.w = fmaf(v.y, wr[f][1].w, a.w);
-        a.x = fmaf(v.z, wr[f][2].x, a.x); a.y = fmaf(v.z, wr[f][2].y, a.y); a.z = fmaf(v.z, wr[f][2].z, a.z); a.w = fmaf(v.z, wr[f][2].w, a.w);
-      }
-      m.x = fmaxf(m.x, a.x); m.y = fmaxf(m.y, a.y); m.z = fmaxf(m.z, a.z); m.w = fmaxf(m.w, a.w);
+  const int M2 = S / 2, O = S / 4;
+
+  auto issue = [&](int tile) {                             // start the patch of `tile` on its way into raw_s
+    const int tx = tile % tiles_x, r0 = tile / tiles_x, ty = r0 % tiles_y, bt = r0 / tiles_y;
+    const int b = bt / T_, t = bt - b * T_;
+    const int ix0 = 2 * (2 * tx * FS_OX - 1), iy0 = 2 * (2 * ty * FS_OY - 1);   // may be -2: inside the pads
+    const T* src = clip + b * sB + (long long)(t - 2) * sT;
+    for (int i = threadIdx.x; i < 5 * FS_IY * FS_IX; i += 256) {
+      const int x = i % FS_IX, r = i / FS_IX, yy = r % FS_IY, f = r / FS_IY;
+      const int gx = ix0 + x, gy = iy0 + yy;
+      const bool valid = gx < S && gy < S;
+      cp_async_px(raw_s + (size_t)i * 4, src + f * sT + (long long)(valid ? gy : 0) * sH + (long long)(valid ? gx : 0) * sW,
+                  (int)(4 * sizeof(T)), valid);
     }
-    // ReLU, then positions outside the 112x112 map must not win the 3x3 max: after ReLU 0 is neutral
-    const bool inside = (unsigned)(my0 + my) < (unsigned)M2 && (unsigned)(mx0 + mx) < (unsigned)M2;
-    if (!inside) m = make_float4(0.f, 0.f, 0.f, 0.f);
-    m.x = fmaxf(m.x, 0.f); m.y = fmaxf(m.y, 0.f); m.z = fmaxf(m.z, 0.f); m.w = fmaxf(m.w, 0.f);
-    *reinterpret_cast<float4*>(map_s + pos * FS_C + cg) = m;
-  }
-  __syncthreads();
-  const int O = S / 4;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int tile = blockIdx.x;
+  if (tile < n_tiles) issue(tile);
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, r0 = tile / tiles_x, ty = r0 % tiles_y, bt = r0 / tiles_y;
+    const int ox0 = tx * FS_OX, oy0 = ty * FS_OY;
+    const int mx0 = 2 * ox0 - 1, my0 = 2 * oy0 - 1;                         // map origin (may be -1)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    for (int i = threadIdx.x; i < 5 * FS_IY * FS_IX; i += 256) in_s[i] = load_px4<T>(raw_s + (size_t)i * 4);   // own copies
+    __syncthreads();                                                        // in_s complete, raw_s free
+    if (tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x);
+    for (int pos = pl; pos < FS_MY * FS_MX; pos += 16) {
+      const int my = pos / FS_MX, mx = pos - my * FS_MX;
+      float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
-  for (int j = 0; j < (FS_OX * FS_OY) / 16; ++j) {
-    const int o = pl * ((FS_OX * FS_OY) / 16) + j, oy = o / FS_OX, ox = o - oy * FS_OX;
-    if (oy0 + oy >= O || ox0 + ox >= O) continue;
-    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < 4; ++q) {                      // MaxPool3d((1,2,2)) over the conv + BN outputs
+        const int px = (2 * my + (q >> 1)) * FS_IX + 2 * mx + (q & 1);
+        float4 a = bc;
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const float4 v = *reinterpret_cast<const float4*>(map_s + ((2 * oy + dy) * FS_MX + 2 * ox + dx) * FS_C + cg);
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        for (int f = 0; f < 5; ++f) {
+          const float4 v = in_s[f * FS_IY * FS_IX + px];
+          a.x = fmaf(v.x, wr[f][0].x, a.x); a.y = fmaf(v.x, wr[f][0].y, a.y); a.z = fmaf(v.x, wr[f][0].z, a.z); a.w = fmaf(v.x, wr[f][0].w, a.w);
+          a.x = fmaf(v.y, wr[f][1].x, a.x); a.y = fmaf(v.y, wr[f][1].y, a.y); a.z = fmaf(v.y, wr[f][1].z, a.z); a.w = fmaf(v.y, wr[f][1].w, a.w);
+          a.x = fmaf(v.z, wr[f][2].x, a.x); a.y = fmaf(v.z, wr[f][2].y, a.y); a.z = fmaf(v.z, wr[f][2].z, a.z); a.w = fmaf(v.z, wr[f][2].w, a.w);
+        }
+        m.x = fmaxf(m.x, a.x); m.y = fmaxf(m.y, a.y); m.z = fmaxf(m.z, a.z); m.w = fmaxf(m.w, a.w);
       }
-    store4<T>(y + (((long long)bt * O + oy0 + oy) * O + ox0 + ox) * FS_C + cg, m);
+      // ReLU, then positions outside the 112x112 map must not win the 3x3 max: after ReLU 0 is neutral
+      const bool inside = (unsigned)(my0 + my) < (unsigned)M2 && (unsigned)(mx0 + mx) < (unsigned)M2;
+      if (!inside) m = make_float4(0.f, 0.f, 0.f, 0.f);
+      m.x = fmaxf(m.x, 0.f); m.y = fmaxf(m.y, 0.f); m.z = fmaxf(m.z, 0.f); m.w = fmaxf(m.w, 0.f);
+      *reinterpret_cast<float4*>(map_s + pos * FS_C + cg) = m;
+    }
+    __syncthreads();                                                        // map complete; in_s may be overwritten
+#pragma unroll
+    for (int j = 0; j < (FS_OX * FS_OY) / 16; ++j) {
+      const int o = pl * ((FS_OX * FS_OY) / 16) + j, oy = o / FS_OX, ox = o - oy * FS_OX;
+      if (oy0 + oy >= O || ox0 + ox >= O) continue;
+      float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float4 v = *reinterpret_cast<const float4*>(map_s + ((2 * oy + dy) * FS_MX + 2 * ox + dx) * FS_C + cg);
+          m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+      store4<T>(y + (((long long)bt * O + oy0 + oy) * O + ox0 + ox) * FS_C + cg, m);
+    }
+    // the next iteration's two barriers (after the widening pass) separate this pool phase from the next map writes
   }
 }
 
@@ -318,21 +347,32 @@ int ftcn_stem_launch(const ClipLayout& clip, int clip0, int B, const float* w_ta
                      cudaStream_t s) {
   if (clip.S % 4 || B <= 0) { set_error("ftcn_stem: clip size %d not a multiple of 4", clip.S); return AF_ERR_INVALID; }
   static bool configured[64] = {};
+  static int sms[64] = {};
   int dev = 0;
   AFB_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    AFB_CUDA(cudaFuncSetAttribute(ftcn_stem_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
-    AFB_CUDA(cudaFuncSetAttribute(ftcn_stem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+  if (dev < 0 || dev >= 64) { set_error("ftcn_stem: device index %d out of range", dev); return AF_ERR_INVALID; }
+  if (!configured[dev]) {
+    AFB_CUDA(cudaFuncSetAttribute(ftcn_stem_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs_smem_bytes<bf16>()));
+    AFB_CUDA(cudaFuncSetAttribute(ftcn_stem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs_smem_bytes<float>()));
+    AFB_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+    configured[dev] = true;
   }
   const int O = clip.S / 4;
-  dim3 grid((O + FS_OX - 1) / FS_OX, (O + FS_OY - 1) / FS_OY, B * clip.T);
-  if (clip.is_bf16)
-    ftcn_stem_kernel<bf16><<<grid, 256, FS_SMEM, s>>>((const bf16*)clip.base + (long long)clip0 * clip.sB, clip.sB, clip.sT,
-                                                      clip.sH, clip.sW, clip.T, clip.S, w_tap_c_cout, bias, (bf16*)y);
-  else
-    ftcn_stem_kernel<float><<<grid, 256, FS_SMEM, s>>>((const float*)clip.base + (long long)clip0 * clip.sB, clip.sB, clip.sT,
-                                                       clip.sH, clip.sW, clip.T, clip.S, w_tap_c_cout, bias, (float*)y);
+  const int tiles_x = (O + FS_OX - 1) / FS_OX, tiles_y = (O + FS_OY - 1) / FS_OY;
+  const long long n_tiles_ll = (long long)tiles_x * tiles_y * B * clip.T;
+  if (n_tiles_ll >= (1LL << 31)) { set_error("ftcn_stem: chunk too large"); return AF_ERR_INVALID; }
+  const int n_tiles = (int)n_tiles_ll;
+  if (clip.is_bf16) {
+    const int grid = n_tiles < 2 * sms[dev] ? n_tiles : 2 * sms[dev];            // 2 resident blocks per SM
+    ftcn_stem_kernel<bf16><<<grid, 256, fs_smem_bytes<bf16>(), s>>>((const bf16*)clip.base + (long long)clip0 * clip.sB, clip.sB,
+                                                                    clip.sT, clip.sH, clip.sW, clip.T, clip.S, w_tap_c_cout, bias,
+                                                                    (bf16*)y, tiles_x, tiles_y, n_tiles);
+  } else {
+    const int grid = n_tiles < sms[dev] ? n_tiles : sms[dev];                    // fp32 staging: 1 block per SM
+    ftcn_stem_kernel<float><<<grid, 256, fs_smem_bytes<float>(), s>>>((const float*)clip.base + (long long)clip0 * clip.sB, clip.sB,
+                                                                      clip.sT, clip.sH, clip.sW, clip.T, clip.S, w_tap_c_cout,
+                                                                      bias, (float*)y, tiles_x, tiles_y, n_tiles);
+  }
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;
