@@ -65,10 +65,12 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
                                                    int bgr, uint8_t* __restrict__ out_u8, T* dst,
                                                    long long sB, long long sT, long long sH,
                                                    long long sW, const float* __restrict__ lut) {
-  __shared__ int s_ad[32], s_bd[32], s_x0[8], s_y0[8];
-  __shared__ int s_win[6];             // valid canvas window [x_lo, x_hi) x [y_lo, y_hi), strict-interior rows [yi_lo, yi_hi)
-  __shared__ const uint8_t* s_org;     // address of canvas pixel (0,0) in the frame
-  __shared__ long long s_pitch;
+  // block-uniform values are packed so that a thread fetches them with five vector LDS (the kernel is LSU-bound)
+  __shared__ int2 s_col[32], s_row[8];         // (adelta, bdelta) per column, (X0, Y0) per row
+  __shared__ int4 s_win;                       // valid canvas window x_lo, x_hi, y_lo, y_hi
+  __shared__ int2 s_win_i;                     // rows whose 16-byte fetch windows stay inside the frame buffer
+  struct __align__(16) Org { const uint8_t* p; long long pitch; };
+  __shared__ Org s_org;                        // address of canvas pixel (0,0) in the frame, row pitch
   const int bt = blockIdx.z;
   const int b = bt / T_, t = bt - b * T_;
   const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -81,14 +83,13 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
     const double A12 = __dmul_rn(-g.tfm[1], D), A21 = __dmul_rn(-g.tfm[3], D);
     if (tid < 32) {
       const double xx = (double)(blockIdx.x * 32 + tid);
-      s_ad[tid] = cv_round(__dmul_rn(__dmul_rn(A11, xx), 1024.0));
-      s_bd[tid] = cv_round(__dmul_rn(__dmul_rn(A21, xx), 1024.0));
+      s_col[tid] = make_int2(cv_round(__dmul_rn(__dmul_rn(A11, xx), 1024.0)), cv_round(__dmul_rn(__dmul_rn(A21, xx), 1024.0)));
     } else {
       const double b1 = __dsub_rn(__dmul_rn(-A11, g.tfm[2]), __dmul_rn(A12, g.tfm[5]));
       const double b2 = __dsub_rn(__dmul_rn(-A21, g.tfm[2]), __dmul_rn(A22, g.tfm[5]));
       const double yy = (double)(blockIdx.y * 8 + tid - 32);
-      s_x0[tid - 32] = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(A12, yy), b1), 1024.0)) + 16;
-      s_y0[tid - 32] = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(A22, yy), b2), 1024.0)) + 16;
+      s_row[tid - 32] = make_int2(cv_round(__dmul_rn(__dadd_rn(__dmul_rn(A12, yy), b1), 1024.0)) + 16,
+                                  cv_round(__dmul_rn(__dadd_rn(__dmul_rn(A22, yy), b2), 1024.0)) + 16);
     }
   } else if (tid == 40) {
     // canvas pixel (cx,cy) is frame pixel (cx+ltx, cy+lty); it exists iff it is inside the canvas AND inside this
@@ -98,18 +99,19 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
     const int ltx = g.left_top[0], lty = g.left_top[1];
     const int bx1 = max(f.box[0], 0), by1 = max(f.box[1], 0);
     const int bx2 = min(f.box[2], f.width), by2 = min(f.box[3], f.height);
-    s_win[0] = max(0, bx1 - ltx); s_win[1] = min(g.canvas_wh[0], bx2 - ltx);
-    s_win[2] = max(0, by1 - lty); s_win[3] = min(g.canvas_wh[1], by2 - lty);
-    // rows whose 16-byte fetch windows cannot leave the frame buffer: frame rows 1 .. height-2
-    s_win[4] = max(s_win[2], 1 - lty); s_win[5] = min(s_win[3], f.height - 1 - lty);
-    s_org = f.data + (long long)lty * f.pitch + (long long)ltx * 3;
-    s_pitch = f.pitch;
+    const int4 win = make_int4(max(0, bx1 - ltx), min(g.canvas_wh[0], bx2 - ltx), max(0, by1 - lty), min(g.canvas_wh[1], by2 - lty));
+    s_win = win;
+    // frame rows 1 .. height-2; an empty range when the pitch is too short for the wide fetches
+    s_win_i = f.pitch >= 16 ? make_int2(max(win.z, 1 - lty), min(win.w, f.height - 1 - lty)) : make_int2(0, 0);
+    s_org.p = f.data + (long long)lty * f.pitch + (long long)ltx * 3;
+    s_org.pitch = f.pitch;
   }
   __syncthreads();
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = blockIdx.y * 8 + threadIdx.y;
   if (x >= S || y >= S) return;
-  const int X = (s_x0[threadIdx.y] + s_ad[threadIdx.x]) >> 5, Y = (s_y0[threadIdx.y] + s_bd[threadIdx.x]) >> 5;
+  const int2 col = s_col[threadIdx.x], row = s_row[threadIdx.y];
+  const int X = (row.x + col.x) >> 5, Y = (row.y + col.y) >> 5;
   int sx = X >> 5, sy = Y >> 5;
   sx = max(-32768, min(32767, sx));
   sy = max(-32768, min(32767, sy));
@@ -118,11 +120,14 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
   // product are exact in fp32, so this is the integer 32*a*b (<= 32768) with the one saturating case a = b = 32.
   const int w00 = min((32 - fy) * (32 - fx) * 32, 32767), w01 = (32 - fy) * fx * 32;
   const int w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
-  const int xlo = s_win[0], xhi = s_win[1], ylo = s_win[2], yhi = s_win[3];
-  const uint8_t* org = s_org;
-  const long long pitch = s_pitch;
+  const int4 win = s_win;
+  const int2 win_i = s_win_i;
+  const int xlo = win.x, xhi = win.y, ylo = win.z, yhi = win.w;
+  const Org o_ = s_org;
+  const uint8_t* org = o_.p;
+  const long long pitch = o_.pitch;
   int acc[3] = {0, 0, 0};                 // in memory channel order; BGR frames are swapped at the end
-  if (sx >= xlo && sx + 1 < xhi && sy >= s_win[4] && sy + 1 < s_win[5] && pitch >= 16) {
+  if (sx >= xlo && sx + 1 < xhi && sy >= win_i.x && sy + 1 < win_i.y) {
     // all four taps exist: two 6-byte fetches
     const uint8_t* p = org + (long long)sy * pitch + (long long)sx * 3;
     const uint2 r0 = load6(p), r1 = load6(p + pitch);
