@@ -4,7 +4,7 @@ Host side (Python) of the C-ABI library in csrc/ (include/afb200.h).  Importing 
 package does not load the CUDA library; the first engine/crop call does, and raises if the
 built `libafb200.so` is missing — there is no CPU fallback.
 """
-from . import arch, features, live, parallel, synthetic  # noqa: F401
+from . import arch, features, live, parallel, report, synthetic  # noqa: F401
 from ._lib import Afb200Error, LIB_PATH, lib  # noqa: F401
 from .classifier import B200Engine, Classifier, RGBBackboneB200  # noqa: F401
 from .crop import CropAlignB200, clip_geometry, estimate_clip_transform, get_crop_box  # noqa: F401
