@@ -45,6 +45,7 @@ def parse():
                          "plugin (SURVEY 8f row 4) through the same pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-kernel-events", action="store_true", help="do not bracket each conv launch with CUDA events")
     ap.add_argument("--chunk-front", type=int, default=0)
     ap.add_argument("--chunk-back", type=int, default=0)
     return ap.parse_args()
@@ -271,7 +272,7 @@ def run_ours(args):
         dist.barrier()
     eng.set_option("ridge_x1000", int(1e3 * peaks["bf16_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)))
     eng.set_option("reset_stats", 1)
-    eng.set_option("profile_events", 1)
+    eng.set_option("profile_events", 0 if args.no_kernel_events else 1)
     launches0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AFB200_VERSION 101
+#define AFB200_VERSION 102
 
 typedef struct af_engine* af_handle;
 
@@ -143,6 +143,11 @@ af_status af_create(af_handle* out, int32_t device, const af_weights* w, int32_t
                     int32_t precision);
 af_status af_destroy(af_handle h);
 
+/* Process-wide diagnostic knobs (tests only).  "block_n" = 64 | 128 | 256 forces the output-tile width of the
+ * generic tcgen05 conv kernel wherever Cout allows (0 = the planner's own choice), so that every tile shape the
+ * production schedule can pick is testable on small inputs. */
+af_status af_set_global_option(const char* name, int64_t value);
+
 /* Counters for the benchmark's roofline line.  With option "profile_events" = 1 every
  * conv launch is bracketed by CUDA events on its stream (no synchronisation); the getters
  * below synchronise the device and aggregate them since the last "reset_stats" option call:
@@ -210,6 +215,16 @@ af_status af_crop_u8(const af_frame_desc* frames_dev, const af_clip_geom* geom_d
                      int32_t frames_per_clip, int32_t size, int32_t bgr, uint8_t* out_dev,
                      void* stream);
 
+/* K1 on its own (SURVEY.md 8b `crop_pack`): the same warp followed by the callers' pack step
+ *   x = (float(u8) - 255*mean_c) / (255*std_c), NTHWC -> NCTHW   (demo.py:84-87,317-319; TEST2.py:147-158)
+ * written straight into a caller tensor viewed as [B,3,T,S,S] with ELEMENT strides `out_strides`
+ * (contiguous NCTHW, channels_last_3d, a slice of a larger batch ...), fp32 or bf16 — the aligned u8 clip
+ * never exists in memory.  Equals af_crop_u8 followed by that pack step bit for bit (IEEE fp32 division). */
+af_status af_crop_pack(const af_frame_desc* frames_dev, const af_clip_geom* geom_dev, int32_t batch,
+                       int32_t frames_per_clip, int32_t size, int32_t bgr, const float mean255[3],
+                       const float std255[3], void* clip_out_dev, int32_t out_dtype /* AF_F32 | AF_BF16 */,
+                       const int64_t out_strides[5], void* stream);
+
 /* Fused fast path: the same warp, normalised and written directly into the engine's
  * internal clip layout, followed by the trunk.  Replaces crop_align_func + the three
  * torch pack lines + classifier(images_t) of the hot loop (demo.py:309-328). */
@@ -232,6 +247,13 @@ af_status af_conv_shortcut_ndhwc(const void* x_dev, const af_conv_desc* conv_hos
                                  const af_conv_desc* shortcut_host, void* y_dev, int32_t batch, int32_t t,
                                  int32_t hgt, int32_t wid, int32_t hgt2, int32_t wid2, int32_t relu,
                                  void* stream);
+
+/* Test/diagnostic entry: the fused stem kernel (K3: conv k[5,7,7] s[1,2,2] p[2,3,3] + folded BN + ReLU +
+ * MaxPool3d k[1,3,3] s[1,2,2] p[0,1,1]; stem_helper.py:156-178) on its own, exactly as the bf16 trunk launches it.
+ * clip_dev: bf16 [B,T,S,S,4] (channel 3 ignored); y_dev: bf16 [B,T,S/4,S/4,64].  per_frame_kernel = 0 runs the
+ * temporal-sweep kernel when T % 4 == 0 (the production path), 1 forces the per-frame row-halo kernel. */
+af_status af_stem_pool_ndhwc4(const void* clip_dev, const af_conv_desc* stem_host, void* y_dev, int32_t batch,
+                              int32_t t, int32_t s, int32_t per_frame_kernel, void* stream);
 
 /* Copy intermediate activations of the LAST af_forward/af_infer call out for stage
  * parity tests: which = 1..5 (s1..s5 outputs) as fp32 NCTHW [B,C,T,H,W] into out_dev.

@@ -59,7 +59,7 @@ class AfClipGeom(C.Structure):
 
 EXPORTS = ("af_last_error", "af_version", "af_launch_count", "af_create", "af_destroy", "af_set_option",
            "af_forward", "af_forward_frames", "af_infer_u8", "af_infer_u8_host", "af_submit_u8_host", "af_wait", "af_crop_u8", "af_crop_infer",
-           "af_conv_ndhwc", "af_conv_shortcut_ndhwc", "af_get_stage", "af_get_stat")
+           "af_conv_ndhwc", "af_conv_shortcut_ndhwc", "af_get_stage", "af_get_stat", "af_crop_pack", "af_stem_pool_ndhwc4", "af_set_global_option")
 
 _lib = None
 
@@ -110,6 +110,13 @@ def lib():
     L.af_conv_shortcut_ndhwc.restype = i32
     L.af_conv_shortcut_ndhwc.argtypes = [vp, C.POINTER(AfConvDesc), vp, C.POINTER(AfConvDesc), vp, i32, i32, i32, i32, i32,
                                          i32, i32, vp]
+    L.af_crop_pack.restype = i32
+    L.af_crop_pack.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), vp, i32,
+                               C.POINTER(i64), vp]
+    L.af_stem_pool_ndhwc4.restype = i32
+    L.af_stem_pool_ndhwc4.argtypes = [vp, C.POINTER(AfConvDesc), vp, i32, i32, i32, i32, vp]
+    L.af_set_global_option.restype = i32
+    L.af_set_global_option.argtypes = [C.c_char_p, i64]
     L.af_get_stat.restype = i32
     L.af_get_stat.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double)]
     L.af_get_stage.restype = i32

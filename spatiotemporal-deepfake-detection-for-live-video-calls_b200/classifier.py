@@ -153,6 +153,8 @@ class RGBBackboneB200(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if x.dim() != 5 or x.shape[2] != 3:
             raise ValueError("RGBBackboneB200 takes frames [B,T,3,H,W], got %s" % (tuple(x.shape),))
+        if not x.is_cuda:
+            raise RuntimeError("afb200: the B200 backbone needs a CUDA tensor (no CPU fallback)")
         eng = self._clf._warped_network
         dev = x.device if x.device.index is not None else torch.device("cuda", torch.cuda.current_device())
         logits, feats = eng.engine_for(dev).forward_frames(x.permute(0, 2, 1, 3, 4))     # strided NCTHW view

@@ -151,6 +151,28 @@ def crop_u8(frame_tensors, big_boxes, geoms, frames_per_clip, size=224, bgr=Fals
     return out
 
 
+def crop_pack(frame_tensors, big_boxes, geoms, frames_per_clip, size, mean255, std255, out: torch.Tensor = None,
+              dtype=torch.bfloat16, bgr=False, device=None) -> torch.Tensor:
+    """K1 on its own (af_crop_pack): warp + `(u8 - 255*mean)/(255*std)` written straight into `out`, a [B,3,T,S,S]
+    fp32/bf16 CUDA tensor with ANY strides (contiguous NCTHW, channels_last_3d, a permuted NTHWC buffer ...);
+    allocated contiguous when not given.  Equals crop_u8 followed by the callers' pack lines bit for bit."""
+    dev = device if device is not None else (out.device if out is not None else frame_tensors[0].device)
+    B = len(geoms)
+    if out is None:
+        out = torch.empty((B, 3, frames_per_clip, size, size), dtype=dtype, device=dev)
+    assert out.is_cuda and tuple(out.shape) == (B, 3, frames_per_clip, size, size) and out.dtype in (torch.float32, torch.bfloat16)
+    fd_t, cg_t = pack_descriptors(frame_tensors, big_boxes, geoms, dev)
+    m = np.ascontiguousarray(mean255, np.float32)
+    sd = np.ascontiguousarray(std255, np.float32)
+    strides = (C.c_int64 * 5)(*out.stride())
+    with torch.cuda.device(dev):
+        check(lib().af_crop_pack(C.c_void_p(fd_t.data_ptr()), C.c_void_p(cg_t.data_ptr()), B, frames_per_clip, size, int(bgr),
+                                 m.ctypes.data_as(C.POINTER(C.c_float)), sd.ctypes.data_as(C.POINTER(C.c_float)),
+                                 C.c_void_p(out.data_ptr()), 0 if out.dtype == torch.float32 else 1, strides,
+                                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "af_crop_pack")
+    return out
+
+
 class CropAlignB200:
     """Drop-in for FasterCropAlignXRay(size): `(landmarks, images) -> (lm68_T, u8 [T,S,S,3])`.
     landmarks: list of (box, lm5, lm68, big_box) with lm coordinates relative to the big box;
@@ -184,13 +206,20 @@ class CropAlignB200:
         # Each crop is uploaded as is and addressed in CANVAS coordinates: the descriptor's
         # base pointer is moved back by the crop's offset d inside the canvas, so canvas pixel
         # (x,y) resolves to crop pixel (x-d.x, y-d.y); the box mask keeps every read inside the crop.
+        # The kernel fetches interior taps as aligned 16-byte windows (crop_pack.cu: load6), which may reach up to
+        # 15 bytes past either end of a crop: every crop sits in one upload buffer with 16 bytes of slack around it.
         keep, descs, bbs = [], [], []
-        for img, d in zip(images, diff):
-            t = torch.from_numpy(np.ascontiguousarray(img)).to(self.device)
-            keep.append(t)
+        sizes = [int(img.shape[0]) * int(img.shape[1]) * 3 for img in images]
+        offs = np.concatenate([[0], np.cumsum([(n + 16 + 15) // 16 * 16 for n in sizes])]).astype(np.int64) + 16
+        host = np.zeros(int(offs[-1]) + 16, np.uint8)
+        for img, o, n in zip(images, offs, sizes):
+            host[o:o + n] = np.ascontiguousarray(img).reshape(-1)
+        buf = torch.from_numpy(host).to(self.device)
+        keep.append(buf)
+        for img, d, o in zip(images, diff, offs):
             ih, iw = img.shape[:2]
             pitch = iw * 3
-            descs.append((t.data_ptr() - (int(d[1]) * pitch + int(d[0]) * 3), pitch, int(h), int(w)))
+            descs.append((buf.data_ptr() + int(o) - (int(d[1]) * pitch + int(d[0]) * 3), pitch, int(h), int(w)))
             bbs.append((int(d[0]), int(d[1]), int(d[0]) + iw, int(d[1]) + ih))
         out = crop_u8(descs, bbs, [(tfm, (0, 0), (int(w), int(h)))], len(images), self.image_size,
                       device=self.device)

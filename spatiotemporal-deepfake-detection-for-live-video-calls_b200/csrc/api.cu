@@ -885,6 +885,18 @@ af_status af_set_option(af_handle h, const char* name, int64_t value) {
   return AF_ERR_INVALID;
 }
 
+af_status af_set_global_option(const char* name, int64_t value) {
+  if (!name) { set_error("af_set_global_option: null"); return AF_ERR_INVALID; }
+  std::string n(name);
+  if (n == "block_n") {
+    if (value != 0 && value != 64 && value != 128 && value != 256) { set_error("af_set_global_option: block_n must be 0, 64, 128 or 256"); return AF_ERR_INVALID; }
+    conv_umma_force_block_n((int)value);
+    return AF_OK;
+  }
+  set_error("af_set_global_option: unknown option '%s'", name);
+  return AF_ERR_INVALID;
+}
+
 af_status af_get_stat(af_handle h, const char* name, double* value) {
   if (!h || !name || !value) { set_error("af_get_stat: null"); return AF_ERR_INVALID; }
   AFB_CUDA(cudaSetDevice(h->device));
@@ -1093,6 +1105,24 @@ af_status af_crop_u8(const af_frame_desc* frames_dev, const af_clip_geom* geom_d
                                 bgr, out_dev, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
+af_status af_crop_pack(const af_frame_desc* frames_dev, const af_clip_geom* geom_dev, int32_t batch,
+                       int32_t frames_per_clip, int32_t size, int32_t bgr, const float mean255[3], const float std255[3],
+                       void* clip_out_dev, int32_t out_dtype, const int64_t out_strides[5], void* stream) {
+  if (!frames_dev || !geom_dev || !clip_out_dev || !mean255 || !std255 || !out_strides || batch <= 0 ||
+      frames_per_clip <= 0 || size <= 0) {
+    set_error("af_crop_pack: invalid arguments");
+    return AF_ERR_INVALID;
+  }
+  if (out_dtype != AF_F32 && out_dtype != AF_BF16) { set_error("af_crop_pack: clip dtype must be AF_F32 or AF_BF16"); return AF_ERR_INVALID; }
+  if (out_strides[1] == 0) { set_error("af_crop_pack: channel stride must be non-zero"); return AF_ERR_INVALID; }
+  ClipLayout dst;
+  dst.base = clip_out_dev;
+  dst.sB = out_strides[0]; dst.sC = out_strides[1]; dst.sT = out_strides[2]; dst.sH = out_strides[3]; dst.sW = out_strides[4];
+  dst.T = frames_per_clip; dst.S = size; dst.is_bf16 = out_dtype == AF_BF16;
+  return (af_status)crop_launch((const FrameDesc*)frames_dev, (const ClipGeom*)geom_dev, batch, frames_per_clip, size, bgr,
+                                nullptr, &dst, mean255, std255, (cudaStream_t)stream);
+}
+
 af_status af_crop_infer(af_handle h, const af_frame_desc* frames_dev, const af_clip_geom* geom_dev, int32_t batch,
                         int32_t bgr, const float mean255[3], const float std255[3], float* logits_dev,
                         float* scores_dev, float* features_dev, void* stream) {
@@ -1185,6 +1215,49 @@ af_status af_conv_shortcut_ndhwc(const void* x_dev, const af_conv_desc* conv_hos
   if (bias) cudaFree(bias);
   free_layer(L);
   free_layer(L2);
+  return (af_status)rc;
+}
+
+af_status af_stem_pool_ndhwc4(const void* clip_dev, const af_conv_desc* stem_host, void* y_dev, int32_t batch, int32_t t,
+                              int32_t s_, int32_t per_frame_kernel, void* stream) {
+  if (!clip_dev || !stem_host || !y_dev || batch <= 0 || t <= 0 || s_ <= 0) { set_error("af_stem_pool_ndhwc4: invalid arguments"); return AF_ERR_INVALID; }
+  const af_conv_desc& d = *stem_host;
+  if (d.cin != 3 || d.cout != 64 || d.kt != 5 || d.kh != 7 || d.kw != 7 || d.st != 1 || d.sh != 2 || d.sw != 2 || d.pt != 2 ||
+      d.ph != 3 || d.pw != 3 || (s_ % 4) != 0) {
+    set_error("af_stem_pool_ndhwc4: takes the reference stem (3->64, k[5,7,7], s[1,2,2], p[2,3,3]) and size %% 4 == 0");
+    return AF_ERR_INVALID;
+  }
+  int rc = conv_rows_init();
+  if (rc) return (af_status)rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  bf16* w35 = nullptr;
+  float* bias = nullptr;
+  void* padded = nullptr;
+  const long long Tp = t + 4, Hp = s_ + 6, Wp = s_ + 8;
+  const size_t pad_bytes = (size_t)batch * Tp * Hp * Wp * 4 * 2;
+  rc = upload_stem_direct(d, &w35);
+  if (!rc && (cudaMalloc(&bias, 64 * sizeof(float)) != cudaSuccess ||
+              cudaMemcpy(bias, d.bias, 64 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+              cudaMalloc(&padded, pad_bytes) != cudaSuccess || cudaMemsetAsync(padded, 0, pad_bytes, st) != cudaSuccess)) {
+    set_error("af_stem_pool_ndhwc4: device allocation failed");
+    rc = AF_ERR_CUDA;
+  }
+  if (!rc) {
+    ClipLayout cl;
+    cl.sW = 4; cl.sH = Wp * 4; cl.sT = Hp * Wp * 4; cl.sB = Tp * Hp * Wp * 4; cl.T = t; cl.S = s_; cl.is_bf16 = true;
+    cl.base = (char*)padded + (2 * cl.sT + 3 * cl.sH + 3 * cl.sW) * 2;
+    const long long q[5] = {(long long)t * s_ * s_ * 4, 1, (long long)s_ * s_ * 4, (long long)s_ * 4, 4};   // [B,3,T,S,S] view of NDHWC4
+    rc = pack_clip_launch(clip_dev, AF_BF16, q, batch, cl, st);
+  }
+  if (!rc && cudaMemsetAsync(y_dev, 0, (size_t)batch * t * (s_ / 4) * (s_ / 4) * 64 * 2, st) != cudaSuccess) rc = AF_ERR_CUDA;
+  if (!rc) rc = conv_stem_direct_launch(padded, batch, t, s_, w35, bias, y_dev, 1, st, per_frame_kernel);
+  if (!rc && cudaStreamSynchronize(st) != cudaSuccess) {
+    set_error("af_stem_pool_ndhwc4: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = AF_ERR_CUDA;
+  }
+  if (w35) cudaFree(w35);
+  if (bias) cudaFree(bias);
+  if (padded) cudaFree(padded);
   return (af_status)rc;
 }
 

@@ -70,6 +70,7 @@ bool conv_umma_supported(const ConvProblem& p);
 int conv_umma_launch(const ConvProblem& p, cudaStream_t s);
 int conv_umma_init();
 void conv_umma_timeline_dump(int n);
+void conv_umma_force_block_n(int bn);
 // conv_rows.cu (row-halo tcgen05 kernel for Cout=64 layers with vertical taps)
 bool conv_rows_supported(const ConvProblem& p);
 int conv_rows_launch(const ConvProblem& p, cudaStream_t s);
@@ -79,7 +80,7 @@ bool conv_tsweep_supported(const ConvProblem& p);
 int conv_tsweep_launch(const ConvProblem& p, cudaStream_t s);
 int conv_tsweep_init();
 int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const void* w35, const float* bias, void* y,
-                            int pool, cudaStream_t s);
+                            int pool, cudaStream_t s, int force_per_frame = 0);
 // pool_head.cu
 int maxpool_spatial_launch(const void* x, void* y, int B, int T, int H, int W, int C, bool is_bf16,
                            cudaStream_t s);   // k[1,3,3] s[1,2,2] p[0,1,1]
@@ -99,6 +100,7 @@ struct ClipLayout {     // engine-internal normalised clip: padded NDHWC4
   long long sB, sT, sH, sW;   // element strides
   int T, S;
   bool is_bf16;
+  long long sC = 0;     // 0: 4 packed channels per pixel (the engine's NDHWC4); else 3 channels sC elements apart
 };
 int stem_unfold_launch(const ClipLayout& clip, int clip0, int B, void* U, cudaStream_t s);
 int pack_clip_launch(const void* src, int dtype, const long long strides[5], int B,

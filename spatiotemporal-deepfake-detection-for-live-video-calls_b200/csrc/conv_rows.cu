@@ -645,7 +645,7 @@ int conv_rows_launch(const ConvProblem& p, cudaStream_t s) {
 // output rows are 2 input rows = 1024 B apart (the descriptor's SBO).  Weights: [35][64][32] bf16.
 // y is the zero-initialised POOLED output (fused MaxPool3d [1,3,3]/[1,2,2]) or the dense conv output.
 int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const void* w35, const float* bias, void* y,
-                            int pool, cudaStream_t s) {
+                            int pool, cudaStream_t s, int force_per_frame) {
   if (!g_rows_encode) { set_error("conv_stem_direct: not initialised"); return AF_ERR_INVALID; }
   const int Ho = S / 2, Wo = S / 2, Tp = T + 4, Hp = S + 6, Wp = S + 8;
   if ((S & 1) || Wo % RB_X) { set_error("conv_stem_direct: unsupported clip size %d", S); return AF_ERR_INVALID; }
@@ -692,7 +692,7 @@ int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const vo
   }
   static const bool no_sweep = getenv("AFB200_NO_STEM_SWEEP") != nullptr;
   const int sweep_dyn = SW_W_BYTES + SW_A_STAGES * rp.a_stage_bytes + 2 * RB_OUT_BYTES + RB_N * 4 + 16 * 8 + 16 + 1024;
-  const bool sweep = !no_sweep && (T % RB_G == 0) && sweep_dyn <= g_rows_max_smem;
+  const bool sweep = !no_sweep && !force_per_frame && (T % RB_G == 0) && sweep_dyn <= g_rows_max_smem;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(RB_THREADS); cfg.stream = s;
   cudaLaunchAttribute attr[1];

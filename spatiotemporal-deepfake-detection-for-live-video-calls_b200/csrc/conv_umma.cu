@@ -402,6 +402,7 @@ int g_driver_version = 0;
 bool g_corner_dhw = false;    // AFB200_IM2COL_CORNERS=dhw flips the corner array order (bring-up knob)
 
 int g_max_smem = 0;
+int g_force_block_n = 0;      // af_set_global_option("block_n"): 64 / 128 / 256 forces the tile width where Cout allows (tests)
 unsigned long long* g_timeline = nullptr;      // AFB200_TIMELINE=1
 struct TimelineInfo { int grid, tiles, kblocks, bn; };
 TimelineInfo g_timeline_info[256];
@@ -494,6 +495,8 @@ int encode_im2col(CUtensorMap* map, const void* x, int B, int Ti, int Hi, int Wi
 
 }  // namespace
 
+void conv_umma_force_block_n(int bn) { g_force_block_n = bn; }
+
 int conv_umma_init() {
   if (g_encode_tiled && g_encode_im2col) return AF_OK;
   cudaDriverEntryPointQueryResult q;
@@ -572,7 +575,7 @@ struct UmmaPlan {
 };
 struct PlanKey {
   const void *x, *w, *y, *res, *x2, *w2; const float* bias;
-  int v[26];
+  int v[27];
   bool operator==(const PlanKey& o) const { return memcmp(this, &o, sizeof(PlanKey)) == 0; }
 };
 struct PlanKeyHash {
@@ -592,7 +595,7 @@ int conv_umma_launch(const ConvProblem& p, cudaStream_t s) {
   PlanKey key;
   memset(&key, 0, sizeof(key));
   key.x = p.x; key.w = p.w; key.y = p.y; key.res = p.res; key.bias = p.bias; key.x2 = p.x2; key.w2 = p.w2;
-  const int vals[26] = {p.B, p.Ti, p.Hi, p.Wi, p.Cin, p.To, p.Ho, p.Wo, p.Cout, p.kt, p.kh, p.kw, p.st, p.sh, p.sw,
+  const int vals[27] = {g_force_block_n, p.B, p.Ti, p.Hi, p.Wi, p.Cin, p.To, p.Ho, p.Wo, p.Cout, p.kt, p.kh, p.kw, p.st, p.sh, p.sw,
                         p.pt, p.ph, p.pw, p.relu, p.pool_t, p.Cin2, p.T2, p.H2, p.W2, p.sh2, p.sw2};
   memcpy(key.v, vals, sizeof(vals));
   auto it = g_plans.find(key);
@@ -638,7 +641,8 @@ int build_plan(const ConvProblem& p, UmmaPlan& plan) {
     else if (p.Cin <= 128 && bn > 128) bn = 128;
   }
   static const char* fbn = getenv("AFB200_BLOCK_N");
-  if (fbn) { int v = atoi(fbn); if ((v == 64 || v == 128 || v == 256) && p.Cout % v == 0) bn = v; }
+  int force_bn = g_force_block_n ? g_force_block_n : (fbn ? atoi(fbn) : 0);
+  if ((force_bn == 64 || force_bn == 128 || force_bn == 256) && p.Cout % force_bn == 0) bn = force_bn;
   up.num_n_tiles = p.Cout / bn;
 
   if (up.im2col) {

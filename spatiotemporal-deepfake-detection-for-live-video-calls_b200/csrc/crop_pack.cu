@@ -38,6 +38,10 @@ template <> __device__ __forceinline__ void store_px4<bf16>(bf16* p, float a, fl
   *reinterpret_cast<uint2*>(p) = t;
 }
 
+template <typename T> __device__ __forceinline__ void store_1(T* p, float v);
+template <> __device__ __forceinline__ void store_1<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void store_1<bf16>(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
 struct Norm { float mean[3], stdv[3]; };
 
 __device__ __forceinline__ float norm1(float v, float m, float s) { return __fdiv_rn(__fsub_rn(v, m), s); }
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
                                                    const ClipGeom* __restrict__ geom, int T_, int S,
                                                    int bgr, uint8_t* __restrict__ out_u8, T* dst,
                                                    long long sB, long long sT, long long sH,
-                                                   long long sW, const float* __restrict__ lut) {
+                                                   long long sW, long long sC, const float* __restrict__ lut) {
   // block-uniform values are packed so that a thread fetches them with five vector LDS (the kernel is LSU-bound)
   __shared__ int2 s_col[32], s_row[8];         // (adelta, bdelta) per column, (X0, Y0) per row
   __shared__ int4 s_win;                       // valid canvas window x_lo, x_hi, y_lo, y_hi
@@ -158,7 +162,13 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
 
   if (kToClip) {
     T* q = dst + b * sB + t * sT + y * sH + x * sW;
-    store_px4<T>(q, __ldg(lut + o[0]), __ldg(lut + 256 + o[1]), __ldg(lut + 512 + o[2]));
+    if (sC == 0) {
+      store_px4<T>(q, __ldg(lut + o[0]), __ldg(lut + 256 + o[1]), __ldg(lut + 512 + o[2]));
+    } else {      // caller tensor viewed as [B,3,T,S,S] with its own strides (af_crop_pack)
+      store_1<T>(q, __ldg(lut + o[0]));
+      store_1<T>(q + sC, __ldg(lut + 256 + o[1]));
+      store_1<T>(q + 2 * sC, __ldg(lut + 512 + o[2]));
+    }
   } else {
     uint8_t* q = out_u8 + (((long long)bt * S + y) * S + x) * 3;
     q[0] = (uint8_t)o[0]; q[1] = (uint8_t)o[1]; q[2] = (uint8_t)o[2];
@@ -294,13 +304,13 @@ int crop_launch(const FrameDesc* frames, const ClipGeom* geom, int B, int T, int
     if (rc) return rc;
   }
   if (dst == nullptr) {
-    crop_kernel<float, false><<<grid, block, 0, s>>>(frames, geom, T, S, bgr, out_u8, nullptr, 0, 0, 0, 0, nullptr);
+    crop_kernel<float, false><<<grid, block, 0, s>>>(frames, geom, T, S, bgr, out_u8, nullptr, 0, 0, 0, 0, 0, nullptr);
   } else if (dst->is_bf16) {
     crop_kernel<bf16, true><<<grid, block, 0, s>>>(frames, geom, T, S, bgr, nullptr, (bf16*)dst->base, dst->sB,
-                                                   dst->sT, dst->sH, dst->sW, lut);
+                                                   dst->sT, dst->sH, dst->sW, dst->sC, lut);
   } else {
     crop_kernel<float, true><<<grid, block, 0, s>>>(frames, geom, T, S, bgr, nullptr, (float*)dst->base, dst->sB,
-                                                    dst->sT, dst->sH, dst->sW, lut);
+                                                    dst->sT, dst->sH, dst->sW, dst->sC, lut);
   }
   ++g_launches;
   AFB_CUDA(cudaGetLastError());

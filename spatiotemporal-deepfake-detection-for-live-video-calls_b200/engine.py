@@ -107,6 +107,8 @@ class Engine:
         stage, the `backbone(x) -> [B,T',D]` contract of dualrun's AltFreezingRGBEncoder."""
         if x.dim() != 5 or tuple(x.shape[1:]) != (3, self.clip_t, self.clip_s, self.clip_s):
             raise ValueError("afb200 engine takes [B,3,%d,%d,%d] clips, got %s" % (self.clip_t, self.clip_s, self.clip_s, tuple(x.shape)))
+        if x.device != self.device:
+            raise ValueError("clip tensor is on %s, engine on %s" % (x.device, self.device))
         if x.dtype not in _DTYPES:
             x = x.float()
         B = x.shape[0]
@@ -234,6 +236,27 @@ def conv_ndhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride
                               C.c_void_p(residual.data_ptr()) if residual is not None else None,
                               C.c_void_p(y.data_ptr()), B, T, H, W, int(relu), prec, impl,
                               C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "af_conv_ndhwc")
+    return y
+
+
+def set_global_option(name: str, value: int):
+    """Process-wide diagnostic knob (af_set_global_option), e.g. ("block_n", 64|128|256|0)."""
+    check(lib().af_set_global_option(name.encode(), int(value)), "af_set_global_option(%s)" % name)
+
+
+def stem_pool_ndhwc4(clip: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, per_frame_kernel: bool = False) -> torch.Tensor:
+    """The fused stem kernel on its own (test/diagnostic entry af_stem_pool_ndhwc4): clip bf16 [B,T,S,S,4] (channel 3
+    ignored), folded stem weight [64,3,5,7,7] + bias [64] -> relu(conv) max-pooled 3x3/2, bf16 [B,T,S/4,S/4,64]."""
+    assert clip.is_cuda and clip.is_contiguous() and clip.dtype == torch.bfloat16 and clip.shape[-1] == 4
+    B, T, S, S2, _ = clip.shape
+    assert S == S2
+    d, keep = _conv_desc(weight, bias, (1, 2, 2), (2, 3, 3))
+    y = torch.empty((B, T, S // 4, S // 4, 64), dtype=torch.bfloat16, device=clip.device)
+    with torch.cuda.device(clip.device):
+        check(lib().af_stem_pool_ndhwc4(C.c_void_p(clip.data_ptr()), C.byref(d), C.c_void_p(y.data_ptr()), B, T, S,
+                                        int(per_frame_kernel), C.c_void_p(torch.cuda.current_stream(clip.device).cuda_stream)),
+              "af_stem_pool_ndhwc4")
+    del keep
     return y
 
 

@@ -27,7 +27,10 @@ class ClassifierSvc:
         self.engine.mean255, self.engine.std255 = mean_std_255("svc")
         self.clip_size, self.imsize = clip_size, imsize
         self._last_scores: Optional[np.ndarray] = None
-        self._last_logits: Optional[np.ndarray] = None
+        # The reference keeps `_last_logits` only for 2-class heads and sets it to None for the 1-logit head
+        # (TEST2.py:184-199); TEST2.py:1107-1110 softmaxes it when it is not None, so it must stay None here.
+        self._last_logits = None
+        self.last_logits_1d: Optional[np.ndarray] = None      # the raw logits of the last call, float32 [B]
 
     def infer_scores(self, aligned_batch_bthwc) -> np.ndarray:
         arr = np.asarray(aligned_batch_bthwc)
@@ -38,7 +41,7 @@ class ClassifierSvc:
             # the reference casts whatever it gets to fp32; aligned crops are always u8
             arr = np.clip(np.rint(arr), 0, 255).astype(np.uint8)
         scores, logits = self.engine.infer_scores_u8_host(arr, return_logits=True)
-        self._last_scores, self._last_logits = scores.copy(), logits
+        self._last_scores, self.last_logits_1d = scores.copy(), logits
         return scores
 
     def infer_scores_stream(self, batches):
@@ -66,5 +69,6 @@ class CropAlignSvc:
         self.fn = CropAlignB200(imsize, device=device)
 
     def __call__(self, infos, imgs):
-        _, aligned = self.fn(infos, imgs)
-        return aligned
+        """-> (lm68_T, aligned u8 [T,S,S,3]), the 2-tuple both callers unpack as `_, aligned = svc(infos, imgs)`
+        (TEST2.py:207-212,401; test/af_realtime.py:104,325)."""
+        return self.fn(infos, imgs)

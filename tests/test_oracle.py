@@ -158,7 +158,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     L.af_version.restype = ctypes.c_int32
-    assert L.af_version() == 101
+    assert L.af_version() == 102
     assert afb200.lib().af_last_error() is not None
 
 

@@ -98,3 +98,19 @@ def test_wire_format_against_the_reference(tmp_path):
     for _ in range(20):
         s = rng.uniform(0, 1, size=int(rng.integers(1, 40))).tolist()
         assert afb200.live.score_with_stability(s, 0.7) == pytest.approx(ns["score_with_stability"](s, 0.7))
+    # _pool_track (TEST2.py:636-683): all eight methods + the fallback, lifted the same way
+    m = re.search(r"\n        def _pool_track\((.*?)\):\n(.*?)\n            # fallback\n            return float\(np\.median\(s\)\)\n", src, re.S)
+    assert m, "reference _pool_track not found"
+    body = m.group(2) + "\n            # fallback\n            return float(np.median(s))"
+    exec("def _pool_track(" + m.group(1) + "):\n" + "\n".join(l[8:] for l in body.split("\n")), ns)
+    methods = ["mean", "median", "logit_median", "topk", "topk_median", "percentile", "trimmed_mean", "adaptive", "nonsense"]
+    for trial in range(30):
+        n = int(rng.integers(1, 60))
+        s = (rng.uniform(0.4, 0.55, size=n) if trial % 3 == 0 else rng.uniform(0, 1, size=n)).tolist()   # tight and wide IQRs
+        for meth in methods:
+            kw = dict(topk_ratio=float(rng.choice([0.1, 0.2, 0.5])), percentile_p=float(rng.choice([50.0, 80.0, 95.0, 120.0])),
+                      trim_ratio=float(rng.choice([0.0, 0.2, 0.6])))
+            want = ns["_pool_track"](s, meth, **kw)
+            got = afb200.live.pool_track(s, meth, **kw)
+            assert got == pytest.approx(want, rel=1e-12, abs=1e-15), (meth, kw, n)
+    assert afb200.live.pool_track([], "mean") == ns["_pool_track"]([], "mean") == 0.0
