@@ -37,7 +37,17 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
+    ap.add_argument("--workload", default="clips", choices=["clips", "offline", "live", "rgb"],
+                    help="clips: BASELINE configs[1] (the headline; also runs short forms of the others unless --no-extra); "
+                         "offline / live / rgb: BASELINE configs 3 / 4 / 5 on their own")
+    ap.add_argument("--offline-clips", type=int, default=4096)
+    ap.add_argument("--live-streams", type=int, default=64)
+    ap.add_argument("--live-seconds", type=float, default=4.0)
+    ap.add_argument("--rgb-batch", type=int, default=64)
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short offline / live / rgb workloads")
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--variant", default="i3d", choices=["i3d", "ftcn_tt"],
@@ -187,7 +197,7 @@ def run_reference(args):
 def build_gpu_inputs(dev, batch, rank):
     """Frames + descriptors resident in HBM for `batch` clips: a ring of 256+ distinct 720p
     frames (sliding 32-frame windows, stride 8, as in the live-call path) and per-clip geometry
-    from seeded synthetic tracks."""
+    from seeded synthetic tracks.  Also returns the (frames, boxes, geoms) lists for the parity leg."""
     import numpy as np
     import torch
     import afb200
@@ -208,7 +218,19 @@ def build_gpu_inputs(dev, batch, rank):
         geoms.append((tfm, lt, wh))
     fd, cg = afb200.crop.pack_descriptors(frames, boxes, geoms, dev)
     src_bytes = sum(int((b[2] - b[0]) * (b[3] - b[1]) * 3) for b in boxes)
-    return pool, fd, cg, src_bytes
+    return pool, fd, cg, src_bytes, (frames, boxes, geoms)
+
+
+def _traffic_for(variant, B, precision):
+    """DRAM bytes per step of the conv launches from the committed ncu capture of THIS variant (None if absent)."""
+    names = ["r02_traffic.json", "r01_traffic.json"] if variant == "i3d" else ["r02_traffic_%s.json" % variant]
+    for nm in names:
+        tp = os.path.join(ROOT, "profiles", nm)
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("batch") == B and precision == "bf16" and tj.get("variant", "i3d") == variant:
+                return tj["conv_dram_bytes_per_step"], tj["source"]
+    return None, None
 
 
 def run_ours(args):
@@ -217,6 +239,8 @@ def run_ours(args):
     import torch.distributed as dist
     import afb200
     from afb200 import parallel, synthetic
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_legs as legs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -230,10 +254,30 @@ def run_ours(args):
     peaks = measured_peaks()
     B = args.batch
     sd = synthetic.synthetic_state_dict(0, args.variant)
+    cores = os.cpu_count() or 1
+
+    if args.workload != "clips":                    # one of BASELINE configs 3/4/5 on its own
+        eng = afb200.Engine(sd, device=local_rank, max_batch=B, precision=args.precision, variant=args.variant)
+        if args.workload == "offline":
+            res = legs.offline_leg(eng, B, args.offline_clips, rank, world, dev)
+            metric, value, unit = "offline_clips_per_s_32x224x224", res["value"], "clips/s"
+        elif args.workload == "live":
+            res = legs.live_leg(eng, args.live_streams, args.live_seconds, rank, world, dev)
+            metric, value, unit = "live_p50_latency_ms", res["latency_ms_p50"], "ms"
+        else:
+            res = legs.rgb_leg(sd, args.rgb_batch, rank, world, dev, local_rank)
+            metric, value, unit = "rgb_branch_clips_per_s", res["value"], "clips/s"
+        if rank == 0:
+            _emit(json.dumps({"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+                              "warmup": args.warmup, "higher_is_better": args.workload != "live", "scaling": "strong",
+                              "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                              "config": {"workload": res["workload"]}, "result": res}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         inputs = make_cpu_clip_inputs(1)
         cpu_reference_step(sd, inputs, 1, args.variant)
@@ -253,14 +297,14 @@ def run_ours(args):
         eng.set_option("chunk_front", args.chunk_front)
     if args.chunk_back:
         eng.set_option("chunk_back", args.chunk_back)
-    pool, fd, cg, src_bytes = build_gpu_inputs(dev, B, rank)
+    pool, fd, cg, src_bytes, clip_sources = build_gpu_inputs(dev, B, rank)
     n_total = B * world
 
     def step():
         logits, scores = eng.crop_infer(fd, cg, B)
         if world > 1:
-            return parallel.gather_scores(scores, n_total)
-        return scores
+            return logits, parallel.gather_scores(scores, n_total)
+        return logits, scores
 
     # clocks are sampled from the warm-up on (the GPU is under the same load) so that short timed regions
     # still get samples; the timed region itself is bracketed below
@@ -278,7 +322,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e0.record()
     for _ in range(args.steps):
-        out = step()
+        last_logits, out = step()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -302,47 +346,30 @@ def run_ours(args):
     conv_n = eng.get_stat("conv_umma_launches")
     simt_ms = eng.get_stat("conv_simt_ms")
     conv_alg_bytes = eng.get_stat("conv_bytes")
+    k1_ms, k1_n = eng.get_stat("feed_ms"), eng.get_stat("feed_launches")
     value = n_total * args.steps / (ms / 1e3)
 
-    # end-to-end through the host-buffer C-ABI call (ClassifierSvc.infer_scores boundary)
-    e2e = None
+    # end to end with HOST inputs, two boundaries, both at --steps:
+    #  e2e          crop boundary (matches the reference arm's work: crop/align + pack + classify)
+    #  e2e_aligned  ClassifierSvc.infer_scores boundary (pre-aligned u8 clips)
+    e2e = e2e_aligned = None
     if not args.no_e2e:
+        n_e2e = max(3, args.steps)
+        dt, h2d, d2h = legs.e2e_crop_leg(eng, B, n_e2e, 2, rank, dev)
+        e2e = {"value": n_total * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": n_e2e, "boundary": "crop",
+               "api": "afb200.live.FrameRing.put_rows (af_ring_put_rows) + af_crop_infer: per step every one of the %d streams "
+                      "uploads its 8 new decoded 720p frames (the rows under the face box) from pinned host memory into the "
+                      "device ring, the host computes crop boxes + the similarity fit and the descriptors of the 32-frame "
+                      "windows (stride 8), af_crop_infer warps/normalises/classifies, scores are read back; two steps in "
+                      "flight" % B}
+        dt_a, dt_b = legs.e2e_aligned_leg(eng, B, n_e2e, dev)
         clip_bytes = 32 * 224 * 224 * 3
-        # two pinned input batches, used alternately: every step uploads its own clips and reads its own scores back;
-        # the pipelined service call (af_submit_u8_host / af_wait = ClassifierSvc.infer_scores_stream) lets the upload
-        # of step i+1 overlap the compute of step i
-        hosts = [torch.empty((B, 32, 224, 224, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
-        for h_ in hosts:
-            h_.random_(0, 256)
-        for i in range(2):
-            eng.wait(eng.submit_u8_host_ptr(hosts[i].data_ptr(), B), B)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        n_e2e = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        pending = eng.submit_u8_host_ptr(hosts[0].data_ptr(), B)
-        for i in range(1, n_e2e):
-            nxt = eng.submit_u8_host_ptr(hosts[i & 1].data_ptr(), B)
-            scores_h, _ = eng.wait(pending, B)
-            pending = nxt
-        scores_h, _ = eng.wait(pending, B)
-        torch.cuda.synchronize()
-        dt = parallel.max_over_ranks(time.perf_counter() - t0, dev)
-        e2e = {"value": n_total * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": B * clip_bytes,
-               "d2h_bytes_per_step": 8 * B, "steps": n_e2e,
-               "api": "af_submit_u8_host + af_wait (ClassifierSvc.infer_scores_stream: pinned u8 [B,32,224,224,3] -> scores "
-                      "on the host, two batches in flight)"}
-        # the one-call-at-a-time form of the same boundary (ClassifierSvc.infer_scores), for comparison
-        h_logits = torch.empty(B, dtype=torch.float32).pin_memory()
-        h_scores = torch.empty(B, dtype=torch.float32).pin_memory()
-        eng.infer_u8_host_ptr(hosts[0].data_ptr(), B, h_logits.data_ptr(), h_scores.data_ptr())
-        t0 = time.perf_counter()
-        for i in range(n_e2e):
-            eng.infer_u8_host_ptr(hosts[i & 1].data_ptr(), B, h_logits.data_ptr(), h_scores.data_ptr())
-        torch.cuda.synchronize()
-        dt = parallel.max_over_ranks(time.perf_counter() - t0, dev)
-        e2e["blocking_call_value"] = n_total * n_e2e / dt
+        e2e_aligned = {"value": n_total * n_e2e / dt_a, "unit": UNIT, "h2d_bytes_per_step": B * clip_bytes,
+                       "d2h_bytes_per_step": 8 * B, "steps": n_e2e, "boundary": "aligned clips",
+                       "api": "af_submit_u8_host + af_wait (ClassifierSvc.infer_scores_stream: pinned u8 [B,32,224,224,3] -> "
+                              "scores on the host, two batches in flight); no crop kernel on this boundary",
+                       "blocking_call_value": n_total * n_e2e / dt_b}
 
     # p50 batch-1 latency (crop + trunk + score on host), rank 0 only
     p50 = p99 = None
@@ -359,18 +386,47 @@ def run_ours(args):
         p50 = lat[len(lat) // 2]
         p99 = lat[min(len(lat) - 1, int(round(0.99 * (len(lat) - 1))))]
 
+    # parity of the very batch that was timed (rank 0): 4 clips back through af_crop_u8 -> CPU oracle
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = legs.parity_leg(sd, args.variant, last_logits.cpu().numpy(), clip_sources, [0, B // 3, (2 * B) // 3, B - 1] if B >= 4 else list(range(B)), cores)
+
+    # the stock PyTorch (cuDNN) path on the same GPU, N=1 only
+    gpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        gpu_baseline = legs.torch_gpu_leg(sd, args.variant, B, dev, "amp_bf16")
+        gpu_baseline["tf32"] = legs.torch_gpu_leg(sd, args.variant, B, dev, "tf32")
+
+    # BASELINE configs 3 / 4 / 5, short forms (every rank takes part)
+    workloads = None
+    if not args.no_extra and args.variant == "i3d" and args.precision == "bf16":
+        workloads = {"offline_4096": legs.offline_leg(eng, B, args.offline_clips, rank, world, dev),
+                     "live_64_streams": legs.live_leg(eng, args.live_streams, args.live_seconds, rank, world, dev),
+                     "rgb_branch_b64": legs.rgb_leg(sd, args.rgb_batch, rank, world, dev, local_rank)}
+
     launches_t = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(launches_t)
     if rank == 0:
         achieved = conv_flops / (conv_ms * 1e9) if conv_ms > 0 else 0.0
         peak = peaks["bf16_sustained"]
-        traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):
-            tj = json.load(open(tp))
-            if tj.get("batch") == B and args.precision == "bf16":
-                traffic, traffic_src = tj["conv_dram_bytes_per_step"], tj["source"]
+        traffic, traffic_src = _traffic_for(args.variant, B, args.precision)
+        floor_ms = FLOPS_PER_CLIP / (peak * 1e12) * 1e3 if args.variant == "i3d" else None
+        k1_ms_per_launch = k1_ms / k1_n if k1_n else None
+        k1_clips_per_launch = B * args.steps / k1_n if k1_n else None
+        roofline_k1 = None
+        if k1_ms_per_launch:
+            k1_ach = K1_BYTES_PER_CLIP * k1_clips_per_launch / (k1_ms_per_launch * 1e6)       # GB/s
+            k1_ach_moved = (src_bytes / B + 32 * 230 * 232 * 8) * k1_clips_per_launch / (k1_ms_per_launch * 1e6)
+            roofline_k1 = {"bound": "hbm", "kernel": "crop_kernel (K1: gather + integer-exact warp + normalise + pack)",
+                           "achieved": k1_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": k1_ach / peaks["hbm_gbs"],
+                           "algorithmic_bytes_per_clip": K1_BYTES_PER_CLIP, "ms_per_launch": k1_ms_per_launch,
+                           "clips_per_launch": k1_clips_per_launch,
+                           "achieved_bytes_moved": k1_ach_moved,
+                           "note": "achieved = 18.7 MB/clip (SURVEY 8d: u8 crops read once + bf16 NCTHW clip written once) x clips per "
+                                   "launch / CUDA-event duration of the launch; achieved_bytes_moved counts this run's source boxes and "
+                                   "the padded NDHWC4 clip the kernel really writes",
+                           "whole_step_form": K1_BYTES_PER_CLIP * value / world / (peaks["hbm_gbs"] * 1e9)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
@@ -379,19 +435,21 @@ def run_ours(args):
                            "clips_per_step_per_gpu": B, "parallelism": "clip-sharded x%d, scores all-gathered" % world,
                            "l2": "inputs and activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
                            "weights": "seeded synthetic (no checkpoint ships with the reference)"},
-                "e2e": e2e, "gpu_launches": int(launches_t.item()),
+                "e2e": e2e, "e2e_aligned": e2e_aligned, "gpu_launches": int(launches_t.item()),
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak, "traffic": traffic,
                              "traffic_note": "DRAM bytes (read+write) of the %d tcgen05 conv launches of ONE step, from %s" % (int(conv_n / args.steps), traffic_src) if traffic else None,
                              "algorithmic_bytes_per_step": conv_alg_bytes / args.steps,
                              "algorithmic_flops_per_step": conv_flops / args.steps,
-                             "kernel": "tcgen05 conv kernels (conv_umma_kernel<64|128|256> + conv_rows_kernel), all launches of the timed region",
+                             "kernel": "tcgen05 conv kernels (conv_umma_kernel<64|128|256> + conv_rows_kernel + stem_sweep_kernel + conv_tsweep_kernel), all launches of the timed region",
                              "launches": int(conv_n), "kernel_ms_per_step": conv_ms / args.steps,
                              "share_of_step": conv_ms / ms if ms > 0 else None,
                              "peak_source": "%s bf16_tflops_sustained (MEASURED_PEAKS.json)" % peaks["source"],
                              "simt_conv_ms_per_step": simt_ms / args.steps,
                              "whole_step_frac_of_tensor_roofline": (value / world * FLOPS_PER_CLIP / (peak * 1e12)
                                                                     if args.variant == "i3d" else None),
+                             "whole_step_frac_of_burst_roofline": (value / world * FLOPS_PER_CLIP / (peaks["bf16_burst"] * 1e12)
+                                                                   if args.variant == "i3d" else None),
                              # the same launches split by the roofline that bounds each (algorithmic FLOP/byte of the
                              # launch vs the ridge peak_tflops / peak_hbm): how close each class runs to ITS limit
                              "classes": {
@@ -404,11 +462,38 @@ def run_ours(args):
                                                "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                                "frac": hb_bytes / (hb_ms * 1e6) / peaks["hbm_gbs"] if hb_ms > 0 else None,
                                                "bytes": "algorithmic (input + output + residual + weights of each launch)"}}},
-                "cpu_baseline": cpu_baseline, "clocks": clocks, "p50_batch1_latency_ms": p50, "p99_batch1_latency_ms": p99,
-                "k1_src_bytes_per_clip": src_bytes / B}
+                "roofline_k1": roofline_k1,
+                "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline, "parity": parity, "clocks": clocks,
+                "p50_batch1_latency_ms": p50, "p99_batch1_latency_ms": p99,
+                "p50_latency_floor_ms": floor_ms, "p50_frac_of_floor": (floor_ms / p50 if (floor_ms and p50) else None),
+                "k1_src_bytes_per_clip": src_bytes / B, "workloads": workloads}
         _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not (parity["max_abs_dlogit"] <= parity["tolerance"] and parity["crop_bit_exact"]):
+        sys.stderr.write("bench.py: PARITY FAILED on the timed batch: %s\n" % json.dumps(parity))
+        sys.exit(3)
+
+
+def run_torch_gpu(args):
+    """--impl torch_gpu: the stock PyTorch/cuDNN path of the same network on the same B200 (N=1, rank 0)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from afb200 import synthetic
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_legs as legs
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    sd = synthetic.synthetic_state_dict(0, args.variant)
+    mode = {"bf16": "amp_bf16", "fp32": "tf32"}[args.precision]
+    res = legs.torch_gpu_leg(sd, args.variant, args.batch, dev, mode, steps=max(1, args.steps), warmup=max(2, args.warmup))
+    _emit(json.dumps({"metric": METRIC, "value": res.get("value"), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": res.get("ms_per_step"), "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "impl": "torch_gpu",
+                      "config": {"workload": "%s, batch %d, stock PyTorch (%s) on the same GPU, u8 clips resident in HBM" % (_net_name(args.variant), args.batch, mode)},
+                      "gpu_baseline": res, "gpu_launches": 0}))
 
 
 def _net_name(variant):
@@ -443,5 +528,7 @@ if __name__ == "__main__":
         _emit = out.emit
         if a.impl == "reference":
             run_reference(a)
+        elif a.impl == "torch_gpu":
+            run_torch_gpu(a)
         else:
             run_ours(a)

@@ -215,6 +215,15 @@ af_status af_crop_u8(const af_frame_desc* frames_dev, const af_clip_geom* geom_d
                      int32_t frames_per_clip, int32_t size, int32_t bgr, uint8_t* out_dev,
                      void* stream);
 
+/* Device frame ring feed (stands in for the per-track deques of decoded frames the streaming
+ * callers keep on the host, test/af_realtime.py:456-479, TEST2.py:354-391): queue `n` host->device copies, item i
+ * being rows [row0[i], row1[i]) of the decoded frame frames_host[i] (row pitch `pitch` bytes, pinned memory for
+ * truly asynchronous copies) into the same rows of ring slot slots[i] (slot k starts at ring_dev + k*slot_stride).
+ * A caller uploads each NEW frame once - only the rows its face box covers - and every overlapping window then
+ * gathers from the ring through af_crop_infer / af_crop_u8 descriptors. */
+af_status af_ring_put_rows(uint8_t* ring_dev, int64_t slot_stride, int64_t pitch, int32_t n, const int32_t* slots,
+                           const uint8_t* const* frames_host, const int32_t* row0, const int32_t* row1, void* stream);
+
 /* K1 on its own (SURVEY.md 8b `crop_pack`): the same warp followed by the callers' pack step
  *   x = (float(u8) - 255*mean_c) / (255*std_c), NTHWC -> NCTHW   (demo.py:84-87,317-319; TEST2.py:147-158)
  * written straight into a caller tensor viewed as [B,3,T,S,S] with ELEMENT strides `out_strides`

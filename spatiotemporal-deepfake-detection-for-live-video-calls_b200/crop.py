@@ -86,6 +86,64 @@ def clip_geometry(big_boxes, lm5_rel, size=224):
     return left_top, (int(w), int(h)), diff, tfm, trans
 
 
+def get_crop_boxes(shape, boxes, scale=0.5):
+    """get_crop_box for an [N,4] array of detector boxes in one vectorised pass (same arithmetic element by element,
+    so the results are identical to N scalar calls) -> int [N,4]."""
+    height, width = shape
+    b = np.rint(np.asarray(boxes, np.float64)).astype(int).reshape(-1, 2, 2)
+    half = scale * (b[:, 1] - b[:, 0])
+    nb = b + np.stack([-half, half], axis=1)
+    nb[:, :, 0] = np.clip(nb[:, :, 0], 0, width - 1)
+    nb[:, :, 1] = np.clip(nb[:, :, 1], 0, height - 1)
+    return np.rint(nb).astype(int).reshape(-1, 4)
+
+
+def _fit_nonreflective_batch(src, dst):
+    """_fit_nonreflective for B point sets sharing ONE target layout: src [B,n,2], dst [n,2] -> T [B,3,3].  The
+    system matrix depends on dst only and is built once."""
+    n = dst.shape[0]
+    x, y = dst[:, 0:1], dst[:, 1:2]
+    one, zero = np.ones((n, 1)), np.zeros((n, 1))
+    X = np.vstack((np.hstack((x, y, one, zero)), np.hstack((y, -x, zero, one))))
+    U = np.concatenate((src[:, :, 0], src[:, :, 1]), axis=1)              # [B, 2n]
+    r = np.empty((src.shape[0], 4))
+    for b in range(src.shape[0]):       # one single-right-hand-side solve per clip, exactly the scalar routine's call
+        sol, _, rank, _ = np.linalg.lstsq(X, U[b][:, None], rcond=-1)    # (LAPACK's multi-RHS path is 1000x slower here)
+        if rank < 4:
+            raise ValueError("similarity fit needs at least two distinct points")
+        r[b] = sol[:, 0]
+    M = np.zeros((src.shape[0], 3, 3))
+    M[:, 0, 0], M[:, 0, 1] = r[:, 0], -r[:, 1]
+    M[:, 1, 0], M[:, 1, 1] = r[:, 1], r[:, 0]
+    M[:, 2, 0], M[:, 2, 1], M[:, 2, 2] = r[:, 2], r[:, 3], 1.0
+    T = np.linalg.inv(M)
+    T[:, :, 2] = (0.0, 0.0, 1.0)
+    return T
+
+
+def clip_geometry_batch(big_boxes, lm5_rel, size=224):
+    """clip_geometry for B clips at once (the host side of a 32-clip step costs one lstsq pair instead of 64):
+    big_boxes [B,T,4] int, lm5_rel [B,T,5,2] -> list of (tfm 2x3, left_top (x,y), canvas (w,h)) per clip.
+    Same algorithm and the same lstsq calls, incl. the reference's mirrored-target quirk; everything around the
+    solves is vectorised over the clips (transforms agree with the per-clip routine to ~1e-12)."""
+    boxes = np.asarray(big_boxes)
+    B, T = boxes.shape[:2]
+    left_top = boxes[:, :, :2].min(1)                                     # [B,2]
+    wh = boxes[:, :, 2:].max(1) - left_top
+    diff = boxes[:, :, :2] - left_top[:, None]
+    src = (np.asarray(lm5_rel, np.float64) + diff[:, :, None, :]).reshape(B, T * 5, 2)
+    dst = np.repeat((STD_POINTS_256 * size / 256.0)[None], T, 0).reshape(-1, 2)
+    direct = _fit_nonreflective_batch(src, dst)
+    dst_m = dst.copy()
+    dst_m[:, 0] *= -1.0
+    mirrored = _fit_nonreflective_batch(src, dst_m) @ np.diag([-1.0, 1.0, 1.0])
+    src1 = np.concatenate((src, np.ones((B, T * 5, 1))), axis=2)
+    e_d = np.linalg.norm(((src1 @ direct)[:, :, :2] - dst_m[None]).reshape(B, -1), axis=1)     # both vs the mirrored targets
+    e_m = np.linalg.norm(((src1 @ mirrored)[:, :, :2] - dst_m[None]).reshape(B, -1), axis=1)
+    trans = np.where((e_d <= e_m)[:, None, None], direct, mirrored)
+    return [(trans[b][:, 0:2].T.copy(), left_top[b], (int(wh[b, 0]), int(wh[b, 1]))) for b in range(B)]
+
+
 def pack_descriptors(frame_tensors: Sequence[torch.Tensor], big_boxes, geoms, device) -> Tuple[torch.Tensor, torch.Tensor]:
     """Build the device arrays af_crop_u8 / af_crop_infer take.
     frame_tensors: B*T u8 CUDA tensors [H,W,3] (may alias one another; may be row-strided views);

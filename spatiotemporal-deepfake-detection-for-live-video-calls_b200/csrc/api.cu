@@ -220,7 +220,8 @@ struct af_engine {
   std::vector<cudaEvent_t> ev_pool;
   // kind 0: tcgen05 launch whose algorithmic intensity is above the roofline ridge (tensor-bound), 1: CUDA-core conv,
   // 2: tcgen05 launch below the ridge (HBM-bound)
-  double stat_ms[3] = {0, 0, 0}, stat_flops[3] = {0, 0, 0}, stat_launches[3] = {0, 0, 0}, stat_kbytes[3] = {0, 0, 0};
+  // 3: the feeder of a front chunk (crop / pack kernel = K1)
+  double stat_ms[4] = {0, 0, 0, 0}, stat_flops[4] = {0, 0, 0, 0}, stat_launches[4] = {0, 0, 0, 0}, stat_kbytes[4] = {0, 0, 0, 0};
   double stat_bytes = 0;
   double ridge_flop_per_byte = 208.0;   // measured sustained bf16 TFLOP/s / measured HBM TB/s (option "ridge_x1000")
   // kept stages (fp32 NCTHW) for parity tests
@@ -483,7 +484,12 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
     for (int f0 = g0; f0 < g0 + gB; f0 += e->cb_front) {
       const int fB = (g0 + gB - f0) < e->cb_front ? (g0 + gB - f0) : e->cb_front;
       const char* xin = (const char*)e->clip.base + (long long)f0 * e->clip.sB * e->esz;
-      int rc = feed(f0, fB, s);
+      int rc;
+      {
+        ProfRec prec(e, s);
+        rc = feed(f0, fB, s);
+        prec.done(3, 0.0, 0.0);
+      }
       if (rc) return rc;
       bool fused_pool = false;
       bool stem_done = false;
@@ -867,7 +873,7 @@ af_status af_set_option(af_handle h, const char* name, int64_t value) {
     cudaDeviceSynchronize();
     for (auto& r : h->ev_recs) { h->ev_pool.push_back(r.e0); h->ev_pool.push_back(r.e1); }
     h->ev_recs.clear();
-    for (int k = 0; k < 3; ++k) h->stat_ms[k] = h->stat_flops[k] = h->stat_launches[k] = h->stat_kbytes[k] = 0;
+    for (int k = 0; k < 4; ++k) h->stat_ms[k] = h->stat_flops[k] = h->stat_launches[k] = h->stat_kbytes[k] = 0;
     h->stat_bytes = 0;
     return AF_OK;
   }
@@ -925,6 +931,8 @@ af_status af_get_stat(af_handle h, const char* name, double* value) {
   else if (n == "conv_simt_flops") *value = h->stat_flops[1];
   else if (n == "conv_simt_launches") *value = h->stat_launches[1];
   else if (n == "conv_bytes") *value = h->stat_bytes;
+  else if (n == "feed_ms") *value = h->stat_ms[3];
+  else if (n == "feed_launches") *value = h->stat_launches[3];
   else { set_error("af_get_stat: unknown stat '%s'", name); return AF_ERR_INVALID; }
   return AF_OK;
 }
@@ -1103,6 +1111,26 @@ af_status af_crop_u8(const af_frame_desc* frames_dev, const af_clip_geom* geom_d
   static_assert(sizeof(af_clip_geom) == sizeof(ClipGeom), "clip geom layout");
   return (af_status)crop_launch((const FrameDesc*)frames_dev, (const ClipGeom*)geom_dev, batch, frames_per_clip, size,
                                 bgr, out_dev, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+af_status af_ring_put_rows(uint8_t* ring_dev, int64_t slot_stride, int64_t pitch, int32_t n, const int32_t* slots,
+                           const uint8_t* const* frames_host, const int32_t* row0, const int32_t* row1, void* stream) {
+  if (!ring_dev || n < 0 || (n > 0 && (!slots || !frames_host || !row0 || !row1)) || pitch <= 0 || slot_stride < pitch) {
+    set_error("af_ring_put_rows: invalid arguments");
+    return AF_ERR_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int i = 0; i < n; ++i) {
+    if (row1[i] <= row0[i]) continue;
+    if (row0[i] < 0 || (int64_t)row1[i] * pitch > slot_stride || slots[i] < 0 || !frames_host[i]) {
+      set_error("af_ring_put_rows: item %d out of range (slot %d, rows %d..%d)", i, slots[i], row0[i], row1[i]);
+      return AF_ERR_INVALID;
+    }
+    const int64_t off = (int64_t)row0[i] * pitch;
+    AFB_CUDA(cudaMemcpyAsync(ring_dev + (int64_t)slots[i] * slot_stride + off, frames_host[i] + off,
+                             (size_t)((int64_t)(row1[i] - row0[i]) * pitch), cudaMemcpyHostToDevice, s));
+  }
+  return AF_OK;
 }
 
 af_status af_crop_pack(const af_frame_desc* frames_dev, const af_clip_geom* geom_dev, int32_t batch,

@@ -19,7 +19,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .crop import clip_geometry, get_crop_box
+from .crop import clip_geometry, clip_geometry_batch, get_crop_box
 
 
 # ------------------------------------------------------------------ score pooling / decisions (host)
@@ -184,16 +184,36 @@ class FrameRing:
         return slot
 
 
+    def put_rows(self, slots, host_ptrs, row0, row1, stream=None):
+        """Batched feed (af_ring_put_rows): rows [row0[i], row1[i]) of the pinned host frame at address host_ptrs[i]
+        -> ring slot slots[i], all queued on `stream` (a torch.cuda.Stream; default: the current one)."""
+        import ctypes as C
+        import torch
+        from ._lib import check, lib
+        n = len(slots)
+        sl = np.ascontiguousarray(slots, np.int32)
+        hp = np.ascontiguousarray(host_ptrs, np.uint64)
+        r0 = np.ascontiguousarray(row0, np.int32)
+        r1 = np.ascontiguousarray(row1, np.int32)
+        st = stream if stream is not None else torch.cuda.current_stream(self.buf.device)
+        with torch.cuda.device(self.buf.device):
+            check(lib().af_ring_put_rows(C.c_void_p(self.buf.data_ptr()), self.buf.stride(0), self.buf.stride(1), n,
+                                         C.c_void_p(sl.ctypes.data), C.c_void_p(hp.ctypes.data), C.c_void_p(r0.ctypes.data),
+                                         C.c_void_p(r1.ctypes.data), C.c_void_p(st.cuda_stream)), "af_ring_put_rows")
+
+
 def ring_descriptors(ring: FrameRing, clips: List[list], size: int = 224):
     """Descriptors (device arrays) for windows whose frames all live in `ring`."""
     from .crop import pack_descriptors_ring
-    slots, boxes, geoms = [], [], []
-    for win in clips:
-        bigs = np.stack([np.asarray(o[1]) for o in win])
-        lt, wh, diff, tfm, trans = clip_geometry(bigs, [o[2] for o in win], size)
-        slots += [o[0] for o in win]
-        boxes.append(bigs)
-        geoms.append((tfm, lt, wh))
+    slots = [o[0] for win in clips for o in win]
+    boxes = [np.stack([np.asarray(o[1]) for o in win]) for win in clips]
+    if len({len(win) for win in clips}) == 1:        # equal-length windows: one vectorised geometry pass
+        geoms = clip_geometry_batch(np.stack(boxes), np.stack([np.stack([o[2] for o in win]) for win in clips]), size)
+    else:
+        geoms = []
+        for win, bigs in zip(clips, boxes):
+            lt, wh, diff, tfm, trans = clip_geometry(bigs, [o[2] for o in win], size)
+            geoms.append((tfm, lt, wh))
     buf = ring.buf
     return pack_descriptors_ring(buf.data_ptr(), buf.stride(0), buf.stride(1), ring.h, ring.w, slots,
                                  np.concatenate(boxes), geoms, ring.engine.device)

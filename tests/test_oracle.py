@@ -198,3 +198,31 @@ def test_folded_weights_struct(state_dict):
     assert pools == [0, 0, 0, 1] + [0] * 12
     assert [fw.blocks[i].branch1 >= 0 for i in range(16)] == [True, False, False, True, False, False, False,
                                                               True, False, False, False, False, False, True, False, False]
+
+
+def test_vectorised_geometry_equals_the_per_clip_routines():
+    """get_crop_boxes / clip_geometry_batch (host side of a 32-clip step) == get_crop_box / clip_geometry clip by clip,
+    incl. a mirrored track (the reference's reflected-candidate branch, warp_for_xray.py:395-425)."""
+    H, W = 720, 1280
+    boxes, lms = [], []
+    for c in range(6):
+        track = afb200.synthetic.synthetic_track(40 + c)
+        det = np.stack([b for b, _ in track])
+        if c == 2:
+            det[:, [0, 2]] -= 900.0                       # runs off the left frame edge: clipping
+        bigs = afb200.get_crop_boxes((H, W), det, 0.5)
+        assert np.array_equal(bigs, np.stack([afb200.get_crop_box((H, W), b, 0.5) for b in det]))
+        lm = np.stack([l - big[:2][None] for (_, l), big in zip(track, bigs)])
+        if c == 4:                                        # mirror the face inside its box
+            lm = lm.copy()
+            lm[..., 0] = (bigs[:, 2] - bigs[:, 0])[:, None] - lm[..., 0]
+        boxes.append(bigs)
+        lms.append(lm)
+    geoms = afb200.clip_geometry_batch(np.stack(boxes), np.stack(lms), 224)
+    mirrored = 0
+    for c in range(6):
+        lt, wh, diff, tfm, trans = afb200.clip_geometry(boxes[c], lms[c], 224)
+        assert np.array_equal(lt, geoms[c][1]) and tuple(wh) == tuple(geoms[c][2])
+        assert np.abs(tfm - geoms[c][0]).max() <= 1e-12
+        mirrored += int(np.linalg.det(tfm[:, :2]) < 0)
+    assert mirrored == 1
