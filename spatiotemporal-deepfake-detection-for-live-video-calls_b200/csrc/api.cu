@@ -899,6 +899,11 @@ af_status af_set_global_option(const char* name, int64_t value) {
     conv_umma_force_block_n((int)value);
     return AF_OK;
   }
+  if (n == "pair") {
+    if (value < -1 || value > 1) { set_error("af_set_global_option: pair must be -1, 0 or 1"); return AF_ERR_INVALID; }
+    conv_umma_set_pair_mode((int)value);
+    return AF_OK;
+  }
   set_error("af_set_global_option: unknown option '%s'", name);
   return AF_ERR_INVALID;
 }

@@ -71,6 +71,7 @@ int conv_umma_launch(const ConvProblem& p, cudaStream_t s);
 int conv_umma_init();
 void conv_umma_timeline_dump(int n);
 void conv_umma_force_block_n(int bn);
+void conv_umma_set_pair_mode(int mode);
 // conv_rows.cu (row-halo tcgen05 kernel for Cout=64 layers with vertical taps)
 bool conv_rows_supported(const ConvProblem& p);
 int conv_rows_launch(const ConvProblem& p, cudaStream_t s);

@@ -97,14 +97,20 @@ __device__ __forceinline__ void stamp(const UmmaParams& p, int slot) {
   }
 }
 
-template <int BLOCK_N>
+// kPair: the CTA is one half of a 2-CTA cluster running cta_group::2 MMAs on 256-row tiles (see umma_ptx.cuh): it
+// loads its own 128 rows of A and HALF of every weight tile, the leader CTA issues the MMAs and commits to the
+// barriers of both CTAs, each CTA runs the epilogue of its own 128 accumulator rows.
+template <int BLOCK_N, bool kPair>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_r,
                  const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_b2,
                  const UmmaParams p) {
-  constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int B_ROWS = kPair ? BLOCK_N / 2 : BLOCK_N;      // weight rows this CTA stages
+  constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   constexpr int CHUNKS = BLOCK_N / 64;
   pdl_launch_dependents();
   if (threadIdx.x == 0) stamp(p, 0);
@@ -120,12 +126,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_full = tmem_empty + 2;                 // [4]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 4);
+  uint64_t* tmem_empty_peer = res_full + 4;            // [2] leader only: the peer CTA's epilogue has drained the accumulator
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_peer + 2);
 
   // warp index through a shuffle so the compiler knows it is warp-uniform (keeps the role loops'
   // address arithmetic in uniform registers: tcgen05/TMA operands must be uniform)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // pair mode: a tile is 256 rows (m tiles 2*mp, 2*mp+1) x BLOCK_N; an odd m-tile count leaves the last pair's
+  // second CTA with a tile that is entirely out of range (TMA zero-fills its loads and clips its stores)
+  const int num_tiles = (kPair ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
+  const int first_tile = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int cblocks = p.Cin / BLOCK_K;
   const int num_kb = p.kt * p.kh * p.kw * cblocks;
   const int num_kb_all = num_kb + p.cblocks2;        // primary taps, then the fused shortcut's channel blocks
@@ -141,15 +152,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], (CHUNKS >= 2 ? 2 : 1) * EPI_THREADS); }
     for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&tmem_empty_peer[i], 1);
     fence_barrier_init();
   } else if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                 "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                   "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                   "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();      // barrier inits visible to the peer before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   if (threadIdx.x == 0) stamp(p, 1);
@@ -162,10 +181,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
+        const int mp = tile / p.num_n_tiles, n_tile = tile - mp * p.num_n_tiles;
+        const int m_tile = kPair ? 2 * mp + (int)cta_rank : mp;
         const int m0 = m_tile * BLOCK_M;
-        const int n0 = n_tile * BLOCK_N;
+        const int n0 = n_tile * BLOCK_N + (kPair ? (int)cta_rank * B_ROWS : 0);      // this CTA's weight rows
         int r = m0;
         const int wo = r % p.Wo; r /= p.Wo;
         const int ho = r % p.Ho; r /= p.Ho;
@@ -178,20 +198,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           if (elect_one()) {
-            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            if (p.im2col) {
-              tma_load_im2col_5d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, wb, hb, tb, b, (uint16_t)dx, (uint16_t)dy,
-                                 (uint16_t)dt);
-            } else if (p.pool_t) {
-              // tile = (frame pair, 64-pixel block): rows 0..63 from frame 2j, rows 64..127 from frame 2j+1
-              const int ptiles = p.hw >> 6, pair = m_tile / ptiles, pt_ = m_tile - pair * ptiles;
-              const int r0 = pair * 2 * p.hw + pt_ * 64;
-              tma_load_2d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, r0);
-              tma_load_2d(sa + 64 * 128, &tm_a, &full_bar[stage], cb * BLOCK_K, r0 + p.hw);
+            if (kPair) {
+              // both CTAs' bytes are counted on the LEADER's full barrier, which alone is armed (for both)
+              const uint32_t fb = mapa_u32(&full_bar[stage], 0);
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+              if (p.im2col) {
+                tma_load_im2col_5d_pair(sa, &tm_a, fb, cb * BLOCK_K, wb, hb, tb, b, (uint16_t)dx, (uint16_t)dy, (uint16_t)dt);
+              } else if (p.pool_t) {
+                const int ptiles = p.hw >> 6, pair = m_tile / ptiles, pt_ = m_tile - pair * ptiles;
+                const int r0 = pair * 2 * p.hw + pt_ * 64;
+                tma_load_2d_pair(sa, &tm_a, fb, cb * BLOCK_K, r0);
+                tma_load_2d_pair(sa + 64 * 128, &tm_a, fb, cb * BLOCK_K, r0 + p.hw);
+              } else {
+                tma_load_2d_pair(sa, &tm_a, fb, cb * BLOCK_K, m0);
+              }
+              tma_load_2d_pair(sb, &tm_b, fb, cb * BLOCK_K, tap * p.Cout + n0);
             } else {
-              tma_load_2d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, m0);
+              mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+              if (p.im2col) {
+                tma_load_im2col_5d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, wb, hb, tb, b, (uint16_t)dx, (uint16_t)dy,
+                                   (uint16_t)dt);
+              } else if (p.pool_t) {
+                // tile = (frame pair, 64-pixel block): rows 0..63 from frame 2j, rows 64..127 from frame 2j+1
+                const int ptiles = p.hw >> 6, pair = m_tile / ptiles, pt_ = m_tile - pair * ptiles;
+                const int r0 = pair * 2 * p.hw + pt_ * 64;
+                tma_load_2d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, r0);
+                tma_load_2d(sa + 64 * 128, &tm_a, &full_bar[stage], cb * BLOCK_K, r0 + p.hw);
+              } else {
+                tma_load_2d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, m0);
+              }
+              tma_load_2d(sb, &tm_b, &full_bar[stage], cb * BLOCK_K, tap * p.Cout + n0);
             }
-            tma_load_2d(sb, &tm_b, &full_bar[stage], cb * BLOCK_K, tap * p.Cout + n0);
           }
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -206,12 +243,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           if (elect_one()) {
-            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            if (p.im2col2)
-              tma_load_im2col_5d(sa, &tm_a2, &full_bar[stage], cb2 * BLOCK_K, wo * p.sw2, ho * p.sh2, to, b, 0, 0, 0);
-            else
-              tma_load_2d(sa, &tm_a2, &full_bar[stage], cb2 * BLOCK_K, m0);
-            tma_load_2d(sb, &tm_b2, &full_bar[stage], cb2 * BLOCK_K, n0);
+            if (kPair) {
+              const uint32_t fb = mapa_u32(&full_bar[stage], 0);
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+              if (p.im2col2)
+                tma_load_im2col_5d_pair(sa, &tm_a2, fb, cb2 * BLOCK_K, wo * p.sw2, ho * p.sh2, to, b, 0, 0, 0);
+              else
+                tma_load_2d_pair(sa, &tm_a2, fb, cb2 * BLOCK_K, m0);
+              tma_load_2d_pair(sb, &tm_b2, fb, cb2 * BLOCK_K, n0);
+            } else {
+              mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+              if (p.im2col2)
+                tma_load_im2col_5d(sa, &tm_a2, &full_bar[stage], cb2 * BLOCK_K, wo * p.sw2, ho * p.sh2, to, b, 0, 0, 0);
+              else
+                tma_load_2d(sa, &tm_a2, &full_bar[stage], cb2 * BLOCK_K, m0);
+              tma_load_2d(sb, &tm_b2, &full_bar[stage], cb2 * BLOCK_K, n0);
+            }
           }
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -222,15 +269,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // ===================================================== MMA issuer
     // All 32 lanes walk the loop (uniform control flow, operands in uniform registers); one
     // elected lane issues the tcgen05 instructions.
-    {
-      constexpr uint32_t idesc = make_idesc(BLOCK_N);
+    if (kPair && !leader) {
+      // peer CTA: no MMAs to issue.  This warp relays "my epilogue has drained accumulator `as`" to the leader.
+      int it = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
+        mbar_wait(&tmem_empty[it & 1], (it >> 1) & 1);
+        if (lane == 0) mbar_arrive_remote(mapa_u32(&tmem_empty_peer[it & 1], 0));
+        __syncwarp();
+      }
+    } else {
+      constexpr uint32_t idesc = kPair ? make_idesc_mn(256, BLOCK_N) : make_idesc(BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
+        if (kPair) mbar_wait(&tmem_empty_peer[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int kb = 0; kb < num_kb_all; ++kb) {
@@ -244,14 +300,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the >>4 address field
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (kPair) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);        // frees the smem slot when these MMAs retire
+            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+            if (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           }
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
+        if (elect_one()) { if (kPair) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]); }   // accumulator complete -> epilogue(s)
         __syncwarp();
         if (lane == 0) stamp(p, 4);                     // (last tile's value survives)
       }
@@ -271,10 +329,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint64_t* res_bar = res_full + eg * 2;
 
     EpiIter<CHUNKS> cur, pre;
-    cur.init(blockIdx.x, gridDim.x, num_tiles, eg);
+    cur.init(first_tile, tile_stride, num_tiles, eg);
     pre = cur;
     auto issue_res = [&](const EpiIter<CHUNKS>& w, int slot) {
-      const int m_tile = w.tile / p.num_n_tiles, n_tile = w.tile - m_tile * p.num_n_tiles;
+      const int mp = w.tile / p.num_n_tiles, n_tile = w.tile - mp * p.num_n_tiles;
+      const int m_tile = kPair ? 2 * mp + (int)cta_rank : mp;
       mbar_expect_tx(&res_bar[slot], OUT_STAGE_BYTES);
       uint8_t* dst = res_g + slot * OUT_STAGE_BYTES;
       if (p.pool_t) {
@@ -299,7 +358,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       uint8_t* sout = out_g + (p.out_per_group == 2 ? slot : 0) * OUT_STAGE_BYTES;
       const uint8_t* sres = res_g + slot * OUT_STAGE_BYTES;
       if (cur.first_in_tile()) {
-        const int m_tile = cur.tile / p.num_n_tiles, n_tile = cur.tile - m_tile * p.num_n_tiles;
+        const int mp = cur.tile / p.num_n_tiles, n_tile = cur.tile - mp * p.num_n_tiles;
+        const int m_tile = kPair ? 2 * mp + (int)cta_rank : mp;
         m0 = p.pool_t ? (long long)m_tile * 64 : (long long)m_tile * BLOCK_M;   // pooled tiles are 64 rows
         n0 = n_tile * BLOCK_N;
         as = cur.it & 1;
@@ -378,10 +438,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();     // pair: neither CTA leaves while the other may still signal it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
   if (threadIdx.x == 0) stamp(p, 7);
 }
@@ -402,17 +463,18 @@ int g_driver_version = 0;
 bool g_corner_dhw = false;    // AFB200_IM2COL_CORNERS=dhw flips the corner array order (bring-up knob)
 
 int g_max_smem = 0;
+int g_pair_mode = -1;         // af_set_global_option("pair"): 0 never / 1 wherever possible / -1 planner's choice
 int g_force_block_n = 0;      // af_set_global_option("block_n"): 64 / 128 / 256 forces the tile width where Cout allows (tests)
 unsigned long long* g_timeline = nullptr;      // AFB200_TIMELINE=1
 struct TimelineInfo { int grid, tiles, kblocks, bn; };
 TimelineInfo g_timeline_info[256];
 long long g_timeline_n = 0;
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kPair>
 int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const CUtensorMap& tr,
              const CUtensorMap& ta2, const CUtensorMap& tb2, UmmaParams up, cudaStream_t s) {
   static bool configured[64] = {};            // the opt-in shared-memory size is a per-device function attribute
-  auto kern = conv_umma_kernel<BLOCK_N>;
+  auto kern = conv_umma_kernel<BLOCK_N, kPair>;
   int dev = 0;
   AFB_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !configured[dev]) {
@@ -420,24 +482,27 @@ int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   // shared-memory budget: residual layers trade operand stages for 4 residual + 4 output slots
-  const int stage_bytes = A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2;
+  const int stage_bytes = A_STAGE_BYTES + (kPair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
   const bool has_res = up.res != nullptr;
   up.out_per_group = BLOCK_N <= 128 ? 2 : 1;
   const int fixed = (2 * up.out_per_group + (has_res ? 4 : 0)) * OUT_STAGE_BYTES + 2 * BLOCK_N * 4 +
-                    (2 * MAX_STAGES + 8) * 8 + 16 + 1024;
+                    (2 * MAX_STAGES + 10) * 8 + 16 + 1024;
   int stages = (g_max_smem - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) { set_error("conv_umma: shared memory budget too small"); return AF_ERR_INVALID; }
   up.stages = stages;
   const int dyn = fixed + stages * stage_bytes;
-  const int tiles = up.num_m_tiles * up.num_n_tiles;
-  const int grid = limit_grid(tiles, g_num_sms);
+  // pair mode: tiles are 256 rows tall, one 2-CTA cluster (the two SMs of a TPC) per tile
+  const int tiles = (kPair ? (up.num_m_tiles + 1) / 2 : up.num_m_tiles) * up.num_n_tiles;
+  const int grid = kPair ? 2 * limit_grid(tiles, g_num_sms / 2) : limit_grid(tiles, g_num_sms);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = kPair ? 2 : 1;
   up.dbg = nullptr;
   if (g_timeline) {                      // ring of 256 launches x 8 stamps, dumped by conv_umma_timeline_dump()
     up.dbg = g_timeline + (size_t)(g_timeline_n % 256) * 8;
@@ -496,6 +561,7 @@ int encode_im2col(CUtensorMap* map, const void* x, int B, int Ti, int Hi, int Wi
 }  // namespace
 
 void conv_umma_force_block_n(int bn) { g_force_block_n = bn; }
+void conv_umma_set_pair_mode(int mode) { g_pair_mode = mode; }
 
 int conv_umma_init() {
   if (g_encode_tiled && g_encode_im2col) return AF_OK;
@@ -572,10 +638,11 @@ struct UmmaPlan {
   alignas(64) CUtensorMap ta, tb, ty, tr, ta2, tb2;
   UmmaParams up;
   int bn;
+  int pair;      // 2-CTA clusters, cta_group::2 MMAs (weight tiles split between the CTAs of a pair)
 };
 struct PlanKey {
   const void *x, *w, *y, *res, *x2, *w2; const float* bias;
-  int v[27];
+  int v[28];
   bool operator==(const PlanKey& o) const { return memcmp(this, &o, sizeof(PlanKey)) == 0; }
 };
 struct PlanKeyHash {
@@ -595,7 +662,7 @@ int conv_umma_launch(const ConvProblem& p, cudaStream_t s) {
   PlanKey key;
   memset(&key, 0, sizeof(key));
   key.x = p.x; key.w = p.w; key.y = p.y; key.res = p.res; key.bias = p.bias; key.x2 = p.x2; key.w2 = p.w2;
-  const int vals[27] = {g_force_block_n, p.B, p.Ti, p.Hi, p.Wi, p.Cin, p.To, p.Ho, p.Wo, p.Cout, p.kt, p.kh, p.kw, p.st, p.sh, p.sw,
+  const int vals[28] = {g_pair_mode, g_force_block_n, p.B, p.Ti, p.Hi, p.Wi, p.Cin, p.To, p.Ho, p.Wo, p.Cout, p.kt, p.kh, p.kw, p.st, p.sh, p.sw,
                         p.pt, p.ph, p.pw, p.relu, p.pool_t, p.Cin2, p.T2, p.H2, p.W2, p.sh2, p.sw2};
   memcpy(key.v, vals, sizeof(vals));
   auto it = g_plans.find(key);
@@ -607,10 +674,14 @@ int conv_umma_launch(const ConvProblem& p, cudaStream_t s) {
     it = g_plans.emplace(key, plan).first;
   }
   const UmmaPlan& pl = it->second;
+  if (pl.pair) {
+    if (pl.bn == 256) return launch_t<256, true>(pl.ta, pl.tb, pl.ty, pl.tr, pl.ta2, pl.tb2, pl.up, s);
+    return launch_t<128, true>(pl.ta, pl.tb, pl.ty, pl.tr, pl.ta2, pl.tb2, pl.up, s);
+  }
   switch (pl.bn) {
-    case 256: return launch_t<256>(pl.ta, pl.tb, pl.ty, pl.tr, pl.ta2, pl.tb2, pl.up, s);
-    case 128: return launch_t<128>(pl.ta, pl.tb, pl.ty, pl.tr, pl.ta2, pl.tb2, pl.up, s);
-    default: return launch_t<64>(pl.ta, pl.tb, pl.ty, pl.tr, pl.ta2, pl.tb2, pl.up, s);
+    case 256: return launch_t<256, false>(pl.ta, pl.tb, pl.ty, pl.tr, pl.ta2, pl.tb2, pl.up, s);
+    case 128: return launch_t<128, false>(pl.ta, pl.tb, pl.ty, pl.tr, pl.ta2, pl.tb2, pl.up, s);
+    default: return launch_t<64, false>(pl.ta, pl.tb, pl.ty, pl.tr, pl.ta2, pl.tb2, pl.up, s);
   }
 }
 
@@ -644,6 +715,12 @@ int build_plan(const ConvProblem& p, UmmaPlan& plan) {
   int force_bn = g_force_block_n ? g_force_block_n : (fbn ? atoi(fbn) : 0);
   if ((force_bn == 64 || force_bn == 128 || force_bn == 256) && p.Cout % force_bn == 0) bn = force_bn;
   up.num_n_tiles = p.Cout / bn;
+  // CTA pairs wherever the weight tile can be split in two halves of >= 64 rows (g_pair_mode: 0 never, 1 always,
+  // -1 planner's choice)
+  static const char* fpair = getenv("AFB200_PAIR");
+  const int pair_mode = g_pair_mode >= 0 ? g_pair_mode : (fpair ? atoi(fpair) : -1);
+  plan.pair = (bn >= 128 && g_num_sms >= 2 && pair_mode != 0) ? 1 : 0;
+  const uint32_t b_box_rows = (uint32_t)(plan.pair ? bn / 2 : bn);
 
   if (up.im2col) {
     int rc = encode_im2col(&ta, p.x, p.B, p.Ti, p.Hi, p.Wi, p.Cin, p.kt, p.kh, p.kw, p.st, p.sh, p.sw, p.pt, p.ph, p.pw);
@@ -653,7 +730,7 @@ int build_plan(const ConvProblem& p, UmmaPlan& plan) {
     if (rc) return rc;
   }
   const int taps = p.kt * p.kh * p.kw;
-  int rc = encode_2d(&tb, p.w, (uint64_t)taps * p.Cout, (uint64_t)p.Cin, (uint32_t)bn, "W");
+  int rc = encode_2d(&tb, p.w, (uint64_t)taps * p.Cout, (uint64_t)p.Cin, b_box_rows, "W");
   if (rc) return rc;
   if (p.pool_t) {       // pooled output has M/2 rows; every box is 64 rows tall
     rc = encode_2d(&ty, p.y, (uint64_t)p.M / 2, (uint64_t)p.Cout, 64, "Y(pooled)");
@@ -677,7 +754,7 @@ int build_plan(const ConvProblem& p, UmmaPlan& plan) {
     if (up.im2col2) rc = encode_im2col(&plan.ta2, p.x2, p.B, p.T2, p.H2, p.W2, p.Cin2, 1, 1, 1, 1, p.sh2, p.sw2, 0, 0, 0);
     else rc = encode_2d(&plan.ta2, p.x2, (uint64_t)p.M, (uint64_t)p.Cin2, BLOCK_M, "A2");
     if (rc) return rc;
-    rc = encode_2d(&plan.tb2, p.w2, (uint64_t)p.Cout, (uint64_t)p.Cin2, (uint32_t)bn, "W2");
+    rc = encode_2d(&plan.tb2, p.w2, (uint64_t)p.Cout, (uint64_t)p.Cin2, b_box_rows, "W2");
     if (rc) return rc;
   }
 

@@ -125,9 +125,11 @@ def test_stem_kernel_elementwise_incl_tile_borders(dev, case):
     want = _stem_reference(x4, w, b)
     got = afb200.stem_pool_ndhwc4(x4, w, b, per_frame_kernel=per_frame).float().cpu()
     assert got.shape == want.shape == (B, T, S // 4, S // 4, 64)
-    tol = 2.0 ** -8 * max(1.0, want.abs().max().item()) + 1e-3
+    # one bf16 ulp at the largest value (accumulation order may flip a rounding): 2^-7 relative
+    tol = 2.0 ** -7 * max(1.0, want.abs().max().item()) + 1e-3
     diff = (got - want).abs()
     assert diff.max().item() <= tol, (diff.max().item(), tol)
+    assert (diff > 2.0 ** -8 * want.abs().clamp_min(1.0) + 1e-3).float().mean().item() < 1e-3      # and only rarely that much
     # pooled windows that straddle a tile border (conv-output tiles are 8 wide x 16 tall: pooled column 4k reads
     # conv columns 8k-1..8k+1, pooled row 8k reads conv rows 16k-1..16k+1) are merged with red.global.max from two
     # or four CTAs: check them on their own, and check that they are not trivially zero
@@ -160,7 +162,7 @@ def test_stem_kernel_inside_the_engine_matches_standalone(dev, state_dict):
     y = afb200.stem_pool_ndhwc4(x4, w, b).float().cpu().permute(0, 4, 1, 2, 3)
     assert torch.equal(s1, y)
     want = _stem_reference(x4, w, b).permute(0, 4, 1, 2, 3)
-    tol = 2.0 ** -8 * max(1.0, want.abs().max().item()) + 1e-3
+    tol = 2.0 ** -7 * max(1.0, want.abs().max().item()) + 1e-3      # one bf16 ulp
     assert (s1 - want).abs().max().item() <= tol
     eng.close()
 
@@ -243,7 +245,7 @@ def test_crop_pack_equals_crop_u8_then_pack_lines(dev):
         geoms.append((tfm, lt, wh))
     u8 = afb200.crop.crop_u8(frames, boxes, geoms, 32, 224).cpu().numpy()
     want = synthetic.normalise_clip(u8)                          # the callers' pack lines, fp32 on the CPU
-    mean255, std255 = afb200.mean_std_255("demo")
+    mean255, std255 = afb200.mean_std_255("svc")             # float32(mean) * 255 in fp32, as normalise_clip / TEST2.py:147-148
     got = afb200.crop.crop_pack(frames, boxes, geoms, 32, 224, mean255, std255, dtype=torch.float32)
     assert got.is_contiguous() and torch.equal(got.cpu(), want)
     # channels_last_3d destination (TEST2.py:155) and a permuted NTHWC buffer (demo.py:317)
