@@ -172,16 +172,43 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   if (threadIdx.x == 0) stamp(p, 1);
-  pdl_wait_prior_grid();      // everything above overlapped the previous kernel's tail
+  // everything above overlapped the previous kernel's tail; the producer warp additionally starts fetching WEIGHTS
+  // (never written by a kernel) before it waits for the prior grid
+  if (warp != 0) pdl_wait_prior_grid();
   if (threadIdx.x == 0) stamp(p, 2);
 
   if (warp == 0) {
     // ===================================================== TMA producer (all lanes walk the loop,
     // one elected lane issues; see the MMA warp for why)
     {
+      // weight tiles of the first tile's first `pre` k-blocks: issued before griddepcontrol.wait, so their HBM / L2
+      // latency (the longest of the first operands: nothing has touched these bytes since the previous pass) overlaps
+      // the predecessor's drain.  The stage's barrier is armed here for the whole stage (A arrives later).
+      int pre = 0;
+      if (first_tile < num_tiles) {
+        pre = stages < num_kb ? stages : num_kb;
+        const int n_tile0 = first_tile % p.num_n_tiles;
+        const int n00 = n_tile0 * BLOCK_N + (kPair ? (int)cta_rank * B_ROWS : 0);
+        if (elect_one()) {
+          for (int kb = 0; kb < pre; ++kb) {
+            uint8_t* sb = smem + kb * STAGE_BYTES + A_STAGE_BYTES;
+            const int tap0 = kb / cblocks, cb0 = kb - tap0 * cblocks;
+            if (kPair) {
+              if (leader) mbar_expect_tx(&full_bar[kb], 2 * STAGE_BYTES);
+              tma_load_2d_pair(sb, &tm_b, mapa_u32(&full_bar[kb], 0), cb0 * BLOCK_K, tap0 * p.Cout + n00);
+            } else {
+              mbar_expect_tx(&full_bar[kb], STAGE_BYTES);
+              tma_load_2d(sb, &tm_b, &full_bar[kb], cb0 * BLOCK_K, tap0 * p.Cout + n00);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      pdl_wait_prior_grid();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
+        const bool w_ahead = tile == first_tile;      // this tile's first `pre` weight tiles are already in flight
         const int mp = tile / p.num_n_tiles, n_tile = tile - mp * p.num_n_tiles;
         const int m_tile = kPair ? 2 * mp + (int)cta_rank : mp;
         const int m0 = m_tile * BLOCK_M;
@@ -201,7 +228,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (kPair) {
               // both CTAs' bytes are counted on the LEADER's full barrier, which alone is armed (for both)
               const uint32_t fb = mapa_u32(&full_bar[stage], 0);
-              if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+              const bool have_w = w_ahead && kb < pre;
+              if (leader && !have_w) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
               if (p.im2col) {
                 tma_load_im2col_5d_pair(sa, &tm_a, fb, cb * BLOCK_K, wb, hb, tb, b, (uint16_t)dx, (uint16_t)dy, (uint16_t)dt);
               } else if (p.pool_t) {
@@ -212,9 +240,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               } else {
                 tma_load_2d_pair(sa, &tm_a, fb, cb * BLOCK_K, m0);
               }
-              tma_load_2d_pair(sb, &tm_b, fb, cb * BLOCK_K, tap * p.Cout + n0);
+              if (!have_w) tma_load_2d_pair(sb, &tm_b, fb, cb * BLOCK_K, tap * p.Cout + n0);
             } else {
-              mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+              const bool have_w = w_ahead && kb < pre;
+              if (!have_w) mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
               if (p.im2col) {
                 tma_load_im2col_5d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, wb, hb, tb, b, (uint16_t)dx, (uint16_t)dy,
                                    (uint16_t)dt);
@@ -227,7 +256,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               } else {
                 tma_load_2d(sa, &tm_a, &full_bar[stage], cb * BLOCK_K, m0);
               }
-              tma_load_2d(sb, &tm_b, &full_bar[stage], cb * BLOCK_K, tap * p.Cout + n0);
+              if (!have_w) tma_load_2d(sb, &tm_b, &full_bar[stage], cb * BLOCK_K, tap * p.Cout + n0);
             }
           }
           __syncwarp();
@@ -719,7 +748,9 @@ int build_plan(const ConvProblem& p, UmmaPlan& plan) {
   // -1 planner's choice)
   static const char* fpair = getenv("AFB200_PAIR");
   const int pair_mode = g_pair_mode >= 0 ? g_pair_mode : (fpair ? atoi(fpair) : -1);
-  plan.pair = (bn >= 128 && g_num_sms >= 2 && pair_mode != 0) ? 1 : 0;
+  // (measured on B200, 32 clips: pairs gain 5-20 % on every K >= 256 layer; the K <= 128 HBM streams of s2 lose 10 %)
+  const int k_total = p.kt * p.kh * p.kw * p.Cin + (p.x2 ? p.Cin2 : 0);
+  plan.pair = (bn >= 128 && g_num_sms >= 2 && pair_mode != 0 && (pair_mode == 1 || k_total > 128)) ? 1 : 0;
   const uint32_t b_box_rows = (uint32_t)(plan.pair ? bn / 2 : bn);
 
   if (up.im2col) {

@@ -7,7 +7,7 @@ from afb200 import synthetic
 import bench
 dev = torch.device("cuda", 0)
 eng = afb200.Engine(synthetic.synthetic_state_dict(0), max_batch=32, precision="bf16")
-pool, fd, cg, _ = bench.build_gpu_inputs(dev, 2, 0)
+pool, fd, cg, _, _ = bench.build_gpu_inputs(dev, 2, 0)
 fd1, cg1 = fd[: 32 * 40].contiguous(), cg[:64].contiguous()
 for _ in range(10):
     eng.crop_infer(fd1, cg1, 1)
