@@ -264,6 +264,13 @@ af_status af_conv_shortcut_ndhwc(const void* x_dev, const af_conv_desc* conv_hos
 af_status af_stem_pool_ndhwc4(const void* clip_dev, const af_conv_desc* stem_host, void* y_dev, int32_t batch,
                               int32_t t, int32_t s, int32_t per_frame_kernel, void* stream);
 
+/* Test/diagnostic entry: the fused tail of an s2 bottleneck block (conv_bc_fused.cu),
+ *   y = relu(c(relu(b(x))) + residual)   with b = 1x3x3 64->64 (+folded BN), c = 1x1x1 64->256 (+folded BN)
+ * (resnet_helper.py:311-326,438-444) on bf16 NDHWC device tensors: x [B,T,H,W,64], residual / y [B,T,H,W,256]. */
+af_status af_conv_bc_fused_ndhwc(const void* x_dev, const af_conv_desc* conv_b_host, const af_conv_desc* conv_c_host,
+                                 const void* residual_dev, void* y_dev, int32_t batch, int32_t t, int32_t hgt,
+                                 int32_t wid, void* stream);
+
 /* Copy intermediate activations of the LAST af_forward/af_infer call out for stage
  * parity tests: which = 1..5 (s1..s5 outputs) as fp32 NCTHW [B,C,T,H,W] into out_dev.
  * Requires option "keep_stages" = 1 (costs extra memory). */

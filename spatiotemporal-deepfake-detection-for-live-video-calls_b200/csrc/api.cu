@@ -256,9 +256,9 @@ struct ProfRec {
 // both folded biases pre-summed in `bias`.
 struct FusedShortcut { const ConvLayer* L; const void* x; Dims in; const float* bias; };
 
-static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, long long xsB, long long xsT,
-                    long long xsH, long long xsW, int B, const void* res, void* y, bool relu, cudaStream_t s,
-                    int impl_override = -1, int pool_hw = 0, int pool_t = 0, const FusedShortcut* sc = nullptr) {
+static ConvProblem make_problem(const ConvLayer& L, const void* x, Dims in, long long xsB, long long xsT, long long xsH,
+                                long long xsW, int B, const void* res, void* y, bool relu, int pool_hw, int pool_t,
+                                const FusedShortcut* sc) {
   ConvProblem p;
   p.x = x; p.bias = sc ? sc->bias : L.bias; p.res = res; p.y = y;
   if (sc) {
@@ -275,6 +275,45 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
   p.M = (long long)B * o.T * o.H * o.W;
   p.pool_hw = pool_hw;
   p.pool_t = pool_t;
+  p.w = L.w_umma;
+  return p;
+}
+
+static ConvProblem dense_problem(const ConvLayer& L, const void* x, Dims in, int B, const void* res, void* y, bool relu) {
+  const long long sW = in.C, sH = (long long)in.W * in.C, sT = sH * in.H, sB = sT * in.T;
+  return make_problem(L, x, in, sB, sT, sH, sW, B, res, y, relu, 0, 0, nullptr);
+}
+
+// The `b` -> `c` tail of an s2-shaped bottleneck block in one kernel (conv_bc_fused.cu) when the shapes allow it.
+// Returns 1 if it ran, 0 if the caller should run the two convs separately, < 0 on error.
+static int try_fused_bc(af_engine* e, const ConvLayer& Lb, const ConvLayer& Lc, const void* xb, Dims db_in, int B,
+                        const void* res, void* y, cudaStream_t s) {
+  static const bool off = getenv("AFB200_NO_FUSED_BC") != nullptr;
+  if (off || !Lb.w_umma || !Lc.w_umma) return 0;
+  const ConvProblem pb = dense_problem(Lb, xb, db_in, B, nullptr, nullptr, true);
+  const Dims dmid = conv_out(Lb, db_in);
+  const ConvProblem pc = dense_problem(Lc, nullptr, dmid, B, res, y, true);
+  if (!conv_bc_fused_supported(pb, pc)) return 0;
+  OpTrace tr(s);
+  ProfRec prec(e, s);
+  int rc = conv_bc_fused_launch(pb, pc, s);
+  if (rc) return rc;
+  const double flops = 2.0 * (double)pb.M * (Lb.cout * 9.0 * Lb.cin_p + (double)Lc.cout * Lc.cin_p);
+  const double bytes = ((double)pb.M * (Lb.cin_p + 2.0 * Lc.cout) + 9.0 * Lb.cin_p * Lb.cout + (double)Lc.cin_p * Lc.cout) * 2.0;
+  prec.done(flops >= (e ? e->ridge_flop_per_byte : 208.0) * bytes ? 0 : 2, flops, bytes);
+  if (OpTrace::enabled()) {
+    char nm[128];
+    snprintf(nm, sizeof(nm), "conv fused b k1x3x3 + c k1x1x1 M=%lld N=%d->%d +res", pb.M, Lb.cout, Lc.cout);
+    tr.done(nm, flops, bytes);
+  }
+  return 1;
+}
+
+static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, long long xsB, long long xsT,
+                    long long xsH, long long xsW, int B, const void* res, void* y, bool relu, cudaStream_t s,
+                    int impl_override = -1, int pool_hw = 0, int pool_t = 0, const FusedShortcut* sc = nullptr) {
+  ConvProblem p = make_problem(L, x, in, xsB, xsT, xsH, xsW, B, res, y, relu, pool_hw, pool_t, sc);
+  Dims o = conv_out(L, in);
   const bool is_bf16 = e ? e->is_bf16 : (L.w_umma != nullptr);
   const int impl = impl_override >= 0 ? impl_override : (e ? e->conv_impl : 0);
   OpTrace tr(s);
@@ -397,9 +436,31 @@ static int run_blocks(af_engine* e, int b_begin, int b_end, const void*& x, Dims
     int rc = dense_conv(e, blk.a, x, d, B, nullptr, ya, true, s);
     if (rc) return rc;
     Dims da = conv_out(e->convs[blk.a], d);
+    Dims db = conv_out(e->convs[blk.b], da);
+    // fuse the next block's temporal max-pool into this `c` conv's epilogue when possible
+    static const bool no_tfuse = getenv("AFB200_NO_FUSED_TPOOL") != nullptr;
+    const ConvLayer& Lc = e->convs[blk.c];
+    const bool fuse_t = e->is_bf16 && e->conv_impl == 0 && !e->keep_stages && !no_tfuse && !fsc.L && !blk.spatial_pool &&
+                        bi + 1 < (int)e->blocks.size() &&
+                        e->blocks[bi + 1].temporal_pool_before && (db.T % 2 == 0) && ((db.H * db.W) % 64 == 0) &&
+                        Lc.kt == 1 && Lc.kh == 1 && Lc.kw == 1 && Lc.sh == 1 && Lc.sw == 1 && Lc.st == 1;
+    // identity-residual blocks of s2: `b` and `c` (+residual) as ONE kernel (conv_bc_fused.cu)
+    if (e->is_bf16 && e->conv_impl == 0 && shortcut != nullptr && !fsc.L && !blk.spatial_pool && !fuse_t) {
+      rc = try_fused_bc(e, e->convs[blk.b], Lc, ya, da, B, shortcut, yout, s);
+      if (rc < 0) return rc;
+      if (rc == 1) {
+        d = conv_out(Lc, db);
+        x = yout;
+        if (is_stage_end(e, bi)) {
+          rc = keep_stage(e, stage_no, x, d, clip0, B, s);
+          if (rc) return rc;
+          ++stage_no;
+        }
+        continue;
+      }
+    }
     rc = dense_conv(e, blk.b, ya, da, B, nullptr, yb, true, s);
     if (rc) return rc;
-    Dims db = conv_out(e->convs[blk.b], da);
     if (blk.spatial_pool) {
       // FTCN-TT: MaxPool3d((1,2,2)) behind b_bn and branch1_bn (ReLU and max commute, so the conv epilogue's
       // ReLU stays where it is).  `ya` is dead after conv b and `yb` after its pooling, so they take the pooled maps.
@@ -418,12 +479,6 @@ static int run_blocks(af_engine* e, int b_begin, int b_end, const void*& x, Dims
       }
       void* t0 = ya; ya = yb; yb = t0;             // from here on `yb` names the pooled b output
     }
-    // fuse the next block's temporal max-pool into this `c` conv's epilogue when possible
-    static const bool no_tfuse = getenv("AFB200_NO_FUSED_TPOOL") != nullptr;
-    const ConvLayer& Lc = e->convs[blk.c];
-    const bool fuse_t = e->is_bf16 && e->conv_impl == 0 && !e->keep_stages && !no_tfuse && !fsc.L && bi + 1 < (int)e->blocks.size() &&
-                        e->blocks[bi + 1].temporal_pool_before && (db.T % 2 == 0) && ((db.H * db.W) % 64 == 0) &&
-                        Lc.kt == 1 && Lc.kh == 1 && Lc.kw == 1 && Lc.sh == 1 && Lc.sw == 1 && Lc.st == 1;
     {
       const long long sW = db.C, sH = (long long)db.W * db.C, sT = sH * db.H, sB = sT * db.T;
       rc = run_conv(e, Lc, yb, db, sB, sT, sH, sW, B, shortcut, yout, true, s, -1, 0, fuse_t ? 1 : 0,
@@ -758,6 +813,7 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
     int rc = conv_umma_init();
     if (!rc) rc = conv_rows_init();
     if (!rc) rc = conv_tsweep_init();
+    if (!rc) rc = conv_bc_fused_init();
     if (rc) return (af_status)rc;
   }
   e->convs.resize(w->n_convs);
@@ -1291,6 +1347,39 @@ af_status af_stem_pool_ndhwc4(const void* clip_dev, const af_conv_desc* stem_hos
   if (w35) cudaFree(w35);
   if (bias) cudaFree(bias);
   if (padded) cudaFree(padded);
+  return (af_status)rc;
+}
+
+af_status af_conv_bc_fused_ndhwc(const void* x_dev, const af_conv_desc* conv_b_host, const af_conv_desc* conv_c_host,
+                                 const void* residual_dev, void* y_dev, int32_t batch, int32_t t, int32_t hgt, int32_t wid,
+                                 void* stream) {
+  if (!x_dev || !conv_b_host || !conv_c_host || !residual_dev || !y_dev || batch <= 0) {
+    set_error("af_conv_bc_fused_ndhwc: invalid arguments");
+    return AF_ERR_INVALID;
+  }
+  int rc = conv_umma_init();
+  if (!rc) rc = conv_bc_fused_init();
+  if (rc) return (af_status)rc;
+  ConvLayer Lb, Lc;
+  rc = upload_layer(*conv_b_host, true, Lb);
+  if (!rc) rc = upload_layer(*conv_c_host, true, Lc);
+  if (!rc) {
+    const Dims in = {t, hgt, wid, Lb.cin_p};
+    const ConvProblem pb = dense_problem(Lb, x_dev, in, batch, nullptr, nullptr, true);
+    const ConvProblem pc = dense_problem(Lc, nullptr, conv_out(Lb, in), batch, residual_dev, y_dev, true);
+    if (!conv_bc_fused_supported(pb, pc)) {
+      set_error("af_conv_bc_fused_ndhwc: takes b = 1x3x3 s1 p[0,1,1] 64->64, c = 1x1x1 64->256, width %% 8 == 0");
+      rc = AF_ERR_INVALID;
+    } else {
+      rc = conv_bc_fused_launch(pb, pc, (cudaStream_t)stream);
+    }
+    if (!rc && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+      set_error("af_conv_bc_fused_ndhwc: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = AF_ERR_CUDA;
+    }
+  }
+  free_layer(Lb);
+  free_layer(Lc);
   return (af_status)rc;
 }
 

@@ -82,6 +82,10 @@ int conv_tsweep_launch(const ConvProblem& p, cudaStream_t s);
 int conv_tsweep_init();
 int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const void* w35, const float* bias, void* y,
                             int pool, cudaStream_t s, int force_per_frame = 0);
+// conv_bc_fused.cu (s2 bottleneck tail: 1x3x3 64->64 + ReLU, then 1x1x1 64->256 + residual + ReLU, one kernel)
+bool conv_bc_fused_supported(const ConvProblem& b, const ConvProblem& c);
+int conv_bc_fused_launch(const ConvProblem& b, const ConvProblem& c, cudaStream_t s);
+int conv_bc_fused_init();
 // pool_head.cu
 int maxpool_spatial_launch(const void* x, void* y, int B, int T, int H, int W, int C, bool is_bf16,
                            cudaStream_t s);   // k[1,3,3] s[1,2,2] p[0,1,1]

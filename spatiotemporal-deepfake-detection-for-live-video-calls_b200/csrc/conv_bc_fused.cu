@@ -1,0 +1,421 @@
+// K2d: the `b` -> `c` tail of an s2 bottleneck block in ONE kernel:
+//     y = relu( W_c . relu( conv1x3x3(x; W_b) + bias_b ) + bias_c + residual )
+// (BottleneckTransform.forward b, b_bn, b_relu, c, c_bn and ResBlock.forward's add + ReLU:
+//  altfreezing/slowfast/models/resnet_helper.py:311-326,438-444; BN folded by the host.)
+//
+// Why: in s2 (56x56 maps, 64 -> 64 -> 256 channels) the 1x3x3 conv is tensor-pipe bound (N = 64 caps it at the
+// shared-memory operand read rate) and the 1x1x1 conv is an HBM stream (51 MB residual in, 51 MB out per clip).  As two
+// kernels they run back to back; fused, the `b` MMAs run underneath the `c` epilogue's HBM traffic and the 64-channel
+// intermediate (12.8 MB per clip, written and read back) never leaves the SM.
+//
+// Work unit: one 8-wide x 16-tall output tile (128 pixels) of one frame.
+//   warp 0      TMA producer: the three dx-shifted 18-row halo boxes of the tile (the kh = 3 vertical taps are views of
+//               one box, as in conv_rows.cu); W_b (9 x 64 x 64) and W_c (256 x 64) are loaded once and stay resident
+//   warp 1      MMA issuer: b(i) -> acc_b[i & 1] (128 x 64 fp32, TMEM), then c(i-1): Yb(i-1) [128 x 64 bf16, smem] x W_c^T
+//               -> acc_c (128 x 256): c of a tile is issued AFTER b of the next one so the first epilogue hides behind it
+//   warps 2-5   epilogue 1: acc_b -> +bias_b, ReLU, bf16 -> Yb in the K-major SWIZZLE_128B layout the c MMA reads
+//   warps 6-13  epilogue 2 (two warpgroups on alternate 64-channel chunks): acc_c -> +bias_c +residual -> ReLU -> bf16,
+//               IN PLACE in the slot the residual tile was TMA-loaded into, then a TMA store from that slot
+// TMEM: acc_b x2 (128 columns) + acc_c (256 columns).  Shared memory: 72 + 32 KB weights, 2 x 18 KB halo ring, 16 KB Yb,
+// 4 x 16 KB residual/output slots = 222.5 KB.
+#include <cuda.h>
+
+#include "../../include/afb200.h"
+#include "common.cuh"
+#include "umma_ptx.cuh"
+
+namespace afb {
+namespace {
+
+constexpr int FX = 8, FR = 16;                  // tile: 8 columns x 16 rows
+constexpr int F_MID = 64, F_OUT = 256;          // channels: b 64 -> 64, c 64 -> 256
+constexpr int F_THREADS = 32 * 14;
+constexpr int F_A_STAGES = 2;
+constexpr int F_A_BYTES = (FR + 2) * FX * 128;  // 18 rows x 8 pixels x 64 bf16
+constexpr int F_WB_BYTES = 9 * F_MID * 128;
+constexpr int F_WC_BYTES = F_OUT * 128;
+constexpr int F_TILE_BYTES = 128 * 128;         // 128 pixels x 64 channels bf16
+constexpr int F_SMEM = F_WB_BYTES + F_WC_BYTES + F_A_STAGES * F_A_BYTES + F_TILE_BYTES + 4 * F_TILE_BYTES +
+                       (F_MID + F_OUT) * 4 + 32 * 8 + 16 + 1024;
+
+struct FusedParams {
+  const float* bias_b;
+  const float* bias_c;
+  int x_tiles, y_tiles, frames;     // tiles per row / column of a frame, B*T frames
+  int num_tiles;
+};
+
+__device__ __forceinline__ void f_tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                              int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+      "%7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void f_tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void f_tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)m),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// named barrier among the 128 threads of one warpgroup (ids 1..3; 0 is __syncthreads)
+__device__ __forceinline__ void wg_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(F_THREADS, 1)
+conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_wb,
+                     const __grid_constant__ CUtensorMap tm_wc, const __grid_constant__ CUtensorMap tm_r,
+                     const __grid_constant__ CUtensorMap tm_y, const FusedParams p) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_wb = smem;
+  uint8_t* smem_wc = smem_wb + F_WB_BYTES;
+  uint8_t* smem_a = smem_wc + F_WC_BYTES;
+  uint8_t* smem_yb = smem_a + F_A_STAGES * F_A_BYTES;
+  uint8_t* smem_slot = smem_yb + F_TILE_BYTES;                 // [2 groups][2 slots] x 16 KB
+  float* bias_b_s = reinterpret_cast<float*>(smem_slot + 4 * F_TILE_BYTES);
+  float* bias_c_s = bias_b_s + F_MID;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(bias_c_s + F_OUT);
+  uint64_t* a_empty = a_full + F_A_STAGES;
+  uint64_t* w_full = a_empty + F_A_STAGES;
+  uint64_t* accb_full = w_full + 1;       // [2]
+  uint64_t* accb_empty = accb_full + 2;   // [2]
+  uint64_t* yb_full = accb_empty + 2;
+  uint64_t* yb_empty = yb_full + 1;
+  uint64_t* accc_full = yb_empty + 1;
+  uint64_t* accc_empty = accc_full + 1;
+  uint64_t* res_full = accc_empty + 1;    // [2 groups][2 slots]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 4);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t ACCC_COL = 2 * F_MID;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_wb);
+    tma_prefetch_desc(&tm_wc);
+    tma_prefetch_desc(&tm_r);
+    tma_prefetch_desc(&tm_y);
+    for (int i = 0; i < F_A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&accb_full[i], 1); mbar_init(&accb_empty[i], 128); }
+    mbar_init(yb_full, 128);
+    mbar_init(yb_empty, 1);
+    mbar_init(accc_full, 1);
+    mbar_init(accc_empty, 256);
+    for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
+    fence_barrier_init();
+  } else if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < F_MID + F_OUT; i += F_THREADS)
+    bias_b_s[i] = i < F_MID ? __ldg(p.bias_b + i) : __ldg(p.bias_c + i - F_MID);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (elect_one()) {                            // weights are constants: no need to wait for the prior grid
+      mbar_expect_tx(w_full, F_WB_BYTES + F_WC_BYTES);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(smem_wb + tap * (F_MID * 128), &tm_wb, w_full, 0, tap * F_MID);
+      tma_load_2d(smem_wc, &tm_wc, w_full, 0, 0);
+    }
+    __syncwarp();
+    pdl_wait_prior_grid();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int r = tile;
+      const int xt = r % p.x_tiles; r /= p.x_tiles;
+      const int yt = r % p.y_tiles; r /= p.y_tiles;       // r = frame index b*T + t
+      for (int dx = 0; dx < 3; ++dx) {
+        mbar_wait(&a_empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[stage], F_A_BYTES);
+          // padding 1 on every side comes from TMA out-of-bounds zero fill
+          f_tma_load_5d(smem_a + stage * F_A_BYTES, &tm_a, &a_full[stage], 0, xt * FX + dx - 1, yt * FR - 1, r, 0);
+        }
+        __syncwarp();
+        if (++stage == F_A_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    constexpr uint32_t idesc_b = make_idesc(F_MID), idesc_c = make_idesc(F_OUT);
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    const uint32_t wb_addr = smem_u32(smem_wb), wc_addr = smem_u32(smem_wc), yb_addr = smem_u32(smem_yb);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    auto issue_c = [&](int j) {                   // c of this CTA's j-th tile: Yb x W_c^T -> acc_c
+      mbar_wait(yb_full, j & 1);
+      mbar_wait(accc_empty, (j & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc = make_smem_desc(yb_addr), bdesc = make_smem_desc(wc_addr);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + ACCC_COL, adesc + 2 * k, bdesc + 2 * k, idesc_c, k != 0 ? 1u : 0u);
+        umma_commit(yb_empty);                    // Yb may be overwritten once these have read it
+        umma_commit(accc_full);
+      }
+      __syncwarp();
+    };
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&accb_empty[as], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * F_MID;
+      for (int dx = 0; dx < 3; ++dx) {
+        mbar_wait(&a_full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + stage * F_A_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            // vertical tap dy = the same box viewed one image row (8 pixels = 1024 bytes) further down
+            const uint64_t adesc = make_smem_desc(a_addr + dy * (FX * 128));
+            const uint64_t bdesc = make_smem_desc(wb_addr + (dy * 3 + dx) * (F_MID * 128));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_b, (dx | dy | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&a_empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == F_A_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&accb_full[as]);
+      __syncwarp();
+      if (it >= 1) issue_c(it - 1);
+    }
+    if (it >= 1) issue_c(it - 1);
+  } else if (warp < 6) {
+    // ===================================================== epilogue 1 (warps 2-5): acc_b -> Yb
+    pdl_wait_prior_grid();
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&accb_full[as], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[64];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * F_MID;
+      TMEM_LD_32x32b_x32(taddr, v);
+      TMEM_LD_32x32b_x32(taddr + 32, (v + 32));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&accb_empty[as]);
+      mbar_wait(yb_empty, (it & 1) ^ 1);          // c of the previous tile has read Yb
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        uint4 o;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float f0 = fmaxf(__uint_as_float(v[q * 8 + 2 * e]) + bias_b_s[q * 8 + 2 * e], 0.f);
+          const float f1 = fmaxf(__uint_as_float(v[q * 8 + 2 * e + 1]) + bias_b_s[q * 8 + 2 * e + 1], 0.f);
+          o2[e] = __floats2bfloat162_rn(f0, f1);
+        }
+        *reinterpret_cast<uint4*>(smem_yb + row * 128 + ((q ^ (row & 7)) << 4)) = o;
+      }
+      fence_proxy_async_smem();                   // generic-proxy writes -> visible to the tensor core's async proxy
+      mbar_arrive(yb_full);
+    }
+  } else {
+    // ===================================================== epilogue 2 (warps 6-13): acc_c + residual -> y
+    pdl_wait_prior_grid();
+    const int eg = (warp - 6) >> 2;               // group 0: chunks 0, 2; group 1: chunks 1, 3
+    const int et = (threadIdx.x - 192) & 127;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    uint8_t* slot_g = smem_slot + eg * 2 * F_TILE_BYTES;
+    uint64_t* res_bar = res_full + eg * 2;
+    // chunk sequence of this group: (tile it, chunk eg), (it, eg + 2), (it + 1, eg), ...
+    int pre_tile = blockIdx.x, pre_chunk = eg;
+    auto issue_res = [&](int slot) {
+      int r = pre_tile;
+      const int xt = r % p.x_tiles; r /= p.x_tiles;
+      const int yt = r % p.y_tiles; r /= p.y_tiles;
+      mbar_expect_tx(&res_bar[slot], F_TILE_BYTES);
+      f_tma_load_4d(slot_g + slot * F_TILE_BYTES, &tm_r, &res_bar[slot], pre_chunk * 64, xt * FX, yt * FR, r);
+      if (pre_chunk + 2 < 4) pre_chunk += 2; else { pre_chunk = eg; pre_tile += gridDim.x; }
+    };
+    if (et == 0)
+      for (int j = 0; j < 2; ++j)
+        if (pre_tile < p.num_tiles) issue_res(j);
+    uint32_t k = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      int r = tile;
+      const int xt = r % p.x_tiles; r /= p.x_tiles;
+      const int yt = r % p.y_tiles; r /= p.y_tiles;
+      mbar_wait(accc_full, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = eg; chunk < 4; chunk += 2, ++k) {
+        const int slot = k & 1;
+        uint8_t* s_io = slot_g + slot * F_TILE_BYTES;
+        uint32_t v[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ACCC_COL + chunk * 64;
+        TMEM_LD_32x32b_x32(taddr, v);
+        TMEM_LD_32x32b_x32(taddr + 32, (v + 32));
+        mbar_wait(&res_bar[slot], (k >> 1) & 1u);
+        tmem_ld_wait();
+        if (chunk + 2 >= 4) {                     // this group's last read of acc_c for the tile
+          tc_fence_before();
+          mbar_arrive(accc_empty);
+        }
+        const float* bias = bias_c_s + chunk * 64;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint8_t* pa = s_io + row * 128 + ((q ^ (row & 7)) << 4);
+          const uint4 t = *reinterpret_cast<const uint4*>(pa);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t);
+          uint4 o;
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float f0 = fmaxf(__uint_as_float(v[q * 8 + 2 * e]) + bias[q * 8 + 2 * e] + __low2float(h2[e]), 0.f);
+            const float f1 = fmaxf(__uint_as_float(v[q * 8 + 2 * e + 1]) + bias[q * 8 + 2 * e + 1] + __high2float(h2[e]), 0.f);
+            o2[e] = __floats2bfloat162_rn(f0, f1);
+          }
+          *reinterpret_cast<uint4*>(pa) = o;
+        }
+        fence_proxy_async_smem();
+        wg_bar_sync(2 + eg);                      // tile chunk complete in the slot
+        if (et == 0) {
+          f_tma_store_4d(&tm_y, s_io, chunk * 64, xt * FX, yt * FR, r);
+          tma_store_commit();
+          tma_store_wait_read<0>();               // the store has read the slot: refill it with the residual two chunks on
+          if (pre_tile < p.num_tiles) issue_res(slot);
+        }
+      }
+    }
+    if (et == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_f_encode = nullptr;
+int g_f_sms = 0, g_f_max_smem = 0;
+
+int f_encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+             const char* what) {
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_f_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r); return AF_ERR_CUDA; }
+  return AF_OK;
+}
+
+}  // namespace
+
+int conv_bc_fused_init() {
+  static bool configured[64] = {};
+  int dev = 0;
+  AFB_CUDA(cudaGetDevice(&dev));
+  if (!g_f_encode) {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    AFB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return AF_ERR_UNSUPPORTED; }
+    g_f_encode = (EncodeTiledFn)fn;
+    AFB_CUDA(cudaDeviceGetAttribute(&g_f_sms, cudaDevAttrMultiProcessorCount, dev));
+    AFB_CUDA(cudaDeviceGetAttribute(&g_f_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  }
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    if (F_SMEM <= g_f_max_smem)
+      AFB_CUDA(cudaFuncSetAttribute(conv_bc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  return AF_OK;
+}
+
+// b: dense NDHWC [B,T,H,W,64] -> 1x3x3, stride 1, pad [0,1,1], 64 -> 64; c: 1x1x1 64 -> 256; residual / y dense [M,256].
+bool conv_bc_fused_supported(const ConvProblem& b, const ConvProblem& c) {
+  if (!g_f_encode || F_SMEM > g_f_max_smem) return false;
+  if (b.Cin != F_MID || b.Cout != F_MID || b.kt != 1 || b.kh != 3 || b.kw != 3 || b.st != 1 || b.sh != 1 || b.sw != 1 ||
+      b.pt != 0 || b.ph != 1 || b.pw != 1 || !b.relu || b.res || b.pool_hw || b.pool_t || b.x2)
+    return false;
+  if (c.Cin != F_MID || c.Cout != F_OUT || c.kt != 1 || c.kh != 1 || c.kw != 1 || c.st != 1 || c.sh != 1 || c.sw != 1 ||
+      !c.relu || !c.res || c.pool_t || c.pool_hw || c.x2)
+    return false;
+  if (b.Wo % FX != 0 || b.M != c.M) return false;
+  if (b.xsW != b.Cin || b.xsH != (long long)b.Wi * b.Cin || b.xsT != (long long)b.Hi * b.Wi * b.Cin ||
+      b.xsB != (long long)b.Ti * b.Hi * b.Wi * b.Cin)
+    return false;
+  return true;
+}
+
+int conv_bc_fused_launch(const ConvProblem& b, const ConvProblem& c, cudaStream_t s) {
+  FusedParams fp;
+  fp.bias_b = b.bias; fp.bias_c = c.bias;
+  fp.x_tiles = b.Wo / FX; fp.y_tiles = (b.Ho + FR - 1) / FR; fp.frames = b.B * b.To;
+  fp.num_tiles = fp.frames * fp.y_tiles * fp.x_tiles;
+  alignas(64) CUtensorMap ta, twb, twc, tr, ty;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)F_MID, (cuuint64_t)b.Wi, (cuuint64_t)b.Hi, (cuuint64_t)b.B * b.Ti, 1};
+    cuuint64_t strides[4] = {(cuuint64_t)F_MID * 2, (cuuint64_t)b.Wi * F_MID * 2, (cuuint64_t)b.Hi * b.Wi * F_MID * 2,
+                             (cuuint64_t)b.B * b.Ti * b.Hi * b.Wi * F_MID * 2};
+    cuuint32_t box[5] = {64, FX, FR + 2, 1, 1};
+    int rc = f_encode(&ta, b.x, 5, dims, strides, box, "fused A");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)F_MID, (cuuint64_t)9 * F_MID};
+    cuuint64_t strides[1] = {(cuuint64_t)F_MID * 2};
+    cuuint32_t box[2] = {64, F_MID};
+    int rc = f_encode(&twb, b.w, 2, dims, strides, box, "fused Wb");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)F_MID, (cuuint64_t)F_OUT};
+    cuuint64_t strides[1] = {(cuuint64_t)F_MID * 2};
+    cuuint32_t box[2] = {64, F_OUT};
+    int rc = f_encode(&twc, c.w, 2, dims, strides, box, "fused Wc");
+    if (rc) return rc;
+  }
+  for (int which = 0; which < 2; ++which) {
+    cuuint64_t dims[4] = {(cuuint64_t)F_OUT, (cuuint64_t)b.Wo, (cuuint64_t)b.Ho, (cuuint64_t)fp.frames};
+    cuuint64_t strides[3] = {(cuuint64_t)F_OUT * 2, (cuuint64_t)b.Wo * F_OUT * 2, (cuuint64_t)b.Ho * b.Wo * F_OUT * 2};
+    cuuint32_t box[4] = {64, FX, FR, 1};
+    int rc = f_encode(which ? &ty : &tr, which ? c.y : c.res, 4, dims, strides, box, which ? "fused Y" : "fused R");
+    if (rc) return rc;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(limit_grid(fp.num_tiles, g_f_sms));
+  cfg.blockDim = dim3(F_THREADS); cfg.dynamicSmemBytes = F_SMEM; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_bc_fused_kernel, ta, twb, twc, tr, ty, fp));
+  ++g_launches;
+  AFB_CUDA(cudaGetLastError());
+  return AF_OK;
+}
+
+}  // namespace afb

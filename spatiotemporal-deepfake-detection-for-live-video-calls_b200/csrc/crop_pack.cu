@@ -182,19 +182,36 @@ __global__ void norm_lut_kernel(Norm nrm, float* __restrict__ lut) {
 }
 
 // u8 [B,T,S,S,3] aligned clips -> normalised padded NDHWC4 clip (A4 of SURVEY.md §8a).
+// One block per 8 image rows of (b, t): no per-pixel index division; S % 4 == 0: a thread converts 4 pixels (three aligned
+// 32-bit loads, four 8-byte stores), otherwise one pixel at a time.  lut as in crop_kernel: fp32 [3][256], built with
+// the callers' IEEE subtraction / division, so the result equals the fp32 pack lines bit for bit.
 template <typename T>
-__global__ void __launch_bounds__(256) pack_u8_kernel(const uint8_t* __restrict__ src, int T_, int S, T* dst,
-                                                      long long sB, long long sT, long long sH, long long sW,
-                                                      long long npix, Norm nrm) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long r = i;
-    const int x = (int)(r % S); r /= S;
-    const int y = (int)(r % S); r /= S;
-    const int t = (int)(r % T_); r /= T_;
-    const uint8_t* p = src + i * 3;
-    store_px4<T>(dst + r * sB + t * sT + y * sH + x * sW, norm1((float)p[0], nrm.mean[0], nrm.stdv[0]),
-                 norm1((float)p[1], nrm.mean[1], nrm.stdv[1]), norm1((float)p[2], nrm.mean[2], nrm.stdv[2]));
+__global__ void __launch_bounds__(64) pack_u8_kernel(const uint8_t* __restrict__ src, int T_, int S, T* dst, long long sB,
+                                                     long long sT, long long sH, long long sW,
+                                                     const float* __restrict__ lut) {
+  __shared__ float s_lut[768];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = __ldg(lut + i);
+  __syncthreads();
+  const int t = blockIdx.y, b = blockIdx.z;
+  for (int y = blockIdx.x * 8; y < min(S, blockIdx.x * 8 + 8); ++y) {
+  const uint8_t* row = src + (((long long)b * T_ + t) * S + y) * (long long)S * 3;
+  T* out = dst + b * sB + t * sT + y * sH;
+  if ((S & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) & 3) == 0)) {
+    const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
+    for (int g = threadIdx.x; g < S / 4; g += blockDim.x) {
+      const uint32_t w0 = __ldg(row4 + 3 * g), w1 = __ldg(row4 + 3 * g + 1), w2 = __ldg(row4 + 3 * g + 2);
+      T* q = out + (long long)(4 * g) * sW;
+      store_px4<T>(q, s_lut[w0 & 255], s_lut[256 + ((w0 >> 8) & 255)], s_lut[512 + ((w0 >> 16) & 255)]);
+      store_px4<T>(q + sW, s_lut[w0 >> 24], s_lut[256 + (w1 & 255)], s_lut[512 + ((w1 >> 8) & 255)]);
+      store_px4<T>(q + 2 * sW, s_lut[(w1 >> 16) & 255], s_lut[256 + (w1 >> 24)], s_lut[512 + (w2 & 255)]);
+      store_px4<T>(q + 3 * sW, s_lut[(w2 >> 8) & 255], s_lut[256 + ((w2 >> 16) & 255)], s_lut[512 + (w2 >> 24)]);
+    }
+  } else {
+    for (int x = threadIdx.x; x < S; x += blockDim.x) {
+      const uint8_t* p = row + 3 * x;
+      store_px4<T>(out + (long long)x * sW, s_lut[p[0]], s_lut[256 + p[1]], s_lut[512 + p[2]]);
+    }
+  }
   }
 }
 
@@ -331,13 +348,17 @@ int stem_unfold_launch(const ClipLayout& clip, int clip0, int B, void* U, cudaSt
 
 int pack_u8_launch(const uint8_t* src, int B, const float mean[3], const float stdv[3],
                    const ClipLayout& d, cudaStream_t s) {
-  const long long npix = (long long)B * d.T * d.S * d.S;
+  if (B <= 0) return AF_OK;
   Norm n;
   for (int c = 0; c < 3; ++c) { n.mean[c] = mean[c]; n.stdv[c] = stdv[c]; }
+  const float* lut = nullptr;
+  int rc = norm_lut_for(n, s, &lut);
+  if (rc) return rc;
+  dim3 grid((d.S + 7) / 8, d.T, B);
   if (d.is_bf16)
-    pack_u8_kernel<bf16><<<flat_grid(npix, 256), 256, 0, s>>>(src, d.T, d.S, (bf16*)d.base, d.sB, d.sT, d.sH, d.sW, npix, n);
+    pack_u8_kernel<bf16><<<grid, 64, 0, s>>>(src, d.T, d.S, (bf16*)d.base, d.sB, d.sT, d.sH, d.sW, lut);
   else
-    pack_u8_kernel<float><<<flat_grid(npix, 256), 256, 0, s>>>(src, d.T, d.S, (float*)d.base, d.sB, d.sT, d.sH, d.sW, npix, n);
+    pack_u8_kernel<float><<<grid, 64, 0, s>>>(src, d.T, d.S, (float*)d.base, d.sB, d.sT, d.sH, d.sW, lut);
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;

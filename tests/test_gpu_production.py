@@ -304,3 +304,37 @@ def test_services_have_the_reference_call_shapes(dev, state_dict, golden_crop):
     assert scores.shape == (1,) and clf._last_logits is None
     assert clf.last_logits_1d.shape == (1,) and np.allclose(scores, 1 / (1 + np.exp(-clf.last_logits_1d)), atol=1e-6)
     assert np.array_equal(clf._last_scores, scores)
+
+
+# ------------------------------------------------------------------ fused b -> c tail of an s2 block
+@pytest.mark.parametrize("case", [
+    # B, T, H, W
+    (1, 2, 16, 8),        # one tile per frame
+    (2, 3, 56, 56),       # s2 geometry: 7 x 4 tiles per frame, last row tile partly outside the image
+    (3, 1, 20, 24),       # ragged rows, 3 clips
+    (1, 40, 24, 16),      # more tiles than SMs: every CTA loops (ring / accumulator / slot phases wrap)
+])
+def test_fused_bc_kernel_vs_torch_fp32(dev, case):
+    """relu(c(relu(b(x))) + residual), b = 1x3x3 64->64, c = 1x1x1 64->256 (resnet_helper.py:311-326,438-444) in ONE
+    kernel; reference in fp32 on the bf16-rounded operands with the intermediate rounded to bf16 as the kernel does."""
+    B, T, H, W = case
+    g = torch.Generator().manual_seed(17 * H + W)
+    x = torch.randn(B, T, H, W, 64, generator=g).to(dev, torch.bfloat16)
+    wb = torch.randn(64, 64, 1, 3, 3, generator=g) * (2.0 / 576) ** 0.5
+    bb = torch.randn(64, generator=g) * 0.1
+    wc = torch.randn(256, 64, 1, 1, 1, generator=g) * (2.0 / 64) ** 0.5
+    bc = torch.randn(256, generator=g) * 0.1
+    res = torch.randn(B, T, H, W, 256, generator=g).to(dev, torch.bfloat16)
+    mid = _conv_ref(x, wb.to(torch.bfloat16).float(), bb, (1, 1, 1), (0, 1, 1), True, None).to(torch.bfloat16)
+    want = _conv_ref(mid, wc.to(torch.bfloat16).float(), bc, (1, 1, 1), (0, 0, 0), True, res)
+    got = afb200.conv_bc_fused_ndhwc(x, wb, bb, wc, bc, res).float().cpu()
+    assert got.shape == want.shape
+    # one bf16 ulp of the output + the effect of one-ulp flips of the bf16 intermediate (64 terms, |w| ~ 0.18)
+    tol = 2.0 ** -7 * max(1.0, want.abs().max().item()) + 2.0 ** -8 * max(1.0, mid.float().abs().max().item()) * 0.6 + 1e-3
+    diff = (got - want).abs()
+    assert diff.max().item() <= tol, (diff.max().item(), tol)
+    assert (diff > 2.0 ** -7 * want.abs().clamp_min(1.0)).float().mean().item() < 2e-3
+    # and against the two separate kernels the fused one replaces
+    y_b = afb200.conv_ndhwc(x, wb, bb, (1, 1, 1), (0, 1, 1), True, None, impl=3)
+    y_c = afb200.conv_ndhwc(y_b, wc, bc, (1, 1, 1), (0, 0, 0), True, res, impl=2).float().cpu()
+    assert (got - y_c).abs().max().item() <= tol
