@@ -265,11 +265,14 @@ af_status af_stem_pool_ndhwc4(const void* clip_dev, const af_conv_desc* stem_hos
                               int32_t t, int32_t s, int32_t per_frame_kernel, void* stream);
 
 /* Test/diagnostic entry: the fused tail of an s2 bottleneck block (conv_bc_fused.cu),
- *   y = relu(c(relu(b(x))) + residual)   with b = 1x3x3 64->64 (+folded BN), c = 1x1x1 64->256 (+folded BN)
- * (resnet_helper.py:311-326,438-444) on bf16 NDHWC device tensors: x [B,T,H,W,64], residual / y [B,T,H,W,256]. */
+ *   y = relu(c(relu(b(x))) + residual)          (identity-shortcut blocks), or
+ *   y = relu(c(relu(b(x))) + shortcut(x2))      (first block of the stage: projection shortcut as a second K block)
+ * with b = 1x3x3 64->64, c = 1x1x1 64->256, shortcut = 1x1x1 stride 1 64->256, all with folded BN
+ * (resnet_helper.py:311-326,411-423,438-444) on bf16 NDHWC device tensors: x, x2 [B,T,H,W,64], residual / y
+ * [B,T,H,W,256].  Give EITHER residual_dev OR (x2_dev, shortcut_host); the other(s) NULL. */
 af_status af_conv_bc_fused_ndhwc(const void* x_dev, const af_conv_desc* conv_b_host, const af_conv_desc* conv_c_host,
-                                 const void* residual_dev, void* y_dev, int32_t batch, int32_t t, int32_t hgt,
-                                 int32_t wid, void* stream);
+                                 const void* residual_dev, const void* x2_dev, const af_conv_desc* shortcut_host,
+                                 void* y_dev, int32_t batch, int32_t t, int32_t hgt, int32_t wid, void* stream);
 
 /* Copy intermediate activations of the LAST af_forward/af_infer call out for stage
  * parity tests: which = 1..5 (s1..s5 outputs) as fp32 NCTHW [B,C,T,H,W] into out_dev.

@@ -120,7 +120,8 @@ def lib():
     L.af_ring_put_rows.restype = i32
     L.af_ring_put_rows.argtypes = [vp, i64, i64, i32, vp, vp, vp, vp, vp]
     L.af_conv_bc_fused_ndhwc.restype = i32
-    L.af_conv_bc_fused_ndhwc.argtypes = [vp, C.POINTER(AfConvDesc), C.POINTER(AfConvDesc), vp, vp, i32, i32, i32, i32, vp]
+    L.af_conv_bc_fused_ndhwc.argtypes = [vp, C.POINTER(AfConvDesc), C.POINTER(AfConvDesc), vp, vp, C.POINTER(AfConvDesc), vp, i32, i32, i32,
+                                         i32, vp]
     L.af_get_stat.restype = i32
     L.af_get_stat.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double)]
     L.af_get_stage.restype = i32

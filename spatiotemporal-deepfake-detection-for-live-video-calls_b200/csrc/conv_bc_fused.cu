@@ -35,8 +35,13 @@ constexpr int F_A_BYTES = (FR + 2) * FX * 128;  // 18 rows x 8 pixels x 64 bf16
 constexpr int F_WB_BYTES = 9 * F_MID * 128;
 constexpr int F_WC_BYTES = F_OUT * 128;
 constexpr int F_TILE_BYTES = 128 * 128;         // 128 pixels x 64 channels bf16
-constexpr int F_SMEM = F_WB_BYTES + F_WC_BYTES + F_A_STAGES * F_A_BYTES + F_TILE_BYTES + 4 * F_TILE_BYTES +
-                       (F_MID + F_OUT) * 4 + 32 * 8 + 16 + 1024;
+// kShortcut (first block of the stage): W_c is followed by the projection shortcut's weights (second K block of the c
+// GEMM, operand = the block INPUT tile, which travels through the halo ring as a 4th box); no residual tile is loaded,
+// so two of the four 16 KB slots suffice.
+constexpr int f_smem(bool shortcut) {
+  return F_WB_BYTES + (shortcut ? 2 : 1) * F_WC_BYTES + F_A_STAGES * F_A_BYTES + F_TILE_BYTES + (shortcut ? 2 : 4) * F_TILE_BYTES +
+         (F_MID + F_OUT) * 4 + 32 * 8 + 16 + 1024;
+}
 
 struct FusedParams {
   const float* bias_b;
@@ -68,19 +73,24 @@ __device__ __forceinline__ void f_tma_store_4d(const CUtensorMap* m, const void*
 // named barrier among the 128 threads of one warpgroup (ids 1..3; 0 is __syncthreads)
 __device__ __forceinline__ void wg_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
+// tm_r: residual [M,256] (kShortcut = false) / tm_x: the block input [B*T,H,W,64] and tm_ws: shortcut weights (true)
+template <bool kShortcut>
 __global__ void __launch_bounds__(F_THREADS, 1)
 conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_wb,
                      const __grid_constant__ CUtensorMap tm_wc, const __grid_constant__ CUtensorMap tm_r,
-                     const __grid_constant__ CUtensorMap tm_y, const FusedParams p) {
+                     const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_x,
+                     const __grid_constant__ CUtensorMap tm_ws, const FusedParams p) {
+  constexpr int WC_BYTES = (kShortcut ? 2 : 1) * F_WC_BYTES;
+  constexpr int N_SLOTS = kShortcut ? 2 : 4;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_wb = smem;
   uint8_t* smem_wc = smem_wb + F_WB_BYTES;
-  uint8_t* smem_a = smem_wc + F_WC_BYTES;
+  uint8_t* smem_a = smem_wc + WC_BYTES;
   uint8_t* smem_yb = smem_a + F_A_STAGES * F_A_BYTES;
-  uint8_t* smem_slot = smem_yb + F_TILE_BYTES;                 // [2 groups][2 slots] x 16 KB
-  float* bias_b_s = reinterpret_cast<float*>(smem_slot + 4 * F_TILE_BYTES);
+  uint8_t* smem_slot = smem_yb + F_TILE_BYTES;                 // [2 groups][2 (1 with kShortcut) slots] x 16 KB
+  float* bias_b_s = reinterpret_cast<float*>(smem_slot + N_SLOTS * F_TILE_BYTES);
   float* bias_c_s = bias_b_s + F_MID;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(bias_c_s + F_OUT);
   uint64_t* a_empty = a_full + F_A_STAGES;
@@ -102,7 +112,7 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_wb);
     tma_prefetch_desc(&tm_wc);
-    tma_prefetch_desc(&tm_r);
+    if (kShortcut) { tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_ws); } else { tma_prefetch_desc(&tm_r); }
     tma_prefetch_desc(&tm_y);
     for (int i = 0; i < F_A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     mbar_init(w_full, 1);
@@ -128,9 +138,10 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   if (warp == 0) {
     // ===================================================== TMA producer
     if (elect_one()) {                            // weights are constants: no need to wait for the prior grid
-      mbar_expect_tx(w_full, F_WB_BYTES + F_WC_BYTES);
+      mbar_expect_tx(w_full, F_WB_BYTES + WC_BYTES);
       for (int tap = 0; tap < 9; ++tap) tma_load_2d(smem_wb + tap * (F_MID * 128), &tm_wb, w_full, 0, tap * F_MID);
       tma_load_2d(smem_wc, &tm_wc, w_full, 0, 0);
+      if (kShortcut) tma_load_2d(smem_wc + F_WC_BYTES, &tm_ws, w_full, 0, 0);
     }
     __syncwarp();
     pdl_wait_prior_grid();
@@ -150,6 +161,15 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         __syncwarp();
         if (++stage == F_A_STAGES) { stage = 0; phase ^= 1; }
       }
+      if (kShortcut) {       // 4th box: the block input under the tile (no halo), operand of the shortcut's K block
+        mbar_wait(&a_empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[stage], F_TILE_BYTES);
+          f_tma_load_5d(smem_a + stage * F_A_BYTES, &tm_x, &a_full[stage], 0, xt * FX, yt * FR, r, 0);
+        }
+        __syncwarp();
+        if (++stage == F_A_STAGES) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
@@ -160,7 +180,7 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    auto issue_c = [&](int j) {                   // c of this CTA's j-th tile: Yb x W_c^T -> acc_c
+    auto issue_c = [&](int j) {                   // c of this CTA's j-th tile: Yb x W_c^T (+ X x W_s^T) -> acc_c
       mbar_wait(yb_full, j & 1);
       mbar_wait(accc_empty, (j & 1) ^ 1);
       tc_fence_after();
@@ -169,9 +189,22 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + ACCC_COL, adesc + 2 * k, bdesc + 2 * k, idesc_c, k != 0 ? 1u : 0u);
         umma_commit(yb_empty);                    // Yb may be overwritten once these have read it
-        umma_commit(accc_full);
+        if (!kShortcut) umma_commit(accc_full);
       }
       __syncwarp();
+      if (kShortcut) {                            // second K block: the block-input tile (4th ring box) x shortcut weights
+        mbar_wait(&a_full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * F_A_BYTES)), bdesc = make_smem_desc(wc_addr + F_WC_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + ACCC_COL, adesc + 2 * k, bdesc + 2 * k, idesc_c, 1u);
+          umma_commit(&a_empty[stage]);
+          umma_commit(accc_full);
+        }
+        __syncwarp();
+        if (++stage == F_A_STAGES) { stage = 0; phase ^= 1; }
+      }
     };
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -198,9 +231,12 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       }
       if (elect_one()) umma_commit(&accb_full[as]);
       __syncwarp();
-      if (it >= 1) issue_c(it - 1);
+      // without the shortcut, c of a tile is issued after b of the NEXT tile (epilogue 1 hides behind it); with it the
+      // ring delivers the tile's 4th box right behind its halo boxes, so c follows b directly
+      if (kShortcut) issue_c(it);
+      else if (it >= 1) issue_c(it - 1);
     }
-    if (it >= 1) issue_c(it - 1);
+    if (!kShortcut && it >= 1) issue_c(it - 1);
   } else if (warp < 6) {
     // ===================================================== epilogue 1 (warps 2-5): acc_b -> Yb
     pdl_wait_prior_grid();
@@ -241,7 +277,7 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     const int et = (threadIdx.x - 192) & 127;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    uint8_t* slot_g = smem_slot + eg * 2 * F_TILE_BYTES;
+    uint8_t* slot_g = smem_slot + eg * (N_SLOTS / 2) * F_TILE_BYTES;
     uint64_t* res_bar = res_full + eg * 2;
     // chunk sequence of this group: (tile it, chunk eg), (it, eg + 2), (it + 1, eg), ...
     int pre_tile = blockIdx.x, pre_chunk = eg;
@@ -253,7 +289,7 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       f_tma_load_4d(slot_g + slot * F_TILE_BYTES, &tm_r, &res_bar[slot], pre_chunk * 64, xt * FX, yt * FR, r);
       if (pre_chunk + 2 < 4) pre_chunk += 2; else { pre_chunk = eg; pre_tile += gridDim.x; }
     };
-    if (et == 0)
+    if (!kShortcut && et == 0)
       for (int j = 0; j < 2; ++j)
         if (pre_tile < p.num_tiles) issue_res(j);
     uint32_t k = 0;
@@ -266,13 +302,18 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       tc_fence_after();
 #pragma unroll 1
       for (int chunk = eg; chunk < 4; chunk += 2, ++k) {
-        const int slot = k & 1;
+        const int slot = kShortcut ? 0 : (int)(k & 1);
         uint8_t* s_io = slot_g + slot * F_TILE_BYTES;
         uint32_t v[64];
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ACCC_COL + chunk * 64;
         TMEM_LD_32x32b_x32(taddr, v);
         TMEM_LD_32x32b_x32(taddr + 32, (v + 32));
-        mbar_wait(&res_bar[slot], (k >> 1) & 1u);
+        if (kShortcut) {                          // plain output staging: the previous store must have read the slot
+          if (et == 0) tma_store_wait_read<0>();
+          wg_bar_sync(2 + eg);
+        } else {
+          mbar_wait(&res_bar[slot], (k >> 1) & 1u);
+        }
         tmem_ld_wait();
         if (chunk + 2 >= 4) {                     // this group's last read of acc_c for the tile
           tc_fence_before();
@@ -282,7 +323,8 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           uint8_t* pa = s_io + row * 128 + ((q ^ (row & 7)) << 4);
-          const uint4 t = *reinterpret_cast<const uint4*>(pa);
+          uint4 t = make_uint4(0u, 0u, 0u, 0u);
+          if (!kShortcut) t = *reinterpret_cast<const uint4*>(pa);
           const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t);
           uint4 o;
           __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
@@ -299,8 +341,10 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         if (et == 0) {
           f_tma_store_4d(&tm_y, s_io, chunk * 64, xt * FX, yt * FR, r);
           tma_store_commit();
-          tma_store_wait_read<0>();               // the store has read the slot: refill it with the residual two chunks on
-          if (pre_tile < p.num_tiles) issue_res(slot);
+          if (!kShortcut) {
+            tma_store_wait_read<0>();             // the store has read the slot: refill it with the residual two chunks on
+            if (pre_tile < p.num_tiles) issue_res(slot);
+          }
         }
       }
     }
@@ -347,21 +391,28 @@ int conv_bc_fused_init() {
     AFB_CUDA(cudaDeviceGetAttribute(&g_f_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   }
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    if (F_SMEM <= g_f_max_smem)
-      AFB_CUDA(cudaFuncSetAttribute(conv_bc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+    if (f_smem(false) <= g_f_max_smem)
+      AFB_CUDA(cudaFuncSetAttribute(conv_bc_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem(false)));
+    if (f_smem(true) <= g_f_max_smem)
+      AFB_CUDA(cudaFuncSetAttribute(conv_bc_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem(true)));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   return AF_OK;
 }
 
 // b: dense NDHWC [B,T,H,W,64] -> 1x3x3, stride 1, pad [0,1,1], 64 -> 64; c: 1x1x1 64 -> 256; residual / y dense [M,256].
+// With c.x2 set (projection shortcut fused into c: pointwise, stride 1, 64 -> 256 over the block input c.x2, biases
+// pre-summed in c.bias) there is no residual.
 bool conv_bc_fused_supported(const ConvProblem& b, const ConvProblem& c) {
-  if (!g_f_encode || F_SMEM > g_f_max_smem) return false;
+  if (!g_f_encode || f_smem(c.x2 != nullptr) > g_f_max_smem) return false;
   if (b.Cin != F_MID || b.Cout != F_MID || b.kt != 1 || b.kh != 3 || b.kw != 3 || b.st != 1 || b.sh != 1 || b.sw != 1 ||
       b.pt != 0 || b.ph != 1 || b.pw != 1 || !b.relu || b.res || b.pool_hw || b.pool_t || b.x2)
     return false;
   if (c.Cin != F_MID || c.Cout != F_OUT || c.kt != 1 || c.kh != 1 || c.kw != 1 || c.st != 1 || c.sh != 1 || c.sw != 1 ||
-      !c.relu || !c.res || c.pool_t || c.pool_hw || c.x2)
+      !c.relu || c.pool_t || c.pool_hw)
+    return false;
+  if (c.x2 ? (c.res || !c.w2 || c.Cin2 != F_MID || c.sh2 != 1 || c.sw2 != 1 || c.T2 != c.To || c.H2 != c.Ho || c.W2 != c.Wo)
+           : !c.res)
     return false;
   if (b.Wo % FX != 0 || b.M != c.M) return false;
   if (b.xsW != b.Cin || b.xsH != (long long)b.Wi * b.Cin || b.xsT != (long long)b.Hi * b.Wi * b.Cin ||
@@ -375,7 +426,8 @@ int conv_bc_fused_launch(const ConvProblem& b, const ConvProblem& c, cudaStream_
   fp.bias_b = b.bias; fp.bias_c = c.bias;
   fp.x_tiles = b.Wo / FX; fp.y_tiles = (b.Ho + FR - 1) / FR; fp.frames = b.B * b.To;
   fp.num_tiles = fp.frames * fp.y_tiles * fp.x_tiles;
-  alignas(64) CUtensorMap ta, twb, twc, tr, ty;
+  alignas(64) CUtensorMap ta, twb, twc, tr, ty, tx, tws;
+  const bool shortcut = c.x2 != nullptr;
   {
     cuuint64_t dims[5] = {(cuuint64_t)F_MID, (cuuint64_t)b.Wi, (cuuint64_t)b.Hi, (cuuint64_t)b.B * b.Ti, 1};
     cuuint64_t strides[4] = {(cuuint64_t)F_MID * 2, (cuuint64_t)b.Wi * F_MID * 2, (cuuint64_t)b.Hi * b.Wi * F_MID * 2,
@@ -402,17 +454,32 @@ int conv_bc_fused_launch(const ConvProblem& b, const ConvProblem& c, cudaStream_
     cuuint64_t dims[4] = {(cuuint64_t)F_OUT, (cuuint64_t)b.Wo, (cuuint64_t)b.Ho, (cuuint64_t)fp.frames};
     cuuint64_t strides[3] = {(cuuint64_t)F_OUT * 2, (cuuint64_t)b.Wo * F_OUT * 2, (cuuint64_t)b.Ho * b.Wo * F_OUT * 2};
     cuuint32_t box[4] = {64, FX, FR, 1};
-    int rc = f_encode(which ? &ty : &tr, which ? c.y : c.res, 4, dims, strides, box, which ? "fused Y" : "fused R");
+    int rc = f_encode(which ? &ty : &tr, (which || shortcut) ? c.y : c.res, 4, dims, strides, box, which ? "fused Y" : "fused R");
+    if (rc) return rc;
+  }
+  tx = ta; tws = twc;
+  if (shortcut) {
+    cuuint64_t dims[5] = {(cuuint64_t)F_MID, (cuuint64_t)c.W2, (cuuint64_t)c.H2, (cuuint64_t)b.B * c.T2, 1};
+    cuuint64_t strides[4] = {(cuuint64_t)F_MID * 2, (cuuint64_t)c.W2 * F_MID * 2, (cuuint64_t)c.H2 * c.W2 * F_MID * 2,
+                             (cuuint64_t)b.B * c.T2 * c.H2 * c.W2 * F_MID * 2};
+    cuuint32_t box[5] = {64, FX, FR, 1, 1};
+    int rc = f_encode(&tx, c.x2, 5, dims, strides, box, "fused X");
+    if (rc) return rc;
+    cuuint64_t wdims[2] = {(cuuint64_t)F_MID, (cuuint64_t)F_OUT};
+    cuuint64_t wstrides[1] = {(cuuint64_t)F_MID * 2};
+    cuuint32_t wbox[2] = {64, F_OUT};
+    rc = f_encode(&tws, c.w2, 2, wdims, wstrides, wbox, "fused Ws");
     if (rc) return rc;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(limit_grid(fp.num_tiles, g_f_sms));
-  cfg.blockDim = dim3(F_THREADS); cfg.dynamicSmemBytes = F_SMEM; cfg.stream = s;
+  cfg.blockDim = dim3(F_THREADS); cfg.dynamicSmemBytes = f_smem(shortcut); cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_bc_fused_kernel, ta, twb, twc, tr, ty, fp));
+  if (shortcut) AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_bc_fused_kernel<true>, ta, twb, twc, tr, ty, tx, tws, fp));
+  else AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_bc_fused_kernel<false>, ta, twb, twc, tr, ty, tx, tws, fp));
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;

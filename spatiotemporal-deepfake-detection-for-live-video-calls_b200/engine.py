@@ -239,20 +239,26 @@ def conv_ndhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride
     return y
 
 
-def conv_bc_fused_ndhwc(x: torch.Tensor, weight_b, bias_b, weight_c, bias_c, residual: torch.Tensor) -> torch.Tensor:
-    """relu(c(relu(b(x))) + residual) in ONE kernel (test/diagnostic entry af_conv_bc_fused_ndhwc): x bf16 [B,T,H,W,64],
-    weight_b [64,64,1,3,3], weight_c [256,64,1,1,1], residual bf16 [B,T,H,W,256]."""
-    for t in (x, residual):
-        assert t.is_cuda and t.is_contiguous() and t.dtype == torch.bfloat16
+def conv_bc_fused_ndhwc(x: torch.Tensor, weight_b, bias_b, weight_c, bias_c, residual: Optional[torch.Tensor] = None,
+                        x2: Optional[torch.Tensor] = None, weight_s=None, bias_s=None) -> torch.Tensor:
+    """relu(c(relu(b(x))) + residual) — or + shortcut(x2) — in ONE kernel (test/diagnostic entry af_conv_bc_fused_ndhwc):
+    x bf16 [B,T,H,W,64], weight_b [64,64,1,3,3], weight_c [256,64,1,1,1], residual bf16 [B,T,H,W,256] or
+    x2 bf16 [B,T,H,W,64] with weight_s [256,64,1,1,1]."""
+    assert (residual is None) != (x2 is None)
+    for t in (x, residual, x2):
+        assert t is None or (t.is_cuda and t.is_contiguous() and t.dtype == torch.bfloat16)
     B, T, H, W, _ = x.shape
     db, keep_b = _conv_desc(weight_b, bias_b, (1, 1, 1), (0, 1, 1))
     dc, keep_c = _conv_desc(weight_c, bias_c, (1, 1, 1), (0, 0, 0))
+    ds, keep_s = _conv_desc(weight_s, bias_s, (1, 1, 1), (0, 0, 0)) if x2 is not None else (None, None)
     y = torch.empty((B, T, H, W, dc.cout), dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
-        check(lib().af_conv_bc_fused_ndhwc(C.c_void_p(x.data_ptr()), C.byref(db), C.byref(dc), C.c_void_p(residual.data_ptr()),
-                                           C.c_void_p(y.data_ptr()), B, T, H, W,
+        check(lib().af_conv_bc_fused_ndhwc(C.c_void_p(x.data_ptr()), C.byref(db), C.byref(dc),
+                                           C.c_void_p(residual.data_ptr()) if residual is not None else None,
+                                           C.c_void_p(x2.data_ptr()) if x2 is not None else None,
+                                           C.byref(ds) if ds is not None else None, C.c_void_p(y.data_ptr()), B, T, H, W,
                                            C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "af_conv_bc_fused_ndhwc")
-    del keep_b, keep_c
+    del keep_b, keep_c, keep_s
     return y
 
 

@@ -338,3 +338,27 @@ def test_fused_bc_kernel_vs_torch_fp32(dev, case):
     y_b = afb200.conv_ndhwc(x, wb, bb, (1, 1, 1), (0, 1, 1), True, None, impl=3)
     y_c = afb200.conv_ndhwc(y_b, wc, bc, (1, 1, 1), (0, 0, 0), True, res, impl=2).float().cpu()
     assert (got - y_c).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("case", [(1, 2, 16, 8), (2, 3, 56, 56), (1, 40, 24, 16)])
+def test_fused_bc_kernel_with_projection_shortcut(dev, case):
+    """First block of s2: relu(c(relu(b(x))) + branch1(x2) + biases), the shortcut accumulated as a second K block of the
+    c GEMM inside the fused kernel (resnet_helper.py:411-423,438-441)."""
+    B, T, H, W = case
+    g = torch.Generator().manual_seed(5 * H + W)
+    x = torch.randn(B, T, H, W, 64, generator=g).to(dev, torch.bfloat16)
+    x2 = torch.randn(B, T, H, W, 64, generator=g).to(dev, torch.bfloat16)
+    wb = torch.randn(64, 64, 1, 3, 3, generator=g) * (2.0 / 576) ** 0.5
+    bb = torch.randn(64, generator=g) * 0.1
+    wc = torch.randn(256, 64, 1, 1, 1, generator=g) * (1.0 / 64) ** 0.5
+    bc = torch.randn(256, generator=g) * 0.1
+    ws = torch.randn(256, 64, 1, 1, 1, generator=g) * (1.0 / 64) ** 0.5
+    bs = torch.randn(256, generator=g) * 0.1
+    mid = _conv_ref(x, wb.to(torch.bfloat16).float(), bb, (1, 1, 1), (0, 1, 1), True, None).to(torch.bfloat16)
+    want = F.relu(_conv_ref(mid, wc.to(torch.bfloat16).float(), bc, (1, 1, 1), (0, 0, 0), False, None) +
+                  _conv_ref(x2, ws.to(torch.bfloat16).float(), bs, (1, 1, 1), (0, 0, 0), False, None))
+    got = afb200.conv_bc_fused_ndhwc(x, wb, bb, wc, bc, x2=x2, weight_s=ws, bias_s=bs).float().cpu()
+    tol = 2.0 ** -7 * max(1.0, want.abs().max().item()) + 2.0 ** -8 * max(1.0, mid.float().abs().max().item()) * 0.6 + 1e-3
+    diff = (got - want).abs()
+    assert diff.max().item() <= tol, (diff.max().item(), tol)
+    assert (diff > 2.0 ** -7 * want.abs().clamp_min(1.0)).float().mean().item() < 2e-3

@@ -34,7 +34,7 @@ with open(out_csv, "w", newline="") as f:
     w.writerow([units.get(c, "") for c in COLS])
     for r in rows:
         w.writerow([r[c] for c in COLS])
-conv = [r for r in rows if any(n in r["Kernel Name"] for n in ("conv_umma_kernel", "conv_rows_kernel", "conv_tsweep_kernel", "stem_sweep_kernel"))]
+conv = [r for r in rows if any(n in r["Kernel Name"] for n in ("conv_umma_kernel", "conv_rows_kernel", "conv_tsweep_kernel", "stem_sweep_kernel", "conv_bc_fused_kernel"))]
 rd = sum(to_bytes(r, "dram__bytes_read.sum") for r in conv)
 wr = sum(to_bytes(r, "dram__bytes_write.sum") for r in conv)
 allb = sum(to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum") for r in rows)
