@@ -59,26 +59,38 @@ __device__ __forceinline__ uint2 load6(const uint8_t* p) {
   return make_uint2(__funnelshift_r(w0, w1, s2), __funnelshift_r(w1, w2, s2));
 }
 
-// Per block (32 columns x 8 rows of one frame): the f64 part of OpenCV's coordinate maths is done once per column
+// Per block (32 columns x 32 rows of one frame, 4 rows per thread): the f64 part of OpenCV's coordinate maths is done once per column
 // (adelta, bdelta) and once per row (X0, Y0) by 40 threads and shared through smem, together with the frame's
 // descriptor reduced to "valid canvas window" form.  lut: fp32 [3][256] = (v - mean_c) / std_c for every u8 value
 // (built by norm_lut_kernel with the same IEEE division the callers' pack step performs).
+//
+// Pixel path.  The four taps of an output pixel are the 2x2 source pixels at (sx, sy); a tap outside the frame's
+// valid window contributes zero (cv2's BORDER_CONSTANT and the canvas' black surround).  The FAST path (block-uniform:
+// the window is at least 2x2 and does not touch the frame's first or last row, so 16-byte fetch windows stay inside the
+// frame buffer) is branch-free: the 2x2 fetch position is clamped INTO the window, the weights of taps outside the
+// window are zeroed, and when clamping moved the position by one pixel / row the fetched data is shifted back under
+// the taps (a 24-bit funnel shift / a row select).  Pixels whose taps are all outside get four zero weights.  One code
+// path for interior, edge and outside pixels means no warp divergence along the rotated crop's borders.
+constexpr int CROP_ROWS = 32;      // output rows per block (8 thread rows x 4)
 template <typename T, bool kToClip>
 __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__ frames,
                                                    const ClipGeom* __restrict__ geom, int T_, int S,
                                                    int bgr, uint8_t* __restrict__ out_u8, T* dst,
                                                    long long sB, long long sT, long long sH,
                                                    long long sW, long long sC, const float* __restrict__ lut) {
-  // block-uniform values are packed so that a thread fetches them with five vector LDS (the kernel is LSU-bound)
-  __shared__ int2 s_col[32], s_row[8];         // (adelta, bdelta) per column, (X0, Y0) per row
+  // block-uniform values are packed so that a thread fetches them with a few vector LDS (the kernel is issue-bound)
+  __shared__ int2 s_col[32], s_row[CROP_ROWS];   // (adelta, bdelta) per column, (X0, Y0) per row
   __shared__ int4 s_win;                       // valid canvas window x_lo, x_hi, y_lo, y_hi
-  __shared__ int2 s_win_i;                     // rows whose 16-byte fetch windows stay inside the frame buffer
+  __shared__ int s_fast;                       // fast path usable for this frame
   struct __align__(16) Org { const uint8_t* p; long long pitch; };
   __shared__ Org s_org;                        // address of canvas pixel (0,0) in the frame, row pitch
+  __shared__ float s_lut[768];
   const int bt = blockIdx.z;
   const int b = bt / T_, t = bt - b * T_;
   const int tid = threadIdx.y * 32 + threadIdx.x;
-  if (tid < 40) {
+  if (kToClip)
+    for (int i = tid; i < 768; i += 256) s_lut[i] = __ldg(lut + i);
+  if (tid < 32 + CROP_ROWS) {
     const ClipGeom g = geom[b];
     // cv::invertAffineTransform (f64)
     double D = __dsub_rn(__dmul_rn(g.tfm[0], g.tfm[4]), __dmul_rn(g.tfm[1], g.tfm[3]));
@@ -91,11 +103,11 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
     } else {
       const double b1 = __dsub_rn(__dmul_rn(-A11, g.tfm[2]), __dmul_rn(A12, g.tfm[5]));
       const double b2 = __dsub_rn(__dmul_rn(-A21, g.tfm[2]), __dmul_rn(A22, g.tfm[5]));
-      const double yy = (double)(blockIdx.y * 8 + tid - 32);
+      const double yy = (double)(blockIdx.y * CROP_ROWS + tid - 32);
       s_row[tid - 32] = make_int2(cv_round(__dmul_rn(__dadd_rn(__dmul_rn(A12, yy), b1), 1024.0)) + 16,
                                   cv_round(__dmul_rn(__dadd_rn(__dmul_rn(A22, yy), b2), 1024.0)) + 16);
     }
-  } else if (tid == 40) {
+  } else if (tid == 32 + CROP_ROWS) {
     // canvas pixel (cx,cy) is frame pixel (cx+ltx, cy+lty); it exists iff it is inside the canvas AND inside this
     // frame's own big box clipped to the frame (faster_crop_align_xray.py:77-83)
     const ClipGeom g = geom[b];
@@ -105,16 +117,28 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
     const int bx2 = min(f.box[2], f.width), by2 = min(f.box[3], f.height);
     const int4 win = make_int4(max(0, bx1 - ltx), min(g.canvas_wh[0], bx2 - ltx), max(0, by1 - lty), min(g.canvas_wh[1], by2 - lty));
     s_win = win;
-    // frame rows 1 .. height-2; an empty range when the pitch is too short for the wide fetches
-    s_win_i = f.pitch >= 16 ? make_int2(max(win.z, 1 - lty), min(win.w, f.height - 1 - lty)) : make_int2(0, 0);
+    // fast path: window >= 2x2, inside frame rows 1 .. height-2 (the aligned 16-byte fetches of load6 then stay
+    // inside the frame buffer) and 32-bit byte offsets suffice
+    s_fast = (win.y - win.x >= 2 && win.w - win.z >= 2 && win.z + lty >= 1 && win.w + lty <= f.height - 1 && f.pitch >= 16 &&
+              f.pitch * (long long)(f.height + 1) < (1LL << 31))
+                 ? 1 : 0;
     s_org.p = f.data + (long long)lty * f.pitch + (long long)ltx * 3;
     s_org.pitch = f.pitch;
   }
   __syncthreads();
   const int x = blockIdx.x * 32 + threadIdx.x;
-  const int y = blockIdx.y * 8 + threadIdx.y;
-  if (x >= S || y >= S) return;
-  const int2 col = s_col[threadIdx.x], row = s_row[threadIdx.y];
+  if (x >= S) return;
+  const int2 col = s_col[threadIdx.x];
+  const int4 win = s_win;
+  const int xlo = win.x, xhi = win.y, ylo = win.z, yhi = win.w;
+  const Org o_ = s_org;
+  const uint8_t* org = o_.p;
+  const bool fast = s_fast != 0;
+#pragma unroll 1
+  for (int ry = threadIdx.y; ry < CROP_ROWS; ry += 8) {
+  const int y = blockIdx.y * CROP_ROWS + ry;
+  if (y >= S) break;
+  const int2 row = s_row[ry];
   const int X = (row.x + col.x) >> 5, Y = (row.y + col.y) >> 5;
   int sx = X >> 5, sy = Y >> 5;
   sx = max(-32768, min(32767, sx));
@@ -122,19 +146,33 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
   const int fx = X & 31, fy = Y & 31;
   // OpenCV's BilinearTab_i entry: rint(float(a/32) * float(b/32) * 32768) saturated to int16.  Both factors and the
   // product are exact in fp32, so this is the integer 32*a*b (<= 32768) with the one saturating case a = b = 32.
-  const int w00 = min((32 - fy) * (32 - fx) * 32, 32767), w01 = (32 - fy) * fx * 32;
-  const int w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
-  const int4 win = s_win;
-  const int2 win_i = s_win_i;
-  const int xlo = win.x, xhi = win.y, ylo = win.z, yhi = win.w;
-  const Org o_ = s_org;
-  const uint8_t* org = o_.p;
-  const long long pitch = o_.pitch;
+  int w00 = min((32 - fy) * (32 - fx) * 32, 32767), w01 = (32 - fy) * fx * 32;
+  int w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
   int acc[3] = {0, 0, 0};                 // in memory channel order; BGR frames are swapped at the end
-  if (sx >= xlo && sx + 1 < xhi && sy >= win_i.x && sy + 1 < win_i.y) {
-    // all four taps exist: two 6-byte fetches
-    const uint8_t* p = org + (long long)sy * pitch + (long long)sx * 3;
-    const uint2 r0 = load6(p), r1 = load6(p + pitch);
+  if (fast) {
+    const int pitch = (int)o_.pitch;
+    // taps outside the window weigh nothing
+    const bool vx0 = sx >= xlo && sx < xhi, vx1 = sx + 1 >= xlo && sx + 1 < xhi;
+    const bool vy0 = sy >= ylo && sy < yhi, vy1 = sy + 1 >= ylo && sy + 1 < yhi;
+    w00 = (vx0 && vy0) ? w00 : 0; w01 = (vx1 && vy0) ? w01 : 0;
+    w10 = (vx0 && vy1) ? w10 : 0; w11 = (vx1 && vy1) ? w11 : 0;
+    // fetch position clamped into the window; ddx / ddy = how far the wanted position is from the fetched one
+    const int csx = min(max(sx, xlo), xhi - 2), csy = min(max(sy, ylo), yhi - 2);
+    const int ddx = sx - csx, ddy = sy - csy;
+    const uint8_t* p = org + (csy * pitch + csx * 3);
+    uint2 r0 = load6(p), r1 = load6(p + pitch);
+    // rows: wanted (sy, sy+1) = fetched (csy, csy+1) shifted by ddy (only |ddy| <= 1 leaves a tap with weight)
+    const uint2 t0 = ddy == 1 ? r1 : r0, t1 = ddy == -1 ? r0 : r1;
+    r0 = t0; r1 = t1;
+    // columns: 6 bytes = pixels (csx, csx+1); ddx = +1: wanted pixel sx is the second one -> shift right by 3 bytes;
+    // ddx = -1: wanted pixel sx+1 is the first one -> shift left by 3 bytes
+    if (ddx == 1) {
+      r0 = make_uint2(__funnelshift_r(r0.x, r0.y, 24), r0.y >> 24);
+      r1 = make_uint2(__funnelshift_r(r1.x, r1.y, 24), r1.y >> 24);
+    } else if (ddx == -1) {
+      r0 = make_uint2(r0.x << 24, __funnelshift_l(r0.x, r0.y, 24));
+      r1 = make_uint2(r1.x << 24, __funnelshift_l(r1.x, r1.y, 24));
+    }
     const int a0 = r0.x & 255, a1 = (r0.x >> 8) & 255, a2 = (r0.x >> 16) & 255;
     const int b0 = r0.x >> 24, b1 = r0.y & 255, b2 = (r0.y >> 8) & 255;
     const int d0 = r1.x & 255, d1 = (r1.x >> 8) & 255, d2 = (r1.x >> 16) & 255;
@@ -143,6 +181,7 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
     acc[1] = w00 * a1 + w01 * b1 + w10 * d1 + w11 * e1;
     acc[2] = w00 * a2 + w01 * b2 + w10 * d2 + w11 * e2;
   } else {
+    const long long pitch = o_.pitch;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int cx = sx + (k & 1), cy = sy + (k >> 1);
@@ -163,15 +202,16 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
   if (kToClip) {
     T* q = dst + b * sB + t * sT + y * sH + x * sW;
     if (sC == 0) {
-      store_px4<T>(q, __ldg(lut + o[0]), __ldg(lut + 256 + o[1]), __ldg(lut + 512 + o[2]));
+      store_px4<T>(q, s_lut[o[0]], s_lut[256 + o[1]], s_lut[512 + o[2]]);
     } else {      // caller tensor viewed as [B,3,T,S,S] with its own strides (af_crop_pack)
-      store_1<T>(q, __ldg(lut + o[0]));
-      store_1<T>(q + sC, __ldg(lut + 256 + o[1]));
-      store_1<T>(q + 2 * sC, __ldg(lut + 512 + o[2]));
+      store_1<T>(q, s_lut[o[0]]);
+      store_1<T>(q + sC, s_lut[256 + o[1]]);
+      store_1<T>(q + 2 * sC, s_lut[512 + o[2]]);
     }
   } else {
     uint8_t* q = out_u8 + (((long long)bt * S + y) * S + x) * 3;
     q[0] = (uint8_t)o[0]; q[1] = (uint8_t)o[1]; q[2] = (uint8_t)o[2];
+  }
   }
 }
 
@@ -311,7 +351,7 @@ int crop_launch(const FrameDesc* frames, const ClipGeom* geom, int B, int T, int
                 uint8_t* out_u8, const ClipLayout* dst, const float mean[3], const float stdv[3],
                 cudaStream_t s) {
   if (B <= 0) return AF_OK;
-  dim3 grid((S + 31) / 32, (S + 7) / 8, B * T), block(32, 8);
+  dim3 grid((S + 31) / 32, (S + CROP_ROWS - 1) / CROP_ROWS, B * T), block(32, 8);
   Norm n = {{0, 0, 0}, {1, 1, 1}};
   if (mean && stdv)
     for (int c = 0; c < 3; ++c) { n.mean[c] = mean[c]; n.stdv[c] = stdv[c]; }
