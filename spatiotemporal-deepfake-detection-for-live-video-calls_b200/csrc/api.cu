@@ -143,6 +143,24 @@ static int upload_stem_direct(const af_conv_desc& d, bf16** out) {
   return AF_OK;
 }
 
+// FTCN-TT stem on the tensor cores (conv_rows.cu: ftcn_stem_umma_kernel): the k[5,1,1] conv as a GEMM over horizontal
+// pixel pairs.  W2[chunk = tap dt (5 = zero)][n][e]: n < 64 -> output channel n of the pair's EVEN pixel, weights on the
+// pair's elements e = 0..2; n >= 64 -> channel n-64 of the ODD pixel, weights on e = 4..6.
+static int upload_ftcn_stem_w2(const af_conv_desc& d, bf16** out) {
+  const size_t n = (size_t)6 * 128 * 8;
+  std::vector<bf16> w(n, __float2bfloat16_rn(0.f));
+  for (int co = 0; co < 64; ++co)
+    for (int c = 0; c < 3; ++c)
+      for (int dt = 0; dt < 5; ++dt) {
+        const bf16 v = __float2bfloat16_rn(d.weight[((size_t)co * 3 + c) * 5 + dt]);
+        w[((size_t)dt * 128 + co) * 8 + c] = v;
+        w[((size_t)dt * 128 + 64 + co) * 8 + 4 + c] = v;
+      }
+  AFB_CUDA(cudaMalloc(out, n * sizeof(bf16)));
+  AFB_CUDA(cudaMemcpy(*out, w.data(), n * sizeof(bf16), cudaMemcpyHostToDevice));
+  return AF_OK;
+}
+
 struct Dims { int T, H, W, C; long long elems() const { return (long long)T * H * W * C; } };
 
 static Dims conv_out(const ConvLayer& L, Dims in) {
@@ -165,6 +183,7 @@ struct af_engine {
   std::vector<ConvLayer> convs;
   ConvLayer stem_u;          // unfolded stem (bf16 engine), valid if has_stem_u
   bool has_stem_u = false;
+  bf16* ftcn_w2 = nullptr;   // FTCN-TT tensor-core stem weights [6][128][8] bf16 (upload_ftcn_stem_w2)
   bf16* stem_w35 = nullptr;  // direct stem weights [35 (dt,dy)][cout][32 (dx*4+c)] bf16
   int stem_direct = 0;       // 1 usable, 0 not tried / disabled, -1 tensor-map encode refused
   int stem = 0;
@@ -555,7 +574,16 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
       if (e->stem_pool2) {
         // FTCN-TT stem: conv k[5,1,1] + BN + max-pool 2x2 + ReLU + max-pool 3x3/2 in one kernel
         OpTrace tr(s);
-        rc = ftcn_stem_launch(e->clip, f0, fB, stem.w_simt, stem.bias, e->fbuf[1], s);
+        if (e->ftcn_w2 && e->conv_impl == 0) {         // tensor-core form (bf16 engine)
+          AFB_CUDA(cudaMemsetAsync(e->fbuf[1], 0, (size_t)fB * dpool.elems() * e->esz, s));
+          ProfRec prec(e, s);
+          const char* phys = (const char*)e->clip_raw + (long long)f0 * e->clip.sB * (long long)e->esz;
+          rc = ftcn_stem_umma_launch(phys, fB, e->T, e->S, e->ftcn_w2, stem.bias, e->fbuf[1], s);
+          prec.done(2, 2.0 * (double)fB * e->T * e->S * e->S * 64 * 15,
+                    (double)fB * ((double)(e->T + 4) * (e->S + 6) * (e->S + 8) * 4 + dpool.elems()) * 2.0);
+        } else {
+          rc = ftcn_stem_launch(e->clip, f0, fB, stem.w_simt, stem.bias, e->fbuf[1], s);
+        }
         if (rc) return rc;
         tr.done("ftcn stem k5x1x1 +pool2 +pool3/2", 2.0 * (double)fB * e->T * e->S * e->S * 64 * 15,
                 (double)fB * ((double)e->T * e->S * e->S * 4 + dpool.elems()) * e->esz);
@@ -732,6 +760,7 @@ af_status af_destroy(af_handle h) {
   for (auto& L : h->convs) free_layer(L);
   free_layer(h->stem_u);
   if (h->stem_w35) cudaFree(h->stem_w35);
+  if (h->ftcn_w2) cudaFree(h->ftcn_w2);
   for (float* fb : h->fused_bias)
     if (fb) cudaFree(fb);
   free_workspace(h);
@@ -833,6 +862,10 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
       set_error("af_create: stem_pool2 needs the FTCN-TT stem (3->64, k[5,1,1], s1, p[2,0,0]) and clip_s %% 4 == 0");
       return AF_ERR_INVALID;
     }
+    if (e->is_bf16 && e->S % 32 == 0 && getenv("AFB200_NO_FTCN_UMMA") == nullptr) {
+      int rc = upload_ftcn_stem_w2(sc, &e->ftcn_w2);
+      if (rc) return (af_status)rc;
+    }
   }
   for (int bi = 0; bi < w->n_blocks; ++bi)
     if (w->blocks[bi].spatial_pool && w->blocks[bi].branch1 < 0) {
@@ -867,14 +900,15 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
     AFB_CUDA(cudaMalloc(&e->fc_w, w->feature_dim * sizeof(float)));
     AFB_CUDA(cudaMemcpy(e->fc_w, w->fc_weight, w->feature_dim * sizeof(float), cudaMemcpyHostToDevice));
   }
-  // padded clip buffer: T+4 frames, S+6 rows, S+8 columns, 4 channels; pads stay zero forever
+  // padded clip buffer: T+4 frames, S+6 rows, S+8 columns, 4 channels; pads stay zero forever.  The logical origin is at
+  // padded (frame 2, row 3, column 3) - column 4 for the FTCN-TT variant, whose stem reads 16-byte-aligned pixel PAIRS
   const long long Tp = e->T + 4, Hp = e->S + 6, Wp = e->S + 8;
   const size_t clip_bytes = (size_t)e->max_batch * Tp * Hp * Wp * 4 * e->esz;
   AFB_CUDA(cudaMalloc(&e->clip_raw, clip_bytes));
   AFB_CUDA(cudaMemset(e->clip_raw, 0, clip_bytes));
   e->clip.sW = 4; e->clip.sH = Wp * 4; e->clip.sT = Hp * Wp * 4; e->clip.sB = Tp * Hp * Wp * 4;
   e->clip.T = e->T; e->clip.S = e->S; e->clip.is_bf16 = e->is_bf16;
-  e->clip.base = (char*)e->clip_raw + (2 * e->clip.sT + 3 * e->clip.sH + 3 * e->clip.sW) * (long long)e->esz;
+  e->clip.base = (char*)e->clip_raw + (2 * e->clip.sT + 3 * e->clip.sH + (e->stem_pool2 ? 4 : 3) * e->clip.sW) * (long long)e->esz;
   int rc = plan_workspace(e);
   if (rc) return (af_status)rc;
   if (e->cb_back > e->max_batch) e->cb_back = e->max_batch;

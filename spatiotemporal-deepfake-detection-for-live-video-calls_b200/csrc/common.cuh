@@ -86,6 +86,8 @@ int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const vo
 bool conv_bc_fused_supported(const ConvProblem& b, const ConvProblem& c);
 int conv_bc_fused_launch(const ConvProblem& b, const ConvProblem& c, cudaStream_t s);
 int conv_bc_fused_init();
+int ftcn_stem_umma_launch(const void* clip_phys, int B, int T, int S, const void* w2, const float* bias, void* y,
+                          cudaStream_t s);
 // pool_head.cu
 int maxpool_spatial_launch(const void* x, void* y, int B, int T, int H, int W, int C, bool is_bf16,
                            cudaStream_t s);   // k[1,3,3] s[1,2,2] p[0,1,1]

@@ -67,10 +67,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 
 // One 8x16-pixel output tile of the epilogue: accumulator (TMEM, fp32) -> +bias, ReLU -> bf16 tile in swizzled
 // smem -> either a 4-D TMA store or the fused 3x3/2 max-pool.  Called by all 128 threads of one epilogue group.
+__device__ __forceinline__ void rows_store_or_pool(const RowsParams& p, const CUtensorMap* tm_y_ptr, uint8_t* sout, int eg, int et,
+                                                   int xt, int yt, int r);
+
 __device__ __forceinline__ void rows_epilogue_tile(const RowsParams& p, const CUtensorMap* tm_y_ptr, uint8_t* sout,
                                                    const float* bias_s, uint32_t taddr, int eg, int et, int row, int xt,
                                                    int yt, int r) {
-  const CUtensorMap& tm_y = *tm_y_ptr;
   if (et == 0) tma_store_wait_read<0>();
   epi_bar_sync(eg);
   uint32_t v[64];
@@ -91,6 +93,14 @@ __device__ __forceinline__ void rows_epilogue_tile(const RowsParams& p, const CU
     for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
     *reinterpret_cast<uint4*>(sout + row * 128 + ((q ^ (row & 7)) << 4)) = o;
   }
+  rows_store_or_pool(p, tm_y_ptr, sout, eg, et, xt, yt, r);
+}
+
+// Second half of the epilogue: the finished 8x16-pixel bf16 tile in swizzled smem -> a 4-D TMA store, or the fused
+// 3x3/2 max-pool.  Called by all 128 threads of one epilogue group.
+__device__ __forceinline__ void rows_store_or_pool(const RowsParams& p, const CUtensorMap* tm_y_ptr, uint8_t* sout, int eg, int et,
+                                                   int xt, int yt, int r) {
+  const CUtensorMap& tm_y = *tm_y_ptr;
   if (!p.pool) {
     fence_proxy_async_smem();
     epi_bar_sync(eg);
@@ -523,6 +533,189 @@ stem_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   }
 }
 
+
+// K6 (FTCN-TT plugin): the temporal-only stem on the tensor cores.
+//   Conv3d(3->64, k[5,1,1], p[2,0,0]) + folded BN + MaxPool3d(1,2,2) + ReLU + MaxPool3d k[1,3,3] s[1,2,2] p[0,1,1]
+//   (i3d_temporal_var_fix_dropout_tt_cfg.py:207-289 applied to stem_helper.py:156-178)
+// K = 5 taps x 3 channels is far too shallow for an MMA as it stands, so the GEMM is laid out around the padded NDHWC4
+// clip (left pad 4 for this variant: pixel PAIRS are 16-byte aligned):
+//   A row    = one horizontal pixel pair of one input row: 2 x 4 bf16 = 16 bytes = exactly one K chunk of the
+//              un-swizzled K-major operand layout; the 5 (+1 zero-weight) temporal taps are 6 such chunks, each a 2 KB
+//              TMA box of its own frame: K = 48, three K=16 MMAs
+//   N = 128  = 64 channels for the pair's even pixel (weights on chunk elements 0..2) | 64 for its odd pixel (4..6)
+//   M = 128  = 8 pairs x 16 rows of ONE ROW PARITY; the other parity is a second accumulator
+// so the four pixels of every 2x2 pooling window are the same accumulator ROW (= epilogue thread) in four column /
+// accumulator ranges: the first max-pool is four register-local fmaxf per channel.  The pooled 8x16 tile (112x112 level)
+// then goes through the same smem tile + 3x3/2 pooling epilogue as the I3D stem (rows_store_or_pool).
+constexpr int FT_BOX_BYTES = 128 * 16;                 // one (frame, row parity) box: 128 rows x 16 bytes
+constexpr int FT_STAGE_BYTES = 12 * FT_BOX_BYTES;      // 6 frames x 2 row parities
+constexpr int FT_W_BYTES = 6 * 128 * 16;               // [6 chunks][128 rows][8 bf16]
+constexpr int FT_STAGES = 4;
+
+// un-swizzled K-major operand: core matrix = 8 rows x 16 bytes contiguous; SBO = distance between 8-row groups,
+// LBO = distance between the two 16-byte K chunks of one K=16 MMA (cute/atom/mma_traits_sm100.hpp, LayoutType::INTERLEAVE)
+__device__ __forceinline__ uint64_t make_smem_desc_noswz(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__global__ void __launch_bounds__(RB_THREADS, 1)
+ftcn_stem_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const bf16* __restrict__ w2, const RowsParams p,
+                      int frames_padded) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem_w + FT_W_BYTES;
+  uint8_t* smem_out = smem_a + FT_STAGES * FT_STAGE_BYTES;
+  float* bias_s = reinterpret_cast<float*>(smem_out + 2 * RB_OUT_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + RB_N);
+  uint64_t* empty_bar = full_bar + FT_STAGES;
+  uint64_t* tmem_full = empty_bar + FT_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 512;                  // 2 tiles in flight x (2 row parities x 128 columns)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    for (int i = 0; i < FT_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+    fence_barrier_init();
+  } else if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // weights (constants, 12 KB, already in operand layout) and bias: plain copies
+  for (int i = threadIdx.x; i < FT_W_BYTES / 16; i += RB_THREADS)
+    reinterpret_cast<uint4*>(smem_w)[i] = __ldg(reinterpret_cast<const uint4*>(w2) + i);
+  if (threadIdx.x < RB_N) bias_s[threadIdx.x] = __ldg(p.bias + threadIdx.x);
+  fence_proxy_async_smem();                            // the tensor core reads smem_w through the async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  pdl_wait_prior_grid();
+
+  if (warp == 0) {
+    // ===================================================== TMA producer: 12 boxes per tile
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int r = tile;
+      const int xt = r % p.x_tiles; r /= p.x_tiles;
+      const int yt = r % p.y_tiles; r /= p.y_tiles;
+      const int to = r % p.To;
+      const int b = r / p.To;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&full_bar[stage], FT_STAGE_BYTES);
+        uint8_t* sa = smem_a + stage * FT_STAGE_BYTES;
+        // clip view: (8 el of a pixel pair, pair, row parity, row pair, padded frame of any clip).  Logical pixel x
+        // sits at padded x + 4, logical row y at padded y + 3: the tile's even logical rows are padded rows of parity
+        // 1 starting at row pair 16*yt + 1, its odd ones parity 0 starting at row pair 16*yt + 2; output frame `to`
+        // reads padded frames to .. to+4 (chunk 5 meets zero weights but must hold finite data: frame to+5)
+        const int f0 = b * frames_padded + to;
+        for (int par = 0; par < 2; ++par)
+          for (int f = 0; f < 6; ++f)
+            tma_load_tile_5d(sa + (par * 6 + f) * FT_BOX_BYTES, &tm_a, &full_bar[stage], 0, xt * RB_X + 2, 1 - par,
+                             yt * RB_R + 1 + par, f0 + f);
+      }
+      __syncwarp();
+      if (++stage == FT_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer: 2 accumulators x 3 MMAs (128 x 128 x 16) per tile
+    constexpr uint32_t idesc = make_idesc(128);
+    const uint32_t w_addr = smem_u32(smem_w);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem_a + stage * FT_STAGE_BYTES);
+      if (elect_one()) {
+#pragma unroll
+        for (int par = 0; par < 2; ++par)
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            umma_bf16(tmem_base + as * 256 + par * 128,
+                      make_smem_desc_noswz(a_addr + (par * 6 + 2 * j) * FT_BOX_BYTES, FT_BOX_BYTES, 128),
+                      make_smem_desc_noswz(w_addr + 2 * j * FT_BOX_BYTES, FT_BOX_BYTES, 128), idesc, j != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tmem_full[as]);
+      }
+      __syncwarp();
+      if (++stage == FT_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===================================================== epilogue: two warpgroups on alternate tiles
+    const int eg = (warp - 2) >> 2;
+    const int et = (threadIdx.x - 64) & 127;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    uint8_t* sout = smem_out + eg * RB_OUT_BYTES;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != eg) continue;
+      const int as = it & 1;
+      mbar_wait(&tmem_full[as], (it >> 1) & 1);
+      tc_fence_after();
+      int r = tile;
+      const int xt = r % p.x_tiles; r /= p.x_tiles;
+      const int yt = r % p.y_tiles; r /= p.y_tiles;   // r = b*To + to
+      epi_bar_sync(eg);                               // every thread is done reading the previous tile in `sout`
+      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 256;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {                   // 16 channels at a time: 4 window pixels x 16 accumulators
+        uint32_t va[16], vb[16], vc[16], vd[16];
+        TMEM_LD_32x32b_x16(tbase + q * 16, va);             // even row, even pixel
+        TMEM_LD_32x32b_x16(tbase + 64 + q * 16, vb);        // even row, odd pixel
+        TMEM_LD_32x32b_x16(tbase + 128 + q * 16, vc);       // odd row, even pixel
+        TMEM_LD_32x32b_x16(tbase + 192 + q * 16, vd);       // odd row, odd pixel
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint4 o;
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float f[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int i = h * 8 + 2 * e + u;
+              const float m = fmaxf(fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])),
+                                    fmaxf(__uint_as_float(vc[i]), __uint_as_float(vd[i])));
+              f[u] = fmaxf(m + bias_s[q * 16 + i], 0.f);
+            }
+            o2[e] = __floats2bfloat162_rn(f[0], f[1]);
+          }
+          const int chunk = q * 2 + h;
+          *reinterpret_cast<uint4*>(sout + row * 128 + ((chunk ^ (row & 7)) << 4)) = o;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+      rows_store_or_pool(p, &tm_a, sout, eg, et, xt, yt, r);      // pool mode: the tensor map is not used
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -559,6 +752,7 @@ int conv_rows_init() {
     AFB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
     AFB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
     AFB_CUDA(cudaFuncSetAttribute(stem_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
+    AFB_CUDA(cudaFuncSetAttribute(ftcn_stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rows_max_smem));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   return AF_OK;
@@ -709,6 +903,42 @@ int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const vo
     cfg.dynamicSmemBytes = dyn;
     AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_rows_kernel<true>, ta, tw, ty, rp));
   }
+  ++g_launches;
+  AFB_CUDA(cudaGetLastError());
+  return AF_OK;
+}
+
+// FTCN-TT stem on the tensor cores (ftcn_stem_umma_kernel).  clip_phys: padded NDHWC4 bf16 clip [B, T+4, S+6, S+8, 4]
+// whose logical pixel (0,0) sits at padded (3, 4); w2: [6][128][8] bf16 in operand layout (api.cu: upload_ftcn_stem_w2);
+// y: ZERO-INITIALISED pooled output [B*T, S/4, S/4, 64].
+int ftcn_stem_umma_launch(const void* clip_phys, int B, int T, int S, const void* w2, const float* bias, void* y, cudaStream_t s) {
+  if (!g_rows_encode) { set_error("ftcn_stem_umma: not initialised"); return AF_ERR_INVALID; }
+  const int M2 = S / 2;                                  // 112-level map
+  if ((S % 32) != 0) { set_error("ftcn_stem_umma: clip size %d is not a multiple of 32", S); return AF_ERR_INVALID; }
+  const int Tp = T + 4, Hp = S + 6, Wp = S + 8;
+  RowsParams rp = {};
+  rp.bias = bias; rp.B = B; rp.To = T; rp.Ho = M2; rp.Wo = M2; rp.relu = 1;
+  rp.x_tiles = M2 / RB_X; rp.y_tiles = (M2 + RB_R - 1) / RB_R;
+  rp.num_tiles = B * T * rp.y_tiles * rp.x_tiles;
+  rp.pool = 1; rp.pool_out = (bf16*)y;
+  alignas(64) CUtensorMap ta;
+  {
+    const cuuint64_t rowpitch = (cuuint64_t)Wp * 8;
+    cuuint64_t dims[5] = {8, (cuuint64_t)Wp / 2, 2, (cuuint64_t)Hp / 2, (cuuint64_t)Tp * B};
+    cuuint64_t strides[4] = {16, rowpitch, 2 * rowpitch, rowpitch * Hp};
+    cuuint32_t box[5] = {8, RB_X, 1, RB_R, 1};
+    int rc = encode_nd(&ta, clip_phys, 5, dims, strides, box, "ftcn stem A (pixel pairs)", CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
+  const int dyn = FT_W_BYTES + FT_STAGES * FT_STAGE_BYTES + 2 * RB_OUT_BYTES + RB_N * 4 + 16 * 8 + 16 + 1024;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(limit_grid(rp.num_tiles, g_rows_sms));
+  cfg.blockDim = dim3(RB_THREADS); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  AFB_CUDA(cudaLaunchKernelEx(&cfg, ftcn_stem_umma_kernel, ta, (const bf16*)w2, rp, Tp));
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;

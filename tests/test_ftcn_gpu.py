@@ -97,3 +97,29 @@ def test_ftcn_classifier_plugin_interface(dev, sd, oracle_out):
     assert len(seen) == 1 and tuple(seen[0].shape) == (2, 1024)           # the hook saw the last Linear's input
     out2 = clf(x[:2].to(dev))                                            # fused head path (no hook)
     assert (out2["final_output"] - out["final_output"]).abs().max().item() <= 1e-5
+
+
+def test_ftcn_tensor_core_stem_elementwise(dev, sd, clips):
+    """Stage s1 of the bf16 engine (ftcn_stem_umma_kernel: conv k[5,1,1] + BN + MaxPool(1,2,2) + ReLU + MaxPool 3x3/2 on the
+    tensor cores) element by element against fp32 torch on the same bf16-rounded clip and folded weights: one bf16 ulp."""
+    import torch.nn.functional as F
+    eng = afb200.Engine(sd, max_batch=3, precision="bf16", variant="ftcn_tt")
+    eng.set_option("keep_stages", 1)
+    x = synthetic.normalise_clip(clips)
+    eng.forward(x.to(dev))
+    got = eng.get_stage(1).cpu()                                            # fp32 NCTHW [3,64,32,56,56]
+    w, b = (torch.from_numpy(a) for a in afb200.fold_conv_bn(sd, afb200.arch.stem_spec_for("ftcn_tt")))
+    xr = x.to(torch.bfloat16).float()
+    y = F.conv3d(xr, w.to(torch.bfloat16).float(), b, 1, (2, 0, 0))
+    y = F.relu(F.max_pool3d(y, (1, 2, 2), (1, 2, 2)))
+    want = F.max_pool3d(y, (1, 3, 3), (1, 2, 2), (0, 1, 1)).to(torch.bfloat16).float()
+    assert got.shape == want.shape
+    diff = (got - want).abs()
+    tol = 2.0 ** -7 * max(1.0, want.abs().max().item()) + 1e-3
+    assert diff.max().item() <= tol, (diff.max().item(), tol)
+    assert (diff > 2.0 ** -8 * want.abs().clamp_min(1.0) + 1e-3).float().mean().item() < 1e-3
+    # tile borders of the pooled 8x16 tiles, clip-end frames, image border
+    assert diff[:, :, :, ::8].max().item() <= tol and diff[:, :, :, :, ::4].max().item() <= tol
+    assert diff[:, :, 0].max().item() <= tol and diff[:, :, -1].max().item() <= tol
+    assert want[:, :, :, 8, 4].abs().max().item() > 0.05
+    eng.close()
