@@ -901,14 +901,15 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
     AFB_CUDA(cudaMemcpy(e->fc_w, w->fc_weight, w->feature_dim * sizeof(float), cudaMemcpyHostToDevice));
   }
   // padded clip buffer: T+4 frames, S+6 rows, S+8 columns, 4 channels; pads stay zero forever.  The logical origin is at
-  // padded (frame 2, row 3, column 3) - column 4 for the FTCN-TT variant, whose stem reads 16-byte-aligned pixel PAIRS
+  // padded (frame 2, row 3, column 3) - (frame 2, row 4, column 4) for the FTCN-TT variant, whose stem reads
+  // 16-byte-aligned pixel pairs of even-aligned row pairs
   const long long Tp = e->T + 4, Hp = e->S + 6, Wp = e->S + 8;
   const size_t clip_bytes = (size_t)e->max_batch * Tp * Hp * Wp * 4 * e->esz;
   AFB_CUDA(cudaMalloc(&e->clip_raw, clip_bytes));
   AFB_CUDA(cudaMemset(e->clip_raw, 0, clip_bytes));
   e->clip.sW = 4; e->clip.sH = Wp * 4; e->clip.sT = Hp * Wp * 4; e->clip.sB = Tp * Hp * Wp * 4;
   e->clip.T = e->T; e->clip.S = e->S; e->clip.is_bf16 = e->is_bf16;
-  e->clip.base = (char*)e->clip_raw + (2 * e->clip.sT + 3 * e->clip.sH + (e->stem_pool2 ? 4 : 3) * e->clip.sW) * (long long)e->esz;
+  e->clip.base = (char*)e->clip_raw + (2 * e->clip.sT + (e->stem_pool2 ? 4 : 3) * (e->clip.sH + e->clip.sW)) * (long long)e->esz;
   int rc = plan_workspace(e);
   if (rc) return (af_status)rc;
   if (e->cb_back > e->max_batch) e->cb_back = e->max_batch;

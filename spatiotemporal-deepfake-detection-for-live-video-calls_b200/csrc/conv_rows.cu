@@ -116,20 +116,24 @@ __device__ __forceinline__ void rows_store_or_pool(const RowsParams& p, const CU
     epi_bar_sync(eg);
     const int Hp = p.Ho >> 1, Wp = p.Wo >> 1;
     const int py0 = yt * (RB_R / 2), px0 = xt * (RB_X / 2);
+    const int ly_max = min(RB_R - 1, p.Ho - 1 - yt * RB_R);      // rows past the image hold garbage
     for (int item = et; item < 45 * 8; item += 128) {
       const int ch = item & 7, pos = item >> 3;
       const int k = pos / 5, j = pos - k * 5;
       const int py = py0 + k, px = px0 + j;
       if (py >= Hp || px >= Wp) continue;
-      const int ly0 = k == 0 ? 0 : 2 * k - 1, ly1 = k == 8 ? 15 : 2 * k + 1;
-      const int lx0 = j == 0 ? 0 : 2 * j - 1, lx1 = j == 4 ? 7 : 2 * j + 1;
+      // window = conv rows 2k-1..2k+1 x columns 2j-1..2j+1 clipped to the tile: fully unrolled, loads predicated
       uint4 m = make_uint4(0u, 0u, 0u, 0u);
       __nv_bfloat162* m2 = reinterpret_cast<__nv_bfloat162*>(&m);
-      for (int ly = ly0; ly <= ly1; ++ly) {
-        if (yt * RB_R + ly >= p.Ho) break;             // rows past the image hold garbage
-        for (int lx = lx0; lx <= lx1; ++lx) {
-          const int rr = ly * RB_X + lx;
-          const uint4 t = *reinterpret_cast<const uint4*>(sout + rr * 128 + ((ch ^ (rr & 7)) << 4));
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int ly = 2 * k - 1 + dy;
+        if (ly < 0 || ly > ly_max) continue;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int lx = 2 * j - 1 + dx;
+          if (lx < 0 || lx >= RB_X) continue;
+          const uint4 t = *reinterpret_cast<const uint4*>(sout + ly * (RB_X * 128) + lx * 128 + ((ch ^ lx) << 4));
           const __nv_bfloat162* t2 = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
           for (int e = 0; e < 4; ++e) m2[e] = __hmax2(m2[e], t2[e]);
@@ -538,17 +542,18 @@ stem_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 //   Conv3d(3->64, k[5,1,1], p[2,0,0]) + folded BN + MaxPool3d(1,2,2) + ReLU + MaxPool3d k[1,3,3] s[1,2,2] p[0,1,1]
 //   (i3d_temporal_var_fix_dropout_tt_cfg.py:207-289 applied to stem_helper.py:156-178)
 // K = 5 taps x 3 channels is far too shallow for an MMA as it stands, so the GEMM is laid out around the padded NDHWC4
-// clip (left pad 4 for this variant: pixel PAIRS are 16-byte aligned):
+// clip (origin at padded row 4 / column 4 for this variant: pixel PAIRS are 16-byte aligned and row pairs start even):
 //   A row    = one horizontal pixel pair of one input row: 2 x 4 bf16 = 16 bytes = exactly one K chunk of the
-//              un-swizzled K-major operand layout; the 5 (+1 zero-weight) temporal taps are 6 such chunks, each a 2 KB
-//              TMA box of its own frame: K = 48, three K=16 MMAs
+//              un-swizzled K-major operand layout; the 5 (+1 zero-weight) temporal taps are 6 such chunks, one per
+//              frame: K = 48, three K=16 MMAs.  ONE 5-D TMA box brings all 6 frames x 32 rows x 8 pairs of a tile
 //   N = 128  = 64 channels for the pair's even pixel (weights on chunk elements 0..2) | 64 for its odd pixel (4..6)
-//   M = 128  = 8 pairs x 16 rows of ONE ROW PARITY; the other parity is a second accumulator
+//   M = 128  = 8 pairs x 16 rows of ONE ROW PARITY (the box interleaves the parities in 8-row groups, so a parity is
+//              the 8-row groups 256 bytes apart: the descriptor's SBO); the other parity is a second accumulator
 // so the four pixels of every 2x2 pooling window are the same accumulator ROW (= epilogue thread) in four column /
 // accumulator ranges: the first max-pool is four register-local fmaxf per channel.  The pooled 8x16 tile (112x112 level)
 // then goes through the same smem tile + 3x3/2 pooling epilogue as the I3D stem (rows_store_or_pool).
-constexpr int FT_BOX_BYTES = 128 * 16;                 // one (frame, row parity) box: 128 rows x 16 bytes
-constexpr int FT_STAGE_BYTES = 12 * FT_BOX_BYTES;      // 6 frames x 2 row parities
+constexpr int FT_FRAME_BYTES = 256 * 16;               // one frame of a tile: 16 row pairs x 2 parities x 8 pixel pairs x 16 B
+constexpr int FT_STAGE_BYTES = 6 * FT_FRAME_BYTES;     // 6 frames
 constexpr int FT_W_BYTES = 6 * 128 * 16;               // [6 chunks][128 rows][8 bf16]
 constexpr int FT_STAGES = 4;
 
@@ -615,16 +620,12 @@ ftcn_stem_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const bf16* __re
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
         mbar_expect_tx(&full_bar[stage], FT_STAGE_BYTES);
-        uint8_t* sa = smem_a + stage * FT_STAGE_BYTES;
-        // clip view: (8 el of a pixel pair, pair, row parity, row pair, padded frame of any clip).  Logical pixel x
-        // sits at padded x + 4, logical row y at padded y + 3: the tile's even logical rows are padded rows of parity
-        // 1 starting at row pair 16*yt + 1, its odd ones parity 0 starting at row pair 16*yt + 2; output frame `to`
-        // reads padded frames to .. to+4 (chunk 5 meets zero weights but must hold finite data: frame to+5)
-        const int f0 = b * frames_padded + to;
-        for (int par = 0; par < 2; ++par)
-          for (int f = 0; f < 6; ++f)
-            tma_load_tile_5d(sa + (par * 6 + f) * FT_BOX_BYTES, &tm_a, &full_bar[stage], 0, xt * RB_X + 2, 1 - par,
-                             yt * RB_R + 1 + par, f0 + f);
+        // clip view: (8 el of a pixel pair, pair, row parity, row pair, padded frame of any clip).  Logical pixel
+        // (y, x) sits at padded (y + 4, x + 4): pair x/2 + 2, row pair y/2 + 2, parity y & 1.  Output frame `to` reads
+        // padded frames to .. to+4 (chunk 5 meets zero weights but must hold finite data: frame to+5, zero-filled by
+        // TMA when it lies past the last clip)
+        tma_load_tile_5d(smem_a + stage * FT_STAGE_BYTES, &tm_a, &full_bar[stage], 0, xt * RB_X + 2, 0, yt * RB_R + 2,
+                         b * frames_padded + to);
       }
       __syncwarp();
       if (++stage == FT_STAGES) { stage = 0; phase ^= 1; }
@@ -648,8 +649,8 @@ ftcn_stem_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const bf16* __re
 #pragma unroll
           for (int j = 0; j < 3; ++j)
             umma_bf16(tmem_base + as * 256 + par * 128,
-                      make_smem_desc_noswz(a_addr + (par * 6 + 2 * j) * FT_BOX_BYTES, FT_BOX_BYTES, 128),
-                      make_smem_desc_noswz(w_addr + 2 * j * FT_BOX_BYTES, FT_BOX_BYTES, 128), idesc, j != 0 ? 1u : 0u);
+                      make_smem_desc_noswz(a_addr + 2 * j * FT_FRAME_BYTES + par * 128, FT_FRAME_BYTES, 256),
+                      make_smem_desc_noswz(w_addr + 2 * j * 2048, 2048, 128), idesc, j != 0 ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
         umma_commit(&tmem_full[as]);
       }
@@ -674,14 +675,23 @@ ftcn_stem_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const bf16* __re
       const int yt = r % p.y_tiles; r /= p.y_tiles;   // r = b*To + to
       epi_bar_sync(eg);                               // every thread is done reading the previous tile in `sout`
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 256;
+      // 16 channels at a time: 4 window pixels x 16 accumulators; the loads of the next 16 are in flight while these
+      // are reduced (two register sets)
+      uint32_t v[2][4][16];
+      TMEM_LD_32x32b_x16(tbase, v[0][0]);             // even row, even pixel
+      TMEM_LD_32x32b_x16(tbase + 64, v[0][1]);        // even row, odd pixel
+      TMEM_LD_32x32b_x16(tbase + 128, v[0][2]);       // odd row, even pixel
+      TMEM_LD_32x32b_x16(tbase + 192, v[0][3]);       // odd row, odd pixel
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {                   // 16 channels at a time: 4 window pixels x 16 accumulators
-        uint32_t va[16], vb[16], vc[16], vd[16];
-        TMEM_LD_32x32b_x16(tbase + q * 16, va);             // even row, even pixel
-        TMEM_LD_32x32b_x16(tbase + 64 + q * 16, vb);        // even row, odd pixel
-        TMEM_LD_32x32b_x16(tbase + 128 + q * 16, vc);       // odd row, even pixel
-        TMEM_LD_32x32b_x16(tbase + 192 + q * 16, vd);       // odd row, odd pixel
+      for (int q = 0; q < 4; ++q) {
         tmem_ld_wait();
+        if (q + 1 < 4) {
+          TMEM_LD_32x32b_x16(tbase + (q + 1) * 16, v[(q + 1) & 1][0]);
+          TMEM_LD_32x32b_x16(tbase + 64 + (q + 1) * 16, v[(q + 1) & 1][1]);
+          TMEM_LD_32x32b_x16(tbase + 128 + (q + 1) * 16, v[(q + 1) & 1][2]);
+          TMEM_LD_32x32b_x16(tbase + 192 + (q + 1) * 16, v[(q + 1) & 1][3]);
+        }
+        const uint32_t(*w)[16] = v[q & 1];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint4 o;
@@ -692,8 +702,8 @@ ftcn_stem_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const bf16* __re
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const int i = h * 8 + 2 * e + u;
-              const float m = fmaxf(fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])),
-                                    fmaxf(__uint_as_float(vc[i]), __uint_as_float(vd[i])));
+              const float m = fmaxf(fmaxf(__uint_as_float(w[0][i]), __uint_as_float(w[1][i])),
+                                    fmaxf(__uint_as_float(w[2][i]), __uint_as_float(w[3][i])));
               f[u] = fmaxf(m + bias_s[q * 16 + i], 0.f);
             }
             o2[e] = __floats2bfloat162_rn(f[0], f[1]);
@@ -909,7 +919,7 @@ int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const vo
 }
 
 // FTCN-TT stem on the tensor cores (ftcn_stem_umma_kernel).  clip_phys: padded NDHWC4 bf16 clip [B, T+4, S+6, S+8, 4]
-// whose logical pixel (0,0) sits at padded (3, 4); w2: [6][128][8] bf16 in operand layout (api.cu: upload_ftcn_stem_w2);
+// whose logical pixel (0,0) sits at padded (4, 4); w2: [6][128][8] bf16 in operand layout (api.cu: upload_ftcn_stem_w2);
 // y: ZERO-INITIALISED pooled output [B*T, S/4, S/4, 64].
 int ftcn_stem_umma_launch(const void* clip_phys, int B, int T, int S, const void* w2, const float* bias, void* y, cudaStream_t s) {
   if (!g_rows_encode) { set_error("ftcn_stem_umma: not initialised"); return AF_ERR_INVALID; }
@@ -926,7 +936,7 @@ int ftcn_stem_umma_launch(const void* clip_phys, int B, int T, int S, const void
     const cuuint64_t rowpitch = (cuuint64_t)Wp * 8;
     cuuint64_t dims[5] = {8, (cuuint64_t)Wp / 2, 2, (cuuint64_t)Hp / 2, (cuuint64_t)Tp * B};
     cuuint64_t strides[4] = {16, rowpitch, 2 * rowpitch, rowpitch * Hp};
-    cuuint32_t box[5] = {8, RB_X, 1, RB_R, 1};
+    cuuint32_t box[5] = {8, RB_X, 2, RB_R, 6};
     int rc = encode_nd(&ta, clip_phys, 5, dims, strides, box, "ftcn stem A (pixel pairs)", CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
   }
