@@ -134,6 +134,19 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
   const Org o_ = s_org;
   const uint8_t* org = o_.p;
   const bool fast = s_fast != 0;
+  // INTERIOR blocks (block-uniform): the source coordinates are an affine function of (x, y) up to rounding, so if the
+  // four corner pixels of the block sample at least one pixel inside the valid window, every pixel's four taps are
+  // inside it and the validity / clamp / shift-back logic of the general fast path is not needed at all.
+  bool interior = fast;
+  if (fast) {
+    const int cx1 = min(31, S - 1 - (int)blockIdx.x * 32), ry1 = min(CROP_ROWS - 1, S - 1 - (int)blockIdx.y * CROP_ROWS);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int2 c = s_col[(k & 1) ? cx1 : 0], r = s_row[(k >> 1) ? ry1 : 0];
+      const int qx = (r.x + c.x) >> 10, qy = (r.y + c.y) >> 10;
+      interior = interior && qx - 1 >= xlo && qx + 2 < xhi && qy - 1 >= ylo && qy + 2 < yhi;
+    }
+  }
 #pragma unroll 1
   for (int ry = threadIdx.y; ry < CROP_ROWS; ry += 8) {
   const int y = blockIdx.y * CROP_ROWS + ry;
@@ -149,7 +162,18 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
   int w00 = min((32 - fy) * (32 - fx) * 32, 32767), w01 = (32 - fy) * fx * 32;
   int w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
   int acc[3] = {0, 0, 0};                 // in memory channel order; BGR frames are swapped at the end
-  if (fast) {
+  if (interior) {
+    const int pitch = (int)o_.pitch;
+    const uint8_t* p = org + (sy * pitch + sx * 3);
+    const uint2 r0 = load6(p), r1 = load6(p + pitch);
+    const int a0 = r0.x & 255, a1 = (r0.x >> 8) & 255, a2 = (r0.x >> 16) & 255;
+    const int b0 = r0.x >> 24, b1 = r0.y & 255, b2 = (r0.y >> 8) & 255;
+    const int d0 = r1.x & 255, d1 = (r1.x >> 8) & 255, d2 = (r1.x >> 16) & 255;
+    const int e0 = r1.x >> 24, e1 = r1.y & 255, e2 = (r1.y >> 8) & 255;
+    acc[0] = w00 * a0 + w01 * b0 + w10 * d0 + w11 * e0;
+    acc[1] = w00 * a1 + w01 * b1 + w10 * d1 + w11 * e1;
+    acc[2] = w00 * a2 + w01 * b2 + w10 * d2 + w11 * e2;
+  } else if (fast) {
     const int pitch = (int)o_.pitch;
     // taps outside the window weigh nothing
     const bool vx0 = sx >= xlo && sx < xhi, vx1 = sx + 1 >= xlo && sx + 1 < xhi;
@@ -196,7 +220,7 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
   }
   int o[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) o[c] = max(0, min(255, (acc[c] + 16384) >> 15));
+  for (int c = 0; c < 3; ++c) o[c] = (acc[c] + 16384) >> 15;      // in [0,255] by construction: weights >= 0, sum <= 2^15
   if (bgr) { const int t0 = o[0]; o[0] = o[2]; o[2] = t0; }
 
   if (kToClip) {
