@@ -18,6 +18,11 @@
 //               IN PLACE in the slot the residual tile was TMA-loaded into, then a TMA store from that slot
 // TMEM: acc_b x2 (128 columns) + acc_c (256 columns).  Shared memory: 72 + 32 KB weights, 2 x 18 KB halo ring, 16 KB Yb,
 // 4 x 16 KB residual/output slots = 222.5 KB.
+//
+// kPoolT (last block of s2): the next stage's MaxPool3d k = s = [2,1,1] (video_model_builder.py:474-480,566-568) is
+// fused as well.  A CTA's consecutive tiles are the SAME spatial tile of frames 2j and 2j+1; the finished bf16 output of
+// the even frame waits in the 128 spare TMEM columns (tcgen05.st, 2 channels per column), the odd frame's epilogue takes
+// the element-wise max with it and stores the pooled tile: the un-pooled 256-channel tensor is never written.
 #include <cuda.h>
 
 #include "../../include/afb200.h"
@@ -47,7 +52,23 @@ struct FusedParams {
   const float* bias_b;
   const float* bias_c;
   int x_tiles, y_tiles, frames;     // tiles per row / column of a frame, B*T frames
-  int num_tiles;
+  int num_tiles;                    // work items per grid: tiles, or (kPoolT) frame-pair units of two tiles each
+};
+
+// The j-th tile of this CTA.  Plain: tile = blockIdx.x + j * gridDim.x over (x tile, y tile, frame).  kPoolT: unit
+// = blockIdx.x + (j >> 1) * gridDim.x over (x tile, y tile, frame pair); the unit's two tiles are frames 2*pair + (j & 1).
+template <bool kPoolT>
+struct TileIter {
+  int x_tiles, y_tiles, num, first, stride;
+  __device__ __forceinline__ TileIter(const FusedParams& p)
+      : x_tiles(p.x_tiles), y_tiles(p.y_tiles), num(p.num_tiles), first(blockIdx.x), stride(gridDim.x) {}
+  __device__ __forceinline__ bool valid(int j) const { return first + (kPoolT ? (j >> 1) : j) * stride < num; }
+  __device__ __forceinline__ void coords(int j, int& xt, int& yt, int& r) const {
+    int u = first + (kPoolT ? (j >> 1) : j) * stride;
+    xt = u % x_tiles; u /= x_tiles;
+    yt = u % y_tiles; u /= y_tiles;
+    r = kPoolT ? 2 * u + (j & 1) : u;
+  }
 };
 
 __device__ __forceinline__ void f_tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
@@ -74,7 +95,7 @@ __device__ __forceinline__ void f_tma_store_4d(const CUtensorMap* m, const void*
 __device__ __forceinline__ void wg_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // tm_r: residual [M,256] (kShortcut = false) / tm_x: the block input [B*T,H,W,64] and tm_ws: shortcut weights (true)
-template <bool kShortcut>
+template <bool kShortcut, bool kPoolT>
 __global__ void __launch_bounds__(F_THREADS, 1)
 conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_wb,
                      const __grid_constant__ CUtensorMap tm_wc, const __grid_constant__ CUtensorMap tm_r,
@@ -107,6 +128,9 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t ACCC_COL = 2 * F_MID;
+  constexpr uint32_t HOLD_COL = ACCC_COL + F_OUT;      // kPoolT: the even frame's bf16 output, 2 channels per column
+  static_assert(!(kShortcut && kPoolT), "the pooled variant is the identity-residual block");
+  const TileIter<kPoolT> tiles(p);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -147,10 +171,24 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     pdl_wait_prior_grid();
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int r = tile;
-      const int xt = r % p.x_tiles; r /= p.x_tiles;
-      const int yt = r % p.y_tiles; r /= p.y_tiles;       // r = frame index b*T + t
+    // kShortcut: the block input under a tile (no halo; operand of the shortcut's K block) travels through the ring
+    // BEHIND the halo boxes of the CTA's next tile, because that is where the MMA warp consumes it (c of a tile is
+    // issued after b of the next one)
+    auto load_x = [&](int j) {
+      int xt, yt, r;
+      tiles.coords(j, xt, yt, r);
+      mbar_wait(&a_empty[stage], phase ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&a_full[stage], F_TILE_BYTES);
+        f_tma_load_5d(smem_a + stage * F_A_BYTES, &tm_x, &a_full[stage], 0, xt * FX, yt * FR, r, 0);
+      }
+      __syncwarp();
+      if (++stage == F_A_STAGES) { stage = 0; phase ^= 1; }
+    };
+    int j = 0;
+    for (; tiles.valid(j); ++j) {
+      int xt, yt, r;                                      // r = frame index b*T + t
+      tiles.coords(j, xt, yt, r);
       for (int dx = 0; dx < 3; ++dx) {
         mbar_wait(&a_empty[stage], phase ^ 1);
         if (elect_one()) {
@@ -161,16 +199,9 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         __syncwarp();
         if (++stage == F_A_STAGES) { stage = 0; phase ^= 1; }
       }
-      if (kShortcut) {       // 4th box: the block input under the tile (no halo), operand of the shortcut's K block
-        mbar_wait(&a_empty[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(&a_full[stage], F_TILE_BYTES);
-          f_tma_load_5d(smem_a + stage * F_A_BYTES, &tm_x, &a_full[stage], 0, xt * FX, yt * FR, r, 0);
-        }
-        __syncwarp();
-        if (++stage == F_A_STAGES) { stage = 0; phase ^= 1; }
-      }
+      if (kShortcut && j >= 1) load_x(j - 1);
     }
+    if (kShortcut && j >= 1) load_x(j - 1);
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     constexpr uint32_t idesc_b = make_idesc(F_MID), idesc_c = make_idesc(F_OUT);
@@ -206,7 +237,7 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         if (++stage == F_A_STAGES) { stage = 0; phase ^= 1; }
       }
     };
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (; tiles.valid(it); ++it) {
       const int as = it & 1;
       mbar_wait(&accb_empty[as], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -231,19 +262,17 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       }
       if (elect_one()) umma_commit(&accb_full[as]);
       __syncwarp();
-      // without the shortcut, c of a tile is issued after b of the NEXT tile (epilogue 1 hides behind it); with it the
-      // ring delivers the tile's 4th box right behind its halo boxes, so c follows b directly
-      if (kShortcut) issue_c(it);
-      else if (it >= 1) issue_c(it - 1);
+      // c of a tile is issued after b of the NEXT tile, so epilogue 1 (acc_b -> Yb) hides behind those MMAs
+      if (it >= 1) issue_c(it - 1);
     }
-    if (!kShortcut && it >= 1) issue_c(it - 1);
+    if (it >= 1) issue_c(it - 1);
   } else if (warp < 6) {
     // ===================================================== epilogue 1 (warps 2-5): acc_b -> Yb
     pdl_wait_prior_grid();
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (; tiles.valid(it); ++it) {
       const int as = it & 1;
       mbar_wait(&accb_full[as], (it >> 1) & 1);
       tc_fence_after();
@@ -280,24 +309,24 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     uint8_t* slot_g = smem_slot + eg * (N_SLOTS / 2) * F_TILE_BYTES;
     uint64_t* res_bar = res_full + eg * 2;
     // chunk sequence of this group: (tile it, chunk eg), (it, eg + 2), (it + 1, eg), ...
-    int pre_tile = blockIdx.x, pre_chunk = eg;
+    int pre_j = 0, pre_chunk = eg;
     auto issue_res = [&](int slot) {
-      int r = pre_tile;
-      const int xt = r % p.x_tiles; r /= p.x_tiles;
-      const int yt = r % p.y_tiles; r /= p.y_tiles;
+      int xt, yt, r;
+      tiles.coords(pre_j, xt, yt, r);
       mbar_expect_tx(&res_bar[slot], F_TILE_BYTES);
       f_tma_load_4d(slot_g + slot * F_TILE_BYTES, &tm_r, &res_bar[slot], pre_chunk * 64, xt * FX, yt * FR, r);
-      if (pre_chunk + 2 < 4) pre_chunk += 2; else { pre_chunk = eg; pre_tile += gridDim.x; }
+      if (pre_chunk + 2 < 4) pre_chunk += 2; else { pre_chunk = eg; ++pre_j; }
     };
     if (!kShortcut && et == 0)
       for (int j = 0; j < 2; ++j)
-        if (pre_tile < p.num_tiles) issue_res(j);
+        if (tiles.valid(pre_j)) issue_res(j);
     uint32_t k = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      int r = tile;
-      const int xt = r % p.x_tiles; r /= p.x_tiles;
-      const int yt = r % p.y_tiles; r /= p.y_tiles;
+    for (; tiles.valid(it); ++it) {
+      int xt, yt, r;
+      tiles.coords(it, xt, yt, r);
+      const bool hold_phase = kPoolT && !(it & 1);      // even frame of a pair: the output waits in TMEM
+      const bool max_phase = kPoolT && (it & 1);        // odd frame: max with the held output, store the pooled tile
       mbar_wait(accc_full, it & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -305,9 +334,14 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         const int slot = kShortcut ? 0 : (int)(k & 1);
         uint8_t* s_io = slot_g + slot * F_TILE_BYTES;
         uint32_t v[64];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ACCC_COL + chunk * 64;
+        uint32_t h[kPoolT ? 32 : 1];
+        const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const uint32_t taddr = tlane + ACCC_COL + chunk * 64;
         TMEM_LD_32x32b_x32(taddr, v);
         TMEM_LD_32x32b_x32(taddr + 32, (v + 32));
+        if (kPoolT) {
+          if (max_phase) TMEM_LD_32x32b_x32(tlane + HOLD_COL + chunk * 32, h);
+        }
         if (kShortcut) {                          // plain output staging: the previous store must have read the slot
           if (et == 0) tma_store_wait_read<0>();
           wg_bar_sync(2 + eg);
@@ -334,16 +368,34 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             const float f1 = fmaxf(__uint_as_float(v[q * 8 + 2 * e + 1]) + bias[q * 8 + 2 * e + 1] + __high2float(h2[e]), 0.f);
             o2[e] = __floats2bfloat162_rn(f0, f1);
           }
-          *reinterpret_cast<uint4*>(pa) = o;
+          if (kPoolT) {
+            if (hold_phase) {
+              h[q * 4 + 0] = o.x; h[q * 4 + 1] = o.y; h[q * 4 + 2] = o.z; h[q * 4 + 3] = o.w;
+            } else {
+              const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&h[q * 4]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o2[e] = __hmax2(o2[e], g2[e]);
+              *reinterpret_cast<uint4*>(pa) = o;
+            }
+          } else {
+            *reinterpret_cast<uint4*>(pa) = o;
+          }
+        }
+        if (kPoolT && hold_phase) {
+          TMEM_ST_32x32b_x32(tlane + HOLD_COL + chunk * 32, h);
+          tmem_st_wait();
+          wg_bar_sync(2 + eg);                    // every thread of the group has consumed the residual slot
+          if (et == 0 && tiles.valid(pre_j)) issue_res(slot);
+          continue;
         }
         fence_proxy_async_smem();
         wg_bar_sync(2 + eg);                      // tile chunk complete in the slot
         if (et == 0) {
-          f_tma_store_4d(&tm_y, s_io, chunk * 64, xt * FX, yt * FR, r);
+          f_tma_store_4d(&tm_y, s_io, chunk * 64, xt * FX, yt * FR, kPoolT ? (r >> 1) : r);
           tma_store_commit();
           if (!kShortcut) {
             tma_store_wait_read<0>();             // the store has read the slot: refill it with the residual two chunks on
-            if (pre_tile < p.num_tiles) issue_res(slot);
+            if (tiles.valid(pre_j)) issue_res(slot);
           }
         }
       }
@@ -391,10 +443,12 @@ int conv_bc_fused_init() {
     AFB_CUDA(cudaDeviceGetAttribute(&g_f_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   }
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    if (f_smem(false) <= g_f_max_smem)
-      AFB_CUDA(cudaFuncSetAttribute(conv_bc_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem(false)));
+    if (f_smem(false) <= g_f_max_smem) {
+      AFB_CUDA(cudaFuncSetAttribute(conv_bc_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem(false)));
+      AFB_CUDA(cudaFuncSetAttribute(conv_bc_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem(false)));
+    }
     if (f_smem(true) <= g_f_max_smem)
-      AFB_CUDA(cudaFuncSetAttribute(conv_bc_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem(true)));
+      AFB_CUDA(cudaFuncSetAttribute(conv_bc_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem(true)));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   return AF_OK;
@@ -402,15 +456,16 @@ int conv_bc_fused_init() {
 
 // b: dense NDHWC [B,T,H,W,64] -> 1x3x3, stride 1, pad [0,1,1], 64 -> 64; c: 1x1x1 64 -> 256; residual / y dense [M,256].
 // With c.x2 set (projection shortcut fused into c: pointwise, stride 1, 64 -> 256 over the block input c.x2, biases
-// pre-summed in c.bias) there is no residual.
+// pre-summed in c.bias) there is no residual.  With c.pool_t set, y is the temporally max-pooled output [B,T/2,H,W,256].
 bool conv_bc_fused_supported(const ConvProblem& b, const ConvProblem& c) {
   if (!g_f_encode || f_smem(c.x2 != nullptr) > g_f_max_smem) return false;
   if (b.Cin != F_MID || b.Cout != F_MID || b.kt != 1 || b.kh != 3 || b.kw != 3 || b.st != 1 || b.sh != 1 || b.sw != 1 ||
       b.pt != 0 || b.ph != 1 || b.pw != 1 || !b.relu || b.res || b.pool_hw || b.pool_t || b.x2)
     return false;
   if (c.Cin != F_MID || c.Cout != F_OUT || c.kt != 1 || c.kh != 1 || c.kw != 1 || c.st != 1 || c.sh != 1 || c.sw != 1 ||
-      !c.relu || c.pool_t || c.pool_hw)
+      !c.relu || c.pool_hw)
     return false;
+  if (c.pool_t && (c.x2 || (b.To & 1))) return false;      // pooled variant: identity residual, whole frame pairs
   if (c.x2 ? (c.res || !c.w2 || c.Cin2 != F_MID || c.sh2 != 1 || c.sw2 != 1 || c.T2 != c.To || c.H2 != c.Ho || c.W2 != c.Wo)
            : !c.res)
     return false;
@@ -425,9 +480,9 @@ int conv_bc_fused_launch(const ConvProblem& b, const ConvProblem& c, cudaStream_
   FusedParams fp;
   fp.bias_b = b.bias; fp.bias_c = c.bias;
   fp.x_tiles = b.Wo / FX; fp.y_tiles = (b.Ho + FR - 1) / FR; fp.frames = b.B * b.To;
-  fp.num_tiles = fp.frames * fp.y_tiles * fp.x_tiles;
+  const bool shortcut = c.x2 != nullptr, pool_t = c.pool_t != 0;
+  fp.num_tiles = (pool_t ? fp.frames / 2 : fp.frames) * fp.y_tiles * fp.x_tiles;
   alignas(64) CUtensorMap ta, twb, twc, tr, ty, tx, tws;
-  const bool shortcut = c.x2 != nullptr;
   {
     cuuint64_t dims[5] = {(cuuint64_t)F_MID, (cuuint64_t)b.Wi, (cuuint64_t)b.Hi, (cuuint64_t)b.B * b.Ti, 1};
     cuuint64_t strides[4] = {(cuuint64_t)F_MID * 2, (cuuint64_t)b.Wi * F_MID * 2, (cuuint64_t)b.Hi * b.Wi * F_MID * 2,
@@ -451,7 +506,8 @@ int conv_bc_fused_launch(const ConvProblem& b, const ConvProblem& c, cudaStream_
     if (rc) return rc;
   }
   for (int which = 0; which < 2; ++which) {
-    cuuint64_t dims[4] = {(cuuint64_t)F_OUT, (cuuint64_t)b.Wo, (cuuint64_t)b.Ho, (cuuint64_t)fp.frames};
+    cuuint64_t dims[4] = {(cuuint64_t)F_OUT, (cuuint64_t)b.Wo, (cuuint64_t)b.Ho,
+                          (cuuint64_t)((which && pool_t) ? fp.frames / 2 : fp.frames)};
     cuuint64_t strides[3] = {(cuuint64_t)F_OUT * 2, (cuuint64_t)b.Wo * F_OUT * 2, (cuuint64_t)b.Ho * b.Wo * F_OUT * 2};
     cuuint32_t box[4] = {64, FX, FR, 1};
     int rc = f_encode(which ? &ty : &tr, (which || shortcut) ? c.y : c.res, 4, dims, strides, box, which ? "fused Y" : "fused R");
@@ -478,8 +534,9 @@ int conv_bc_fused_launch(const ConvProblem& b, const ConvProblem& c, cudaStream_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (shortcut) AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_bc_fused_kernel<true>, ta, twb, twc, tr, ty, tx, tws, fp));
-  else AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_bc_fused_kernel<false>, ta, twb, twc, tr, ty, tx, tws, fp));
+  if (shortcut) AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_bc_fused_kernel<true, false>, ta, twb, twc, tr, ty, tx, tws, fp));
+  else if (pool_t) AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_bc_fused_kernel<false, true>, ta, twb, twc, tr, ty, tx, tws, fp));
+  else AFB_CUDA(cudaLaunchKernelEx(&cfg, conv_bc_fused_kernel<false, false>, ta, twb, twc, tr, ty, tx, tws, fp));
   ++g_launches;
   AFB_CUDA(cudaGetLastError());
   return AF_OK;
