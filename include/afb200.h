@@ -274,6 +274,14 @@ af_status af_conv_bc_fused_ndhwc(const void* x_dev, const af_conv_desc* conv_b_h
                                  const void* residual_dev, const void* x2_dev, const af_conv_desc* shortcut_host,
                                  void* y_dev, int32_t batch, int32_t t, int32_t hgt, int32_t wid, void* stream);
 
+/* The same fused tail for the LAST block of s2, with the next stage's MaxPool3d k = s = [2,1,1]
+ * (video_model_builder.py:474-480,566-568: pathway0_pool before s3) taken in the epilogue:
+ *   y[b, j] = max(f(x)[b, 2j], f(x)[b, 2j+1]),  f = relu(c(relu(b(x))) + residual)
+ * x [B,T,H,W,64], residual [B,T,H,W,256], y [B,T/2,H,W,256] (bf16 NDHWC device tensors), T even. */
+af_status af_conv_bc_fused_tpool_ndhwc(const void* x_dev, const af_conv_desc* conv_b_host, const af_conv_desc* conv_c_host,
+                                       const void* residual_dev, void* y_dev, int32_t batch, int32_t t, int32_t hgt,
+                                       int32_t wid, void* stream);
+
 /* Copy intermediate activations of the LAST af_forward/af_infer call out for stage
  * parity tests: which = 1..5 (s1..s5 outputs) as fp32 NCTHW [B,C,T,H,W] into out_dev.
  * Requires option "keep_stages" = 1 (costs extra memory). */

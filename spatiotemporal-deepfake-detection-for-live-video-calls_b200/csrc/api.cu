@@ -306,14 +306,15 @@ static ConvProblem dense_problem(const ConvLayer& L, const void* x, Dims in, int
 // The `b` -> `c` tail of an s2-shaped bottleneck block in one kernel (conv_bc_fused.cu) when the shapes allow it.
 // Returns 1 if it ran, 0 if the caller should run the two convs separately, < 0 on error.
 static int try_fused_bc(af_engine* e, const ConvLayer& Lb, const ConvLayer& Lc, const void* xb, Dims db_in, int B,
-                        const void* res, void* y, cudaStream_t s, const FusedShortcut* sc = nullptr) {
+                        const void* res, void* y, cudaStream_t s, const FusedShortcut* sc = nullptr, int pool_t = 0) {
   static const bool off = getenv("AFB200_NO_FUSED_BC") != nullptr;
   static const bool off_sc = getenv("AFB200_NO_FUSED_BC_SHORTCUT") != nullptr;
-  if (off || (sc && off_sc) || !Lb.w_umma || !Lc.w_umma) return 0;
+  static const bool off_tp = getenv("AFB200_NO_FUSED_BC_TPOOL") != nullptr;
+  if (off || (sc && off_sc) || (pool_t && off_tp) || !Lb.w_umma || !Lc.w_umma) return 0;
   const ConvProblem pb = dense_problem(Lb, xb, db_in, B, nullptr, nullptr, true);
   const Dims dmid = conv_out(Lb, db_in);
   const long long sW = dmid.C, sH = (long long)dmid.W * dmid.C, sT = sH * dmid.H, sB = sT * dmid.T;
-  const ConvProblem pc = make_problem(Lc, nullptr, dmid, sB, sT, sH, sW, B, sc ? nullptr : res, y, true, 0, 0, sc);
+  const ConvProblem pc = make_problem(Lc, nullptr, dmid, sB, sT, sH, sW, B, sc ? nullptr : res, y, true, 0, pool_t, sc);
   if (!conv_bc_fused_supported(pb, pc)) return 0;
   OpTrace tr(s);
   ProfRec prec(e, s);
@@ -321,12 +322,13 @@ static int try_fused_bc(af_engine* e, const ConvLayer& Lb, const ConvLayer& Lc, 
   if (rc) return rc;
   const double k2 = sc ? (double)sc->L->cin_p : 0.0;
   const double flops = 2.0 * (double)pb.M * (Lb.cout * 9.0 * Lb.cin_p + (double)Lc.cout * (Lc.cin_p + k2));
-  const double bytes = ((double)pb.M * (Lb.cin_p + k2 + (sc ? 1.0 : 2.0) * Lc.cout) + 9.0 * Lb.cin_p * Lb.cout +
+  const double bytes = ((double)pb.M * (Lb.cin_p + k2 + (sc ? 1.0 : pool_t ? 1.5 : 2.0) * Lc.cout) + 9.0 * Lb.cin_p * Lb.cout +
                         (Lc.cin_p + k2) * Lc.cout) * 2.0;
   prec.done(flops >= (e ? e->ridge_flop_per_byte : 208.0) * bytes ? 0 : 2, flops, bytes);
   if (OpTrace::enabled()) {
     char nm[128];
-    snprintf(nm, sizeof(nm), "conv fused b k1x3x3 + c k1x1x1 M=%lld N=%d->%d %s", pb.M, Lb.cout, Lc.cout, sc ? "+shortcut" : "+res");
+    snprintf(nm, sizeof(nm), "conv fused b k1x3x3 + c k1x1x1 M=%lld N=%d->%d %s", pb.M, Lb.cout, Lc.cout,
+             sc ? "+shortcut" : pool_t ? "+res +tpool" : "+res");
     tr.done(nm, flops, bytes);
   }
   return 1;
@@ -467,12 +469,14 @@ static int run_blocks(af_engine* e, int b_begin, int b_end, const void*& x, Dims
                         bi + 1 < (int)e->blocks.size() &&
                         e->blocks[bi + 1].temporal_pool_before && (db.T % 2 == 0) && ((db.H * db.W) % 64 == 0) &&
                         Lc.kt == 1 && Lc.kh == 1 && Lc.kw == 1 && Lc.sh == 1 && Lc.sw == 1 && Lc.st == 1;
-    // identity-residual blocks of s2: `b` and `c` (+residual) as ONE kernel (conv_bc_fused.cu)
-    if (e->is_bf16 && e->conv_impl == 0 && !blk.spatial_pool && !fuse_t) {
-      rc = try_fused_bc(e, e->convs[blk.b], Lc, ya, da, B, shortcut, yout, s, fsc.L ? &fsc : nullptr);
+    // blocks of s2: `b` and `c` (+residual / +projection shortcut / +the next stage's temporal max-pool) as ONE kernel
+    // (conv_bc_fused.cu)
+    if (e->is_bf16 && e->conv_impl == 0 && !blk.spatial_pool) {
+      rc = try_fused_bc(e, e->convs[blk.b], Lc, ya, da, B, shortcut, yout, s, fsc.L ? &fsc : nullptr, fuse_t ? 1 : 0);
       if (rc < 0) return rc;
       if (rc == 1) {
         d = conv_out(Lc, db);
+        if (fuse_t) { d.T /= 2; e->pooled_already = true; }
         x = yout;
         if (is_stage_end(e, bi)) {
           rc = keep_stage(e, stage_no, x, d, clip0, B, s);
@@ -1389,9 +1393,9 @@ af_status af_stem_pool_ndhwc4(const void* clip_dev, const af_conv_desc* stem_hos
   return (af_status)rc;
 }
 
-af_status af_conv_bc_fused_ndhwc(const void* x_dev, const af_conv_desc* conv_b_host, const af_conv_desc* conv_c_host,
-                                 const void* residual_dev, const void* x2_dev, const af_conv_desc* shortcut_host, void* y_dev,
-                                 int32_t batch, int32_t t, int32_t hgt, int32_t wid, void* stream) {
+static af_status bc_fused_entry(const void* x_dev, const af_conv_desc* conv_b_host, const af_conv_desc* conv_c_host,
+                                const void* residual_dev, const void* x2_dev, const af_conv_desc* shortcut_host, void* y_dev,
+                                int32_t batch, int32_t t, int32_t hgt, int32_t wid, int pool_t, void* stream) {
   if (!x_dev || !conv_b_host || !conv_c_host || !y_dev || batch <= 0 || (!residual_dev == !x2_dev) || (!x2_dev != !shortcut_host)) {
     set_error("af_conv_bc_fused_ndhwc: invalid arguments (give either a residual or a shortcut input + conv)");
     return AF_ERR_INVALID;
@@ -1421,10 +1425,11 @@ af_status af_conv_bc_fused_ndhwc(const void* x_dev, const af_conv_desc* conv_b_h
     const ConvProblem pb = dense_problem(Lb, x_dev, in, batch, nullptr, nullptr, true);
     FusedShortcut sc = {&Ls, x2_dev, Dims{t, hgt, wid, Ls.cin_p}, bias};
     const long long sW = dmid.C, sH = (long long)dmid.W * dmid.C, sT = sH * dmid.H, sB = sT * dmid.T;
-    const ConvProblem pc = make_problem(Lc, nullptr, dmid, sB, sT, sH, sW, batch, residual_dev, y_dev, true, 0, 0,
+    const ConvProblem pc = make_problem(Lc, nullptr, dmid, sB, sT, sH, sW, batch, residual_dev, y_dev, true, 0, pool_t,
                                         shortcut_host ? &sc : nullptr);
     if (!conv_bc_fused_supported(pb, pc)) {
-      set_error("af_conv_bc_fused_ndhwc: takes b = 1x3x3 s1 p[0,1,1] 64->64, c = 1x1x1 64->256, width %% 8 == 0");
+      set_error("af_conv_bc_fused_ndhwc: takes b = 1x3x3 s1 p[0,1,1] 64->64, c = 1x1x1 64->256, width %% 8 == 0 (pooled form: "
+                "residual only, even T)");
       rc = AF_ERR_INVALID;
     } else {
       rc = conv_bc_fused_launch(pb, pc, (cudaStream_t)stream);
@@ -1439,6 +1444,18 @@ af_status af_conv_bc_fused_ndhwc(const void* x_dev, const af_conv_desc* conv_b_h
   free_layer(Lc);
   free_layer(Ls);
   return (af_status)rc;
+}
+
+af_status af_conv_bc_fused_ndhwc(const void* x_dev, const af_conv_desc* conv_b_host, const af_conv_desc* conv_c_host,
+                                 const void* residual_dev, const void* x2_dev, const af_conv_desc* shortcut_host, void* y_dev,
+                                 int32_t batch, int32_t t, int32_t hgt, int32_t wid, void* stream) {
+  return bc_fused_entry(x_dev, conv_b_host, conv_c_host, residual_dev, x2_dev, shortcut_host, y_dev, batch, t, hgt, wid, 0, stream);
+}
+
+af_status af_conv_bc_fused_tpool_ndhwc(const void* x_dev, const af_conv_desc* conv_b_host, const af_conv_desc* conv_c_host,
+                                       const void* residual_dev, void* y_dev, int32_t batch, int32_t t, int32_t hgt,
+                                       int32_t wid, void* stream) {
+  return bc_fused_entry(x_dev, conv_b_host, conv_c_host, residual_dev, nullptr, nullptr, y_dev, batch, t, hgt, wid, 1, stream);
 }
 
 af_status af_get_stage(af_handle h, int32_t which, float* out_dev, int64_t capacity_elems, int32_t dims_out[5],

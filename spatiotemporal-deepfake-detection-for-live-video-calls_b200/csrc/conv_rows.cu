@@ -442,7 +442,7 @@ stem_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     pdl_wait_prior_grid();
-    constexpr uint32_t idesc = make_idesc(RB_N), idesc2 = make_idesc(2 * RB_N);
+    constexpr uint32_t idesc = make_idesc(RB_N);
     mbar_wait(w_full, 0);
     tc_fence_after();
     const uint32_t w_base = smem_u32(smem_w);
@@ -459,39 +459,28 @@ stem_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const uint32_t a_addr = smem_u32(smem_a + stage * p.a_stage_bytes);
         if (elect_one()) {
           const int g_lo = f > 4 ? f - 4 : 0, g_hi = f < RB_G - 1 ? f : RB_G - 1;
-          // Output frame g of the unit sees this input frame as tap dt = f - g.  Two consecutive output frames
-          // (g, g+1) use taps (dt, dt-1) of the SAME activation box: their weight tiles are adjacent in smem and their
-          // accumulators adjacent in TMEM, so one 128x128x16 MMA does both and reads the A operand once -- an
-          // N=64 MMA is bound by its shared-memory operand reads (6 KB per 32 tensor clocks), the paired one is not.
-          int g = g_lo;
-          while (g <= g_hi) {
-            const int dt = f - g;
-            const uint32_t d_tmem = tmem_base + (as * RB_G + g) * RB_N;
-            if (g + 1 <= g_hi) {
-              const bool init = dt == 1;            // frame g+1 receives its first contribution (tap 0) here
+          // Output frame g of the unit sees this input frame as tap dt = f - g.  The n = g_hi - g_lo + 1 output frames
+          // fed by this box use taps (dt, dt-1, ...) of the SAME activation rows: their weight tiles are adjacent in smem
+          // and their accumulators adjacent in TMEM, so ONE 128 x 64n x 16 MMA does them all and reads the A operand
+          // once -- an N=64 MMA is bound by its shared-memory operand reads (6 KB per 32 tensor clocks), the wide
+          // ones are not (n = 4: 12 KB per 128 clocks).  Only the very first MMA of a frame whose accumulator opens here
+          // (dt = 0: g_hi = f) is issued on its own, because the accumulate flag is per instruction.
+          const int n = g_hi - g_lo + 1;
+          const int dt_lo = f - g_lo;                 // tap of the first (oldest) output frame
+          const bool opens = f < RB_G;                // g_hi = f receives its first contribution (tap 0)
+          const uint32_t d_tmem = tmem_base + (as * RB_G + g_lo) * RB_N;
+          const uint32_t idesc_n = make_idesc(RB_N * n), idesc_old = make_idesc(RB_N * (n > 1 ? n - 1 : 1));
 #pragma unroll
-              for (int dy = 0; dy < 7; ++dy) {
-                const uint64_t adesc = make_smem_desc_ex(a_addr + dy * A_TAP_BYTES, 1024, LAYOUT);
-                const uint64_t bdesc = make_smem_desc_ex(w_base + (dy * 5 + 4 - dt) * W_TILE_BYTES, SBO_B, LAYOUT);
-                if (dy == 0 && init) {              // the pair's predicate is shared: open g+1's accumulator separately
-                  umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
-                  umma_bf16(d_tmem + RB_N, adesc, bdesc + (W_TILE_BYTES >> 4), idesc, 0u);
-                } else {
-                  umma_bf16(d_tmem, adesc, bdesc, idesc2, 1u);
-                }
-                umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc2, 1u);
-              }
-              g += 2;
+          for (int dy = 0; dy < 7; ++dy) {
+            const uint64_t adesc = make_smem_desc_ex(a_addr + dy * A_TAP_BYTES, 1024, LAYOUT);
+            const uint64_t bdesc = make_smem_desc_ex(w_base + (dy * 5 + 4 - dt_lo) * W_TILE_BYTES, SBO_B, LAYOUT);
+            if (dy == 0 && opens) {
+              if (n > 1) umma_bf16(d_tmem, adesc, bdesc, idesc_old, 1u);
+              umma_bf16(d_tmem + (n - 1) * RB_N, adesc, bdesc + (uint64_t)((n - 1) * (W_TILE_BYTES >> 4)), idesc, 0u);
             } else {
-#pragma unroll
-              for (int dy = 0; dy < 7; ++dy) {
-                const uint64_t adesc = make_smem_desc_ex(a_addr + dy * A_TAP_BYTES, 1024, LAYOUT);
-                const uint64_t bdesc = make_smem_desc_ex(w_base + (dy * 5 + 4 - dt) * W_TILE_BYTES, SBO_B, LAYOUT);
-                umma_bf16(d_tmem, adesc, bdesc, idesc, (dt | dy) != 0 ? 1u : 0u);
-                umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-              }
-              g += 1;
+              umma_bf16(d_tmem, adesc, bdesc, idesc_n, 1u);
             }
+            umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc_n, 1u);
           }
           umma_commit(&empty_bar[stage]);
         }

@@ -240,11 +240,27 @@ def conv_ndhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride
 
 
 def conv_bc_fused_ndhwc(x: torch.Tensor, weight_b, bias_b, weight_c, bias_c, residual: Optional[torch.Tensor] = None,
-                        x2: Optional[torch.Tensor] = None, weight_s=None, bias_s=None) -> torch.Tensor:
+                        x2: Optional[torch.Tensor] = None, weight_s=None, bias_s=None, pool_t: bool = False) -> torch.Tensor:
     """relu(c(relu(b(x))) + residual) — or + shortcut(x2) — in ONE kernel (test/diagnostic entry af_conv_bc_fused_ndhwc):
     x bf16 [B,T,H,W,64], weight_b [64,64,1,3,3], weight_c [256,64,1,1,1], residual bf16 [B,T,H,W,256] or
-    x2 bf16 [B,T,H,W,64] with weight_s [256,64,1,1,1]."""
+    x2 bf16 [B,T,H,W,64] with weight_s [256,64,1,1,1].  pool_t (residual form only, af_conv_bc_fused_tpool_ndhwc): the
+    max over frame pairs is taken in the epilogue and y is [B,T/2,H,W,256]."""
     assert (residual is None) != (x2 is None)
+    if pool_t:
+        assert residual is not None and x.shape[1] % 2 == 0
+        for t in (x, residual):
+            assert t.is_cuda and t.is_contiguous() and t.dtype == torch.bfloat16
+        B, T, H, W, _ = x.shape
+        db, keep_b = _conv_desc(weight_b, bias_b, (1, 1, 1), (0, 1, 1))
+        dc, keep_c = _conv_desc(weight_c, bias_c, (1, 1, 1), (0, 0, 0))
+        y = torch.empty((B, T // 2, H, W, dc.cout), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib().af_conv_bc_fused_tpool_ndhwc(C.c_void_p(x.data_ptr()), C.byref(db), C.byref(dc),
+                                                     C.c_void_p(residual.data_ptr()), C.c_void_p(y.data_ptr()), B, T, H, W,
+                                                     C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
+                  "af_conv_bc_fused_tpool_ndhwc")
+        del keep_b, keep_c
+        return y
     for t in (x, residual, x2):
         assert t is None or (t.is_cuda and t.is_contiguous() and t.dtype == torch.bfloat16)
     B, T, H, W, _ = x.shape

@@ -54,7 +54,7 @@ def test_production_schedule_batch32_matches_oracle_and_decisions(dev, state_dic
     assert (ref > 0).any() and (ref < 0).any()
     assert torch.allclose(scores.cpu(), torch.sigmoid(logits))
     # one launch per layer for the WHOLE batch (production chunks), our kernels only
-    assert 50 <= launches <= 60, launches
+    assert 45 <= launches <= 60, launches
     # every clip's arithmetic is independent of its batch mates and of the tile width its batch size selects
     # (B=1 picks 64/128-wide tiles where B=32 picks 256): bf16 results agree to accumulation-order noise
     for i in (1, 30):
@@ -338,6 +338,32 @@ def test_fused_bc_kernel_vs_torch_fp32(dev, case):
     y_b = afb200.conv_ndhwc(x, wb, bb, (1, 1, 1), (0, 1, 1), True, None, impl=3)
     y_c = afb200.conv_ndhwc(y_b, wc, bc, (1, 1, 1), (0, 0, 0), True, res, impl=2).float().cpu()
     assert (got - y_c).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("case", [(1, 2, 16, 8), (2, 4, 56, 56), (3, 6, 24, 40), (1, 160, 24, 16)])
+def test_fused_bc_kernel_with_temporal_pool(dev, case):
+    """Last block of s2: the next stage's MaxPool3d k = s = [2,1,1] (video_model_builder.py:474-480,566-568) taken inside
+    the fused b -> c kernel: the even frame's output waits in TMEM, the odd frame's epilogue stores the max.  The last
+    case gives every CTA more than one frame pair (the hold columns and residual slots are reused)."""
+    B, T, H, W = case
+    g = torch.Generator().manual_seed(11 * H + W)
+    x = torch.randn(B, T, H, W, 64, generator=g).to(dev, torch.bfloat16)
+    wb = torch.randn(64, 64, 1, 3, 3, generator=g) * (2.0 / 576) ** 0.5
+    bb = torch.randn(64, generator=g) * 0.1
+    wc = torch.randn(256, 64, 1, 1, 1, generator=g) * (1.0 / 64) ** 0.5
+    bc = torch.randn(256, generator=g) * 0.1
+    res = torch.randn(B, T, H, W, 256, generator=g).to(dev, torch.bfloat16)
+    got = afb200.conv_bc_fused_ndhwc(x, wb, bb, wc, bc, res, pool_t=True).float().cpu()
+    assert got.shape == (B, T // 2, H, W, 256)
+    # the un-pooled fused kernel is pinned against torch above; pooling bf16 values is exact
+    full = afb200.conv_bc_fused_ndhwc(x, wb, bb, wc, bc, res).float().cpu()
+    want = torch.maximum(full[:, 0::2], full[:, 1::2])
+    assert torch.equal(got, want), (got - want).abs().max().item()
+    mid = _conv_ref(x, wb.to(torch.bfloat16).float(), bb, (1, 1, 1), (0, 1, 1), True, None).to(torch.bfloat16)
+    ref = _conv_ref(mid, wc.to(torch.bfloat16).float(), bc, (1, 1, 1), (0, 0, 0), True, res)
+    ref = torch.maximum(ref[:, 0::2], ref[:, 1::2])
+    tol = 2.0 ** -7 * max(1.0, ref.abs().max().item()) + 2.0 ** -8 * max(1.0, mid.float().abs().max().item()) * 0.6 + 1e-3
+    assert (got - ref).abs().max().item() <= tol
 
 
 @pytest.mark.parametrize("case", [(1, 2, 16, 8), (2, 3, 56, 56), (1, 40, 24, 16)])
