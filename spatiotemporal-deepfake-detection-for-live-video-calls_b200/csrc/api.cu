@@ -55,6 +55,7 @@ struct ConvLayer {
   float* w_simt = nullptr;  // [taps][cin_p][cout] fp32 (bf16-rounded values in bf16 precision)
   bf16* w_umma = nullptr;   // [taps][cout][cin_p] bf16 (bf16 precision only)
   float* bias = nullptr;    // [cout]
+  std::vector<float> bias_h;  // host copy of bias
 };
 
 static void free_layer(ConvLayer& L) {
@@ -92,6 +93,7 @@ static int upload_layer(const af_conv_desc& d, bool is_bf16, ConvLayer& L) {
   }
   AFB_CUDA(cudaMalloc(&L.bias, d.cout * sizeof(float)));
   AFB_CUDA(cudaMemcpy(L.bias, d.bias, d.cout * sizeof(float), cudaMemcpyHostToDevice));
+  L.bias_h.assign(d.bias, d.bias + d.cout);
   return AF_OK;
 }
 
@@ -124,6 +126,7 @@ static int upload_stem_unfolded(const af_conv_desc& d, ConvLayer& L) {
   AFB_CUDA(cudaMemcpy(L.w_simt, ws.data(), n * sizeof(float), cudaMemcpyHostToDevice));
   AFB_CUDA(cudaMalloc(&L.bias, d.cout * sizeof(float)));
   AFB_CUDA(cudaMemcpy(L.bias, d.bias, d.cout * sizeof(float), cudaMemcpyHostToDevice));
+  L.bias_h.assign(d.bias, d.bias + d.cout);
   return AF_OK;
 }
 
@@ -189,6 +192,7 @@ struct af_engine {
   int stem = 0;
   std::vector<af_block_desc> blocks;
   std::vector<float*> fused_bias;   // per block: bias(c) + bias(branch1) for the fused projection shortcut (or null)
+  std::vector<std::vector<float>> fused_bias_h;   // host copies of fused_bias
   float* fc_w = nullptr;
   float fc_b = 0.f;
   int feat_dim = 0;
@@ -273,13 +277,14 @@ struct ProfRec {
 
 // A projection shortcut fused into the conv it is added to (bf16 tcgen05 path only): conv `L` over `x`,
 // both folded biases pre-summed in `bias`.
-struct FusedShortcut { const ConvLayer* L; const void* x; Dims in; const float* bias; };
+struct FusedShortcut { const ConvLayer* L; const void* x; Dims in; const float* bias; const float* bias_host; };
 
 static ConvProblem make_problem(const ConvLayer& L, const void* x, Dims in, long long xsB, long long xsT, long long xsH,
                                 long long xsW, int B, const void* res, void* y, bool relu, int pool_hw, int pool_t,
                                 const FusedShortcut* sc) {
   ConvProblem p;
   p.x = x; p.bias = sc ? sc->bias : L.bias; p.res = res; p.y = y;
+  p.bias_host = sc ? sc->bias_host : (L.bias_h.empty() ? nullptr : L.bias_h.data());
   if (sc) {
     p.x2 = sc->x; p.w2 = sc->L->w_umma; p.Cin2 = sc->L->cin_p;
     p.T2 = sc->in.T; p.H2 = sc->in.H; p.W2 = sc->in.W; p.sh2 = sc->L->sh; p.sw2 = sc->L->sw;
@@ -441,7 +446,7 @@ static int run_blocks(af_engine* e, int b_begin, int b_end, const void*& x, Dims
     // accumulated into the block's `c` conv (one GEMM over K = Cin_c + Cin_x), which saves writing and
     // re-reading the widest tensor of the stage.
     static const bool no_scfuse = getenv("AFB200_NO_FUSED_SHORTCUT") != nullptr;
-    FusedShortcut fsc = {nullptr, nullptr, d, nullptr};
+    FusedShortcut fsc = {nullptr, nullptr, d, nullptr, nullptr};
     if (blk.branch1 >= 0) {
       const ConvLayer& L1 = e->convs[blk.branch1];
       const ConvLayer& Lc1 = e->convs[blk.c];
@@ -450,7 +455,7 @@ static int run_blocks(af_engine* e, int b_begin, int b_end, const void*& x, Dims
                            L1.cin_p % 64 == 0 && Lc1.kt == 1 && Lc1.kh == 1 && Lc1.kw == 1 && Lc1.st == 1 &&
                            Lc1.sh == 1 && Lc1.sw == 1;
       if (fuse_sc) {
-        fsc.L = &L1; fsc.x = x; fsc.in = d; fsc.bias = e->fused_bias[bi];
+        fsc.L = &L1; fsc.x = x; fsc.in = d; fsc.bias = e->fused_bias[bi]; fsc.bias_host = e->fused_bias_h[bi].data();
         shortcut = nullptr;
       } else {
         int rc = dense_conv(e, blk.branch1, x, d, B, nullptr, ysc, false, s);
@@ -582,7 +587,7 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
           AFB_CUDA(cudaMemsetAsync(e->fbuf[1], 0, (size_t)fB * dpool.elems() * e->esz, s));
           ProfRec prec(e, s);
           const char* phys = (const char*)e->clip_raw + (long long)f0 * e->clip.sB * (long long)e->esz;
-          rc = ftcn_stem_umma_launch(phys, fB, e->T, e->S, e->ftcn_w2, stem.bias, e->fbuf[1], s);
+          rc = ftcn_stem_umma_launch(phys, fB, e->T, e->S, e->ftcn_w2, stem.bias_h.data(), e->fbuf[1], s);
           prec.done(2, 2.0 * (double)fB * e->T * e->S * e->S * 64 * 15,
                     (double)fB * ((double)(e->T + 4) * (e->S + 6) * (e->S + 8) * 4 + dpool.elems()) * 2.0);
         } else {
@@ -599,7 +604,7 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
         AFB_CUDA(cudaMemsetAsync(e->fbuf[1], 0, (size_t)fB * dpool.elems() * e->esz, s));
         ProfRec prec(e, s);
         const char* phys = (const char*)e->clip_raw + (long long)f0 * e->clip.sB * (long long)e->esz;
-        rc = conv_stem_direct_launch(phys, fB, e->T, e->S, e->stem_w35, e->stem_u.bias, e->fbuf[1], 1, s);
+        rc = conv_stem_direct_launch(phys, fB, e->T, e->S, e->stem_w35, e->stem_u.bias_h.data(), e->fbuf[1], 1, s);
         if (rc == AF_ERR_CUDA && strstr(af_last_error(), "cuTensorMapEncodeTiled")) {
           e->stem_direct = -1;                    // driver refused the overlapping-window map: use the unfolded path
         } else {
@@ -888,6 +893,7 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
   }
   e->blocks.assign(w->blocks, w->blocks + w->n_blocks);
   e->fused_bias.assign(w->n_blocks, nullptr);
+  e->fused_bias_h.assign(w->n_blocks, std::vector<float>());
   for (int bi = 0; bi < w->n_blocks && e->is_bf16; ++bi) {
     const af_block_desc& blk = w->blocks[bi];
     if (blk.branch1 < 0 || w->convs[blk.branch1].cout != w->convs[blk.c].cout) continue;
@@ -896,6 +902,7 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
     for (int i = 0; i < n; ++i) sum[i] = w->convs[blk.c].bias[i] + w->convs[blk.branch1].bias[i];
     AFB_CUDA(cudaMalloc(&e->fused_bias[bi], n * sizeof(float)));
     AFB_CUDA(cudaMemcpy(e->fused_bias[bi], sum.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    e->fused_bias_h[bi] = sum;
   }
   if (w->tt_head) {
     int rc = upload_tt_head(e, *w->tt_head);
@@ -1382,7 +1389,7 @@ af_status af_stem_pool_ndhwc4(const void* clip_dev, const af_conv_desc* stem_hos
     rc = pack_clip_launch(clip_dev, AF_BF16, q, batch, cl, st);
   }
   if (!rc && cudaMemsetAsync(y_dev, 0, (size_t)batch * t * (s_ / 4) * (s_ / 4) * 64 * 2, st) != cudaSuccess) rc = AF_ERR_CUDA;
-  if (!rc) rc = conv_stem_direct_launch(padded, batch, t, s_, w35, bias, y_dev, 1, st, per_frame_kernel);
+  if (!rc) rc = conv_stem_direct_launch(padded, batch, t, s_, w35, d.bias, y_dev, 1, st, per_frame_kernel);
   if (!rc && cudaStreamSynchronize(st) != cudaSuccess) {
     set_error("af_stem_pool_ndhwc4: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
     rc = AF_ERR_CUDA;
@@ -1405,6 +1412,7 @@ static af_status bc_fused_entry(const void* x_dev, const af_conv_desc* conv_b_ho
   if (rc) return (af_status)rc;
   ConvLayer Lb, Lc, Ls;
   float* bias = nullptr;
+  std::vector<float> bias_sum_h;
   rc = upload_layer(*conv_b_host, true, Lb);
   if (!rc) rc = upload_layer(*conv_c_host, true, Lc);
   if (!rc && shortcut_host) {
@@ -1412,6 +1420,7 @@ static af_status bc_fused_entry(const void* x_dev, const af_conv_desc* conv_b_ho
     if (!rc) {
       std::vector<float> sum(conv_c_host->cout);
       for (int i = 0; i < conv_c_host->cout; ++i) sum[i] = conv_c_host->bias[i] + shortcut_host->bias[i];
+      bias_sum_h = sum;
       if (cudaMalloc(&bias, sum.size() * sizeof(float)) != cudaSuccess ||
           cudaMemcpy(bias, sum.data(), sum.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
         set_error("af_conv_bc_fused_ndhwc: bias upload failed");
@@ -1423,7 +1432,7 @@ static af_status bc_fused_entry(const void* x_dev, const af_conv_desc* conv_b_ho
     const Dims in = {t, hgt, wid, Lb.cin_p};
     const Dims dmid = conv_out(Lb, in);
     const ConvProblem pb = dense_problem(Lb, x_dev, in, batch, nullptr, nullptr, true);
-    FusedShortcut sc = {&Ls, x2_dev, Dims{t, hgt, wid, Ls.cin_p}, bias};
+    FusedShortcut sc = {&Ls, x2_dev, Dims{t, hgt, wid, Ls.cin_p}, bias, bias_sum_h.data()};
     const long long sW = dmid.C, sH = (long long)dmid.W * dmid.C, sT = sH * dmid.H, sB = sT * dmid.T;
     const ConvProblem pc = make_problem(Lc, nullptr, dmid, sB, sT, sH, sW, batch, residual_dev, y_dev, true, 0, pool_t,
                                         shortcut_host ? &sc : nullptr);

@@ -17,6 +17,7 @@ struct ConvProblem {
   const void* x;
   const void* w;       // SIMT: float [taps][cin][cout];  UMMA: bf16 [taps][cout][cin]
   const float* bias;   // [cout]
+  const float* bias_host = nullptr;   // host copy of `bias` (kernels that take the bias through their launch parameters)
   const void* res;     // nullptr or dense [M, cout]
   void* y;             // dense [M, cout]
   int B, Ti, Hi, Wi, Cin;
@@ -80,13 +81,13 @@ int conv_rows_init();
 bool conv_tsweep_supported(const ConvProblem& p);
 int conv_tsweep_launch(const ConvProblem& p, cudaStream_t s);
 int conv_tsweep_init();
-int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const void* w35, const float* bias, void* y,
+int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const void* w35, const float* bias_host, void* y,
                             int pool, cudaStream_t s, int force_per_frame = 0);
 // conv_bc_fused.cu (s2 bottleneck tail: 1x3x3 64->64 + ReLU, then 1x1x1 64->256 + residual + ReLU, one kernel)
 bool conv_bc_fused_supported(const ConvProblem& b, const ConvProblem& c);
 int conv_bc_fused_launch(const ConvProblem& b, const ConvProblem& c, cudaStream_t s);
 int conv_bc_fused_init();
-int ftcn_stem_umma_launch(const void* clip_phys, int B, int T, int S, const void* w2, const float* bias, void* y,
+int ftcn_stem_umma_launch(const void* clip_phys, int B, int T, int S, const void* w2, const float* bias_host, void* y,
                           cudaStream_t s);
 // pool_head.cu
 int maxpool_spatial_launch(const void* x, void* y, int B, int T, int H, int W, int C, bool is_bf16,

@@ -24,6 +24,8 @@
 // the even frame waits in the 128 spare TMEM columns (tcgen05.st, 2 channels per column), the odd frame's epilogue takes
 // the element-wise max with it and stores the pooled tile: the un-pooled 256-channel tensor is never written.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "../../include/afb200.h"
 #include "common.cuh"
@@ -45,14 +47,17 @@ constexpr int F_TILE_BYTES = 128 * 128;         // 128 pixels x 64 channels bf16
 // so two of the four 16 KB slots suffice.
 constexpr int f_smem(bool shortcut) {
   return F_WB_BYTES + (shortcut ? 2 : 1) * F_WC_BYTES + F_A_STAGES * F_A_BYTES + F_TILE_BYTES + (shortcut ? 2 : 4) * F_TILE_BYTES +
-         (F_MID + F_OUT) * 4 + 32 * 8 + 16 + 1024;
+         32 * 8 + 16 + 1024;
 }
 
 struct FusedParams {
-  const float* bias_b;
-  const float* bias_c;
+  // biases travel in the kernel parameters (constant bank): the epilogues add them as constant-cache operands instead of
+  // shared-memory loads -- the shared-memory data pipe is this kernel's limiter (tensor-core operand reads + staging)
+  float bias_b[F_MID];
+  float bias_c[F_OUT];
   int x_tiles, y_tiles, frames;     // tiles per row / column of a frame, B*T frames
   int num_tiles;                    // work items per grid: tiles, or (kPoolT) frame-pair units of two tiles each
+  int prefetch;                     // L2-prefetch the next tile's inputs (AFB200_NO_L2_PREFETCH=1 turns it off)
 };
 
 // The j-th tile of this CTA.  Plain: tile = blockIdx.x + j * gridDim.x over (x tile, y tile, frame).  kPoolT: unit
@@ -111,9 +116,7 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   uint8_t* smem_a = smem_wc + WC_BYTES;
   uint8_t* smem_yb = smem_a + F_A_STAGES * F_A_BYTES;
   uint8_t* smem_slot = smem_yb + F_TILE_BYTES;                 // [2 groups][2 (1 with kShortcut) slots] x 16 KB
-  float* bias_b_s = reinterpret_cast<float*>(smem_slot + N_SLOTS * F_TILE_BYTES);
-  float* bias_c_s = bias_b_s + F_MID;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(bias_c_s + F_OUT);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_slot + N_SLOTS * F_TILE_BYTES);
   uint64_t* a_empty = a_full + F_A_STAGES;
   uint64_t* w_full = a_empty + F_A_STAGES;
   uint64_t* accb_full = w_full + 1;       // [2]
@@ -152,8 +155,6 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < F_MID + F_OUT; i += F_THREADS)
-    bias_b_s[i] = i < F_MID ? __ldg(p.bias_b + i) : __ldg(p.bias_c + i - F_MID);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -185,10 +186,28 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       __syncwarp();
       if (++stage == F_A_STAGES) { stage = 0; phase ^= 1; }
     };
+    // Everything tile j+1 will read from global memory is pulled into L2 while tile j is loaded: the centre halo box
+    // (its 1-pixel side columns are neighbouring tiles' centres), the shortcut input tile or the four residual chunks.
+    auto prefetch_l2 = [&](int jn) {
+      if (!p.prefetch || !tiles.valid(jn)) return;
+      int xt, yt, r;
+      tiles.coords(jn, xt, yt, r);
+      if (elect_one()) {
+        tma_prefetch_l2_5d(&tm_a, 0, xt * FX, yt * FR - 1, r, 0);
+        if (kShortcut) {
+          tma_prefetch_l2_5d(&tm_x, 0, xt * FX, yt * FR, r, 0);
+        } else {
+          for (int c = 0; c < 4; ++c) tma_prefetch_l2_4d(&tm_r, c * 64, xt * FX, yt * FR, r);
+        }
+      }
+      __syncwarp();
+    };
     int j = 0;
+    prefetch_l2(0);
     for (; tiles.valid(j); ++j) {
       int xt, yt, r;                                      // r = frame index b*T + t
       tiles.coords(j, xt, yt, r);
+      prefetch_l2(j + 1);
       for (int dx = 0; dx < 3; ++dx) {
         mbar_wait(&a_empty[stage], phase ^ 1);
         if (elect_one()) {
@@ -290,8 +309,8 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float f0 = fmaxf(__uint_as_float(v[q * 8 + 2 * e]) + bias_b_s[q * 8 + 2 * e], 0.f);
-          const float f1 = fmaxf(__uint_as_float(v[q * 8 + 2 * e + 1]) + bias_b_s[q * 8 + 2 * e + 1], 0.f);
+          const float f0 = fmaxf(__uint_as_float(v[q * 8 + 2 * e]) + p.bias_b[q * 8 + 2 * e], 0.f);
+          const float f1 = fmaxf(__uint_as_float(v[q * 8 + 2 * e + 1]) + p.bias_b[q * 8 + 2 * e + 1], 0.f);
           o2[e] = __floats2bfloat162_rn(f0, f1);
         }
         *reinterpret_cast<uint4*>(smem_yb + row * 128 + ((q ^ (row & 7)) << 4)) = o;
@@ -353,7 +372,7 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           tc_fence_before();
           mbar_arrive(accc_empty);
         }
-        const float* bias = bias_c_s + chunk * 64;
+        const float* bias = p.bias_c + chunk * 64;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           uint8_t* pa = s_io + row * 128 + ((q ^ (row & 7)) << 4);
@@ -458,7 +477,7 @@ int conv_bc_fused_init() {
 // With c.x2 set (projection shortcut fused into c: pointwise, stride 1, 64 -> 256 over the block input c.x2, biases
 // pre-summed in c.bias) there is no residual.  With c.pool_t set, y is the temporally max-pooled output [B,T/2,H,W,256].
 bool conv_bc_fused_supported(const ConvProblem& b, const ConvProblem& c) {
-  if (!g_f_encode || f_smem(c.x2 != nullptr) > g_f_max_smem) return false;
+  if (!g_f_encode || f_smem(c.x2 != nullptr) > g_f_max_smem || !b.bias_host || !c.bias_host) return false;
   if (b.Cin != F_MID || b.Cout != F_MID || b.kt != 1 || b.kh != 3 || b.kw != 3 || b.st != 1 || b.sh != 1 || b.sw != 1 ||
       b.pt != 0 || b.ph != 1 || b.pw != 1 || !b.relu || b.res || b.pool_hw || b.pool_t || b.x2)
     return false;
@@ -478,9 +497,14 @@ bool conv_bc_fused_supported(const ConvProblem& b, const ConvProblem& c) {
 
 int conv_bc_fused_launch(const ConvProblem& b, const ConvProblem& c, cudaStream_t s) {
   FusedParams fp;
-  fp.bias_b = b.bias; fp.bias_c = c.bias;
+  memcpy(fp.bias_b, b.bias_host, sizeof(fp.bias_b));
+  memcpy(fp.bias_c, c.bias_host, sizeof(fp.bias_c));
   fp.x_tiles = b.Wo / FX; fp.y_tiles = (b.Ho + FR - 1) / FR; fp.frames = b.B * b.To;
   const bool shortcut = c.x2 != nullptr, pool_t = c.pool_t != 0;
+  // measured on B200 (32 clips): prefetching the next tile helps the shortcut form (0.586 -> 0.563 ms) and costs the
+  // residual forms 2-20 % (the residual chunks are already TMA-prefetched two chunks ahead; extra L2 requests only compete)
+  static const char* pf = getenv("AFB200_L2_PREFETCH");
+  fp.prefetch = pf ? atoi(pf) : (shortcut ? 1 : 0);
   fp.num_tiles = (pool_t ? fp.frames / 2 : fp.frames) * fp.y_tiles * fp.x_tiles;
   alignas(64) CUtensorMap ta, twb, twc, tr, ty, tx, tws;
   {

@@ -21,6 +21,7 @@
 // Stride 1 only; no residual (neither the stem nor `b` convs have one:
 // altfreezing/slowfast/models/stem_helper.py:173-178, resnet_helper.py:311-326).
 #include <cuda.h>
+#include <string.h>
 
 #include "../../include/afb200.h"
 #include "common.cuh"
@@ -36,7 +37,9 @@ constexpr int RB_THREADS = 320;   // TMA warp, MMA warp, 2 epilogue warpgroups
 constexpr int RB_OUT_BYTES = 128 * 64 * 2;
 
 struct RowsParams {
-  const float* bias;
+  // the bias travels in the launch parameters (constant bank): the epilogues add it as constant-cache operands instead of
+  // shared-memory loads, which compete with the tensor cores' operand reads for the shared-memory data pipe
+  float bias_v[RB_N];
   int Cin, kt, kh, kw, pt, ph, pw;
   int B, To, Ho, Wo;
   int x_tiles, y_tiles, num_tiles, num_units;
@@ -46,6 +49,7 @@ struct RowsParams {
   int a_tx_bytes;      // bytes one A box actually delivers (mbarrier expect_tx)
   int w_buf_bytes;     // kh * 64 * 128
   int w_resident;      // all phases' weights fit in smem: loaded once per CTA instead of once per unit
+  int prefetch;        // stem sweep: L2-prefetch the next unit's boxes
   int pool;            // fused 3x3/2 max-pool epilogue
   bf16* pool_out;      // [B*To, Ho/2, Wo/2, 64], zero-initialised by the caller
 };
@@ -84,7 +88,7 @@ __device__ __forceinline__ void rows_epilogue_tile(const RowsParams& p, const CU
     float f[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      f[e] = __uint_as_float(v[q * 8 + e]) + bias_s[q * 8 + e];
+      f[e] = __uint_as_float(v[q * 8 + e]) + p.bias_v[q * 8 + e];
       if (p.relu) f[e] = fmaxf(f[e], 0.f);
     }
     uint4 o;
@@ -200,7 +204,6 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + RB_N) bias_s[threadIdx.x - 64] = __ldg(p.bias + threadIdx.x - 64);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -401,7 +404,6 @@ stem_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + RB_N) bias_s[threadIdx.x - 64] = __ldg(p.bias + threadIdx.x - 64);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -428,6 +430,16 @@ stem_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const int yt = r % p.y_tiles; r /= p.y_tiles;
       const int tg = r % tgroups;
       const int b = r / tgroups;
+      if (p.prefetch && unit + (int)gridDim.x < p.num_units) {
+        // the NEXT unit's 8 boxes go to L2 now: with two ring slots the HBM latency of a box is longer than its MMAs
+        int rn = unit + gridDim.x;
+        const int xn = rn % p.x_tiles; rn /= p.x_tiles;
+        const int yn = rn % p.y_tiles; rn /= p.y_tiles;
+        const int tn = rn % tgroups, bn = rn / tgroups;
+        if (elect_one())
+          for (int f = 0; f < RB_G + 4; ++f) tma_prefetch_l2_5d(&tm_a, 0, xn * RB_X, 2 * yn * RB_R, tn * RB_G + f, bn);
+        __syncwarp();
+      }
       for (int f = 0; f < RB_G + 4; ++f) {          // padded frame index of logical frame tg*4 - 2 + f
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
@@ -588,7 +600,6 @@ ftcn_stem_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const bf16* __re
   // weights (constants, 12 KB, already in operand layout) and bias: plain copies
   for (int i = threadIdx.x; i < FT_W_BYTES / 16; i += RB_THREADS)
     reinterpret_cast<uint4*>(smem_w)[i] = __ldg(reinterpret_cast<const uint4*>(w2) + i);
-  if (threadIdx.x < RB_N) bias_s[threadIdx.x] = __ldg(p.bias + threadIdx.x);
   fence_proxy_async_smem();                            // the tensor core reads smem_w through the async proxy
   tc_fence_before();
   __syncthreads();
@@ -693,7 +704,7 @@ ftcn_stem_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const bf16* __re
               const int i = h * 8 + 2 * e + u;
               const float m = fmaxf(fmaxf(__uint_as_float(w[0][i]), __uint_as_float(w[1][i])),
                                     fmaxf(__uint_as_float(w[2][i]), __uint_as_float(w[3][i])));
-              f[u] = fmaxf(m + bias_s[q * 16 + i], 0.f);
+              f[u] = fmaxf(m + p.bias_v[q * 16 + i], 0.f);
             }
             o2[e] = __floats2bfloat162_rn(f[0], f[1]);
           }
@@ -759,7 +770,7 @@ int conv_rows_init() {
 
 bool conv_rows_supported(const ConvProblem& p) {
   if (!g_rows_encode) return false;
-  if (p.Cout != RB_N || p.Cin % 64 != 0 || p.res != nullptr) return false;
+  if (p.Cout != RB_N || p.Cin % 64 != 0 || p.res != nullptr || !p.bias_host) return false;
   if (p.st != 1 || p.sh != 1 || p.sw != 1) return false;
   if (p.Wo % RB_X != 0 || p.kh < 2 || p.kh > 8) return false;    // needs vertical taps to pay off
   if (p.pool_hw && (!p.relu || (p.Ho & 1) || (p.Wo & 1))) return false;
@@ -770,8 +781,8 @@ bool conv_rows_supported(const ConvProblem& p) {
 }
 
 int conv_rows_launch(const ConvProblem& p, cudaStream_t s) {
-  RowsParams rp;
-  rp.bias = p.bias; rp.Cin = p.Cin; rp.kt = p.kt; rp.kh = p.kh; rp.kw = p.kw; rp.pt = p.pt; rp.ph = p.ph; rp.pw = p.pw;
+  RowsParams rp = {};
+  memcpy(rp.bias_v, p.bias_host, sizeof(rp.bias_v)); rp.Cin = p.Cin; rp.kt = p.kt; rp.kh = p.kh; rp.kw = p.kw; rp.pt = p.pt; rp.ph = p.ph; rp.pw = p.pw;
   rp.B = p.B; rp.To = p.To; rp.Ho = p.Ho; rp.Wo = p.Wo; rp.relu = p.relu;
   rp.pool = p.pool_hw; rp.pool_out = (bf16*)p.y;
   rp.x_tiles = p.Wo / RB_X;
@@ -837,13 +848,13 @@ int conv_rows_launch(const ConvProblem& p, cudaStream_t s) {
 // overlapping windows.  GEMM K = 35 (dt,dy) taps x 32; the 7 dy taps are views of one 37-row box (+512 B each),
 // output rows are 2 input rows = 1024 B apart (the descriptor's SBO).  Weights: [35][64][32] bf16.
 // y is the zero-initialised POOLED output (fused MaxPool3d [1,3,3]/[1,2,2]) or the dense conv output.
-int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const void* w35, const float* bias, void* y,
+int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const void* w35, const float* bias_host, void* y,
                             int pool, cudaStream_t s, int force_per_frame) {
   if (!g_rows_encode) { set_error("conv_stem_direct: not initialised"); return AF_ERR_INVALID; }
   const int Ho = S / 2, Wo = S / 2, Tp = T + 4, Hp = S + 6, Wp = S + 8;
   if ((S & 1) || Wo % RB_X) { set_error("conv_stem_direct: unsupported clip size %d", S); return AF_ERR_INVALID; }
-  RowsParams rp;
-  rp.bias = bias; rp.Cin = 64; rp.kt = 5; rp.kh = 7; rp.kw = 1; rp.pt = 0; rp.ph = 0; rp.pw = 0;
+  RowsParams rp = {};
+  memcpy(rp.bias_v, bias_host, sizeof(rp.bias_v)); rp.Cin = 64; rp.kt = 5; rp.kh = 7; rp.kw = 1; rp.pt = 0; rp.ph = 0; rp.pw = 0;
   rp.B = B; rp.To = T; rp.Ho = Ho; rp.Wo = Wo; rp.relu = 1;
   rp.x_tiles = Wo / RB_X; rp.y_tiles = (Ho + RB_R - 1) / RB_R;
   rp.num_tiles = B * T * rp.y_tiles * rp.x_tiles;
@@ -854,6 +865,8 @@ int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const vo
   rp.w_buf_bytes = 7 * RB_N * 64;
   rp.pool = pool; rp.pool_out = (bf16*)y;
   rp.w_resident = 0;
+  static const char* pf = getenv("AFB200_L2_PREFETCH");      // measured: 1.28 -> 1.45 ms with it (the clip is L2-hot from K1)
+  rp.prefetch = pf ? atoi(pf) : 0;
   const int fixed = 2 * rp.w_buf_bytes + 2 * RB_OUT_BYTES + RB_N * 4 + 32 * 8 + 16 + 1024;
   rp.stages = (g_rows_max_smem - fixed) / rp.a_stage_bytes;
   if (rp.stages > 8) rp.stages = 8;
@@ -910,13 +923,13 @@ int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const vo
 // FTCN-TT stem on the tensor cores (ftcn_stem_umma_kernel).  clip_phys: padded NDHWC4 bf16 clip [B, T+4, S+6, S+8, 4]
 // whose logical pixel (0,0) sits at padded (4, 4); w2: [6][128][8] bf16 in operand layout (api.cu: upload_ftcn_stem_w2);
 // y: ZERO-INITIALISED pooled output [B*T, S/4, S/4, 64].
-int ftcn_stem_umma_launch(const void* clip_phys, int B, int T, int S, const void* w2, const float* bias, void* y, cudaStream_t s) {
+int ftcn_stem_umma_launch(const void* clip_phys, int B, int T, int S, const void* w2, const float* bias_host, void* y, cudaStream_t s) {
   if (!g_rows_encode) { set_error("ftcn_stem_umma: not initialised"); return AF_ERR_INVALID; }
   const int M2 = S / 2;                                  // 112-level map
   if ((S % 32) != 0) { set_error("ftcn_stem_umma: clip size %d is not a multiple of 32", S); return AF_ERR_INVALID; }
   const int Tp = T + 4, Hp = S + 6, Wp = S + 8;
   RowsParams rp = {};
-  rp.bias = bias; rp.B = B; rp.To = T; rp.Ho = M2; rp.Wo = M2; rp.relu = 1;
+  memcpy(rp.bias_v, bias_host, sizeof(rp.bias_v)); rp.B = B; rp.To = T; rp.Ho = M2; rp.Wo = M2; rp.relu = 1;
   rp.x_tiles = M2 / RB_X; rp.y_tiles = (M2 + RB_R - 1) / RB_R;
   rp.num_tiles = B * T * rp.y_tiles * rp.x_tiles;
   rp.pool = 1; rp.pool_out = (bf16*)y;

@@ -77,6 +77,19 @@ __device__ __forceinline__ void tma_load_im2col_5d(void* dst, const CUtensorMap*
       "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "h"(ow), "h"(oh), "h"(od)
       : "memory");
 }
+// L2 prefetch of a tile (no shared memory, no barrier): issued a work unit ahead so that the later TMA load of the same box
+// finds its lines in L2 -- with only two or three ring slots per CTA the HBM latency of a box (1.5-2 us under load) is
+// otherwise longer than the MMAs of the boxes in flight.
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"((uint64_t)m), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_5d(const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"((uint64_t)m), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int x, int y) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)m),
                "r"(smem_u32(src)), "r"(x), "r"(y)
