@@ -139,7 +139,8 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_wb);
     tma_prefetch_desc(&tm_wc);
-    if (kShortcut) { tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_ws); } else { tma_prefetch_desc(&tm_r); }
+    if (kShortcut) { tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_ws); }
+    tma_prefetch_desc(&tm_r);
     tma_prefetch_desc(&tm_y);
     for (int i = 0; i < F_A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     mbar_init(w_full, 1);
@@ -341,7 +342,48 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         if (tiles.valid(pre_j)) issue_res(j);
     uint32_t k = 0;
     int it = 0;
-    for (; tiles.valid(it); ++it) {
+    if constexpr (kShortcut) {
+      // No residual tile to wait for, and only 16 KB of staging per group: the output goes out in 32-channel half chunks
+      // through two 8 KB sub-slots (SWIZZLE_64B boxes), so the TMA store of one half is read out of shared memory while
+      // the next half is computed -- with whole 64-channel chunks every chunk waited for the previous store's read.
+      for (; tiles.valid(it); ++it) {
+        int xt, yt, r;
+        tiles.coords(it, xt, yt, r);
+        mbar_wait(accc_full, it & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int half = 2 * eg; half < 8; half += (half & 1) ? 3 : 1, ++k) {      // halves (2eg, 2eg+1, 2eg+4, 2eg+5) of 8
+          uint8_t* s_io = slot_g + (k & 1) * (F_TILE_BYTES / 2);
+          uint32_t v[32];
+          TMEM_LD_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + ACCC_COL + half * 32, v);
+          if (et == 0) tma_store_wait_read<1>();  // the store that last read this sub-slot (two halves ago) has drained it
+          wg_bar_sync(2 + eg);
+          tmem_ld_wait();
+          if (half == 2 * eg + 5) {               // this group's last read of acc_c for the tile
+            tc_fence_before();
+            mbar_arrive(accc_empty);
+          }
+          const float* bias = p.bias_c + half * 32;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o2[e] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[q * 8 + 2 * e]) + bias[q * 8 + 2 * e], 0.f),
+                                            fmaxf(__uint_as_float(v[q * 8 + 2 * e + 1]) + bias[q * 8 + 2 * e + 1], 0.f));
+            *reinterpret_cast<uint4*>(s_io + row * 64 + ((q ^ ((row >> 1) & 3)) << 4)) = o;      // SWIZZLE_64B
+          }
+          fence_proxy_async_smem();
+          wg_bar_sync(2 + eg);
+          if (et == 0) {
+            f_tma_store_4d(&tm_r, s_io, half * 32, xt * FX, yt * FR, r);      // tm_r: the 32-channel-box view of y
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    for (; !kShortcut && tiles.valid(it); ++it) {
       int xt, yt, r;
       tiles.coords(it, xt, yt, r);
       const bool hold_phase = kPoolT && !(it & 1);      // even frame of a pair: the output waits in TMEM
@@ -437,10 +479,10 @@ EncodeTiledFn g_f_encode = nullptr;
 int g_f_sms = 0, g_f_max_smem = 0;
 
 int f_encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
-             const char* what) {
+             const char* what, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = g_f_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r); return AF_ERR_CUDA; }
   return AF_OK;
@@ -533,8 +575,11 @@ int conv_bc_fused_launch(const ConvProblem& b, const ConvProblem& c, cudaStream_
     cuuint64_t dims[4] = {(cuuint64_t)F_OUT, (cuuint64_t)b.Wo, (cuuint64_t)b.Ho,
                           (cuuint64_t)((which && pool_t) ? fp.frames / 2 : fp.frames)};
     cuuint64_t strides[3] = {(cuuint64_t)F_OUT * 2, (cuuint64_t)b.Wo * F_OUT * 2, (cuuint64_t)b.Ho * b.Wo * F_OUT * 2};
-    cuuint32_t box[4] = {64, FX, FR, 1};
-    int rc = f_encode(which ? &ty : &tr, (which || shortcut) ? c.y : c.res, 4, dims, strides, box, which ? "fused Y" : "fused R");
+    // shortcut form: there is no residual; `tr` is the 32-channel-box (SWIZZLE_64B) view of y its epilogue stores through
+    const bool y32 = !which && shortcut;
+    cuuint32_t box[4] = {(cuuint32_t)(y32 ? 32 : 64), FX, FR, 1};
+    int rc = f_encode(which ? &ty : &tr, (which || shortcut) ? c.y : c.res, 4, dims, strides, box, which ? "fused Y" : "fused R",
+                      y32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   tx = ta; tws = twc;
