@@ -11,13 +11,16 @@
 // Work unit: one 8-wide x 16-tall output tile (128 pixels) of one frame.
 //   warp 0      TMA producer: the three dx-shifted 18-row halo boxes of the tile (the kh = 3 vertical taps are views of
 //               one box, as in conv_rows.cu); W_b (9 x 64 x 64) and W_c (256 x 64) are loaded once and stay resident
-//   warp 1      MMA issuer: b(i) -> acc_b[i & 1] (128 x 64 fp32, TMEM), then c(i-1): Yb(i-1) [128 x 64 bf16, smem] x W_c^T
+//   warp 1      MMA issuer: b(i) -> acc_b (128 x 64 fp32, TMEM), then c(i-1): Yb(i-1) [128 x 64 bf16, TMEM] x W_c^T
 //               -> acc_c (128 x 256): c of a tile is issued AFTER b of the next one so the first epilogue hides behind it
-//   warps 2-5   epilogue 1: acc_b -> +bias_b, ReLU, bf16 -> Yb in the K-major SWIZZLE_128B layout the c MMA reads
+//   warps 2-5   epilogue 1: acc_b -> +bias_b, ReLU, bf16 -> Yb written back to TENSOR MEMORY (tcgen05.st, two channels per
+//               column): the c MMA takes its A operand from TMEM, so the intermediate costs neither 16 KB of shared
+//               memory (which buys the third halo-ring slot: two slots could not cover a box's load latency) nor any
+//               shared-memory bandwidth
 //   warps 6-13  epilogue 2 (two warpgroups on alternate 64-channel chunks): acc_c -> +bias_c +residual -> ReLU -> bf16,
 //               IN PLACE in the slot the residual tile was TMA-loaded into, then a TMA store from that slot
-// TMEM: acc_b x2 (128 columns) + acc_c (256 columns).  Shared memory: 72 + 32 KB weights, 2 x 18 KB halo ring, 16 KB Yb,
-// 4 x 16 KB residual/output slots = 222.5 KB.
+// TMEM: acc_b (64 columns) + Yb x2 (2 x 32) + acc_c (256) [+ 128 held output, kPoolT].  Shared memory: 72 + 32 KB weights,
+// 3 x 18 KB halo ring, 4 x 16 KB residual/output slots = 223 KB.
 //
 // kPoolT (last block of s2): the next stage's MaxPool3d k = s = [2,1,1] (video_model_builder.py:474-480,566-568) is
 // fused as well.  A CTA's consecutive tiles are the SAME spatial tile of frames 2j and 2j+1; the finished bf16 output of
@@ -37,7 +40,7 @@ namespace {
 constexpr int FX = 8, FR = 16;                  // tile: 8 columns x 16 rows
 constexpr int F_MID = 64, F_OUT = 256;          // channels: b 64 -> 64, c 64 -> 256
 constexpr int F_THREADS = 32 * 14;
-constexpr int F_A_STAGES = 2;
+constexpr int F_A_STAGES = 3;
 constexpr int F_A_BYTES = (FR + 2) * FX * 128;  // 18 rows x 8 pixels x 64 bf16
 constexpr int F_WB_BYTES = 9 * F_MID * 128;
 constexpr int F_WC_BYTES = F_OUT * 128;
@@ -46,7 +49,7 @@ constexpr int F_TILE_BYTES = 128 * 128;         // 128 pixels x 64 channels bf16
 // GEMM, operand = the block INPUT tile, which travels through the halo ring as a 4th box); no residual tile is loaded,
 // so two of the four 16 KB slots suffice.
 constexpr int f_smem(bool shortcut) {
-  return F_WB_BYTES + (shortcut ? 2 : 1) * F_WC_BYTES + F_A_STAGES * F_A_BYTES + F_TILE_BYTES + (shortcut ? 2 : 4) * F_TILE_BYTES +
+  return F_WB_BYTES + (shortcut ? 2 : 1) * F_WC_BYTES + F_A_STAGES * F_A_BYTES + (shortcut ? 2 : 4) * F_TILE_BYTES +
          32 * 8 + 16 + 1024;
 }
 
@@ -114,22 +117,22 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   uint8_t* smem_wb = smem;
   uint8_t* smem_wc = smem_wb + F_WB_BYTES;
   uint8_t* smem_a = smem_wc + WC_BYTES;
-  uint8_t* smem_yb = smem_a + F_A_STAGES * F_A_BYTES;
-  uint8_t* smem_slot = smem_yb + F_TILE_BYTES;                 // [2 groups][2 (1 with kShortcut) slots] x 16 KB
+  uint8_t* smem_slot = smem_a + F_A_STAGES * F_A_BYTES;        // [2 groups][2 (1 with kShortcut) slots] x 16 KB
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_slot + N_SLOTS * F_TILE_BYTES);
   uint64_t* a_empty = a_full + F_A_STAGES;
   uint64_t* w_full = a_empty + F_A_STAGES;
-  uint64_t* accb_full = w_full + 1;       // [2]
-  uint64_t* accb_empty = accb_full + 2;   // [2]
-  uint64_t* yb_full = accb_empty + 2;
-  uint64_t* yb_empty = yb_full + 1;
-  uint64_t* accc_full = yb_empty + 1;
+  uint64_t* accb_full = w_full + 1;
+  uint64_t* accb_empty = accb_full + 1;
+  uint64_t* yb_full = accb_empty + 1;     // [2]
+  uint64_t* yb_empty = yb_full + 2;       // [2]
+  uint64_t* accc_full = yb_empty + 2;
   uint64_t* accc_empty = accc_full + 1;
   uint64_t* res_full = accc_empty + 1;    // [2 groups][2 slots]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 4);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t YB_COL = F_MID;                   // two bf16 [128 x 64] tiles, 32 columns each
   constexpr uint32_t ACCC_COL = 2 * F_MID;
   constexpr uint32_t HOLD_COL = ACCC_COL + F_OUT;      // kPoolT: the even frame's bf16 output, 2 channels per column
   static_assert(!(kShortcut && kPoolT), "the pooled variant is the identity-residual block");
@@ -144,9 +147,9 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     tma_prefetch_desc(&tm_y);
     for (int i = 0; i < F_A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&accb_full[i], 1); mbar_init(&accb_empty[i], 128); }
-    mbar_init(yb_full, 128);
-    mbar_init(yb_empty, 1);
+    mbar_init(accb_full, 1);
+    mbar_init(accb_empty, 128);
+    for (int i = 0; i < 2; ++i) { mbar_init(&yb_full[i], 128); mbar_init(&yb_empty[i], 1); }
     mbar_init(accc_full, 1);
     mbar_init(accc_empty, 256);
     for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
@@ -227,19 +230,21 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     constexpr uint32_t idesc_b = make_idesc(F_MID), idesc_c = make_idesc(F_OUT);
     mbar_wait(w_full, 0);
     tc_fence_after();
-    const uint32_t wb_addr = smem_u32(smem_wb), wc_addr = smem_u32(smem_wc), yb_addr = smem_u32(smem_yb);
+    const uint32_t wb_addr = smem_u32(smem_wb), wc_addr = smem_u32(smem_wc);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     auto issue_c = [&](int j) {                   // c of this CTA's j-th tile: Yb x W_c^T (+ X x W_s^T) -> acc_c
-      mbar_wait(yb_full, j & 1);
+      const int ys = j & 1;
+      mbar_wait(&yb_full[ys], (j >> 1) & 1);
       mbar_wait(accc_empty, (j & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t adesc = make_smem_desc(yb_addr), bdesc = make_smem_desc(wc_addr);
+        const uint32_t a_tmem = tmem_base + YB_COL + ys * (F_MID / 2);
+        const uint64_t bdesc = make_smem_desc(wc_addr);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + ACCC_COL, adesc + 2 * k, bdesc + 2 * k, idesc_c, k != 0 ? 1u : 0u);
-        umma_commit(yb_empty);                    // Yb may be overwritten once these have read it
+        for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_base + ACCC_COL, a_tmem + 8 * k, bdesc + 2 * k, idesc_c, k != 0 ? 1u : 0u);
+        umma_commit(&yb_empty[ys]);               // this Yb buffer may be overwritten once these have read it
         if (!kShortcut) umma_commit(accc_full);
       }
       __syncwarp();
@@ -258,10 +263,11 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       }
     };
     for (; tiles.valid(it); ++it) {
-      const int as = it & 1;
-      mbar_wait(&accb_empty[as], ((it >> 1) & 1) ^ 1);
+      // acc_b is single-buffered: c of the previous tile is queued between two b's, which is all the time the first
+      // epilogue needs to read it out
+      mbar_wait(accb_empty, (it & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * F_MID;
+      const uint32_t d_tmem = tmem_base;
       for (int dx = 0; dx < 3; ++dx) {
         mbar_wait(&a_full[stage], phase);
         tc_fence_after();
@@ -280,7 +286,7 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         __syncwarp();
         if (++stage == F_A_STAGES) { stage = 0; phase ^= 1; }
       }
-      if (elect_one()) umma_commit(&accb_full[as]);
+      if (elect_one()) umma_commit(accb_full);
       __syncwarp();
       // c of a tile is issued after b of the NEXT tile, so epilogue 1 (acc_b -> Yb) hides behind those MMAs
       if (it >= 1) issue_c(it - 1);
@@ -293,31 +299,28 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     const int row = quad * 32 + lane;
     int it = 0;
     for (; tiles.valid(it); ++it) {
-      const int as = it & 1;
-      mbar_wait(&accb_full[as], (it >> 1) & 1);
+      mbar_wait(accb_full, it & 1);
       tc_fence_after();
       uint32_t v[64];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * F_MID;
-      TMEM_LD_32x32b_x32(taddr, v);
-      TMEM_LD_32x32b_x32(taddr + 32, (v + 32));
+      const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+      TMEM_LD_32x32b_x32(tlane, v);
+      TMEM_LD_32x32b_x32(tlane + 32, (v + 32));
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&accb_empty[as]);
-      mbar_wait(yb_empty, (it & 1) ^ 1);          // c of the previous tile has read Yb
+      mbar_arrive(accb_empty);
+      uint32_t y[32];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        uint4 o;
-        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float f0 = fmaxf(__uint_as_float(v[q * 8 + 2 * e]) + p.bias_b[q * 8 + 2 * e], 0.f);
-          const float f1 = fmaxf(__uint_as_float(v[q * 8 + 2 * e + 1]) + p.bias_b[q * 8 + 2 * e + 1], 0.f);
-          o2[e] = __floats2bfloat162_rn(f0, f1);
-        }
-        *reinterpret_cast<uint4*>(smem_yb + row * 128 + ((q ^ (row & 7)) << 4)) = o;
+      for (int j = 0; j < 32; ++j) {
+        // even channel (even K) in the low half
+        y[j] = pack_bf16x2_relu(__uint_as_float(v[2 * j]) + p.bias_b[2 * j], __uint_as_float(v[2 * j + 1]) + p.bias_b[2 * j + 1]);
       }
-      fence_proxy_async_smem();                   // generic-proxy writes -> visible to the tensor core's async proxy
-      mbar_arrive(yb_full);
+      const int ys = it & 1;
+      mbar_wait(&yb_empty[ys], ((it >> 1) & 1) ^ 1);      // c of the tile two back has read this Yb buffer
+      tc_fence_after();
+      TMEM_ST_32x32b_x32(tlane + YB_COL + ys * (F_MID / 2), y);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&yb_full[ys]);
     }
   } else {
     // ===================================================== epilogue 2 (warps 6-13): acc_c + residual -> y
@@ -367,11 +370,11 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 o;
-            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+            uint32_t* o2 = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              o2[e] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[q * 8 + 2 * e]) + bias[q * 8 + 2 * e], 0.f),
-                                            fmaxf(__uint_as_float(v[q * 8 + 2 * e + 1]) + bias[q * 8 + 2 * e + 1], 0.f));
+              o2[e] = pack_bf16x2_relu(__uint_as_float(v[q * 8 + 2 * e]) + bias[q * 8 + 2 * e],
+                                       __uint_as_float(v[q * 8 + 2 * e + 1]) + bias[q * 8 + 2 * e + 1]);
             *reinterpret_cast<uint4*>(s_io + row * 64 + ((q ^ ((row >> 1) & 3)) << 4)) = o;      // SWIZZLE_64B
           }
           fence_proxy_async_smem();
@@ -425,9 +428,10 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float f0 = fmaxf(__uint_as_float(v[q * 8 + 2 * e]) + bias[q * 8 + 2 * e] + __low2float(h2[e]), 0.f);
-            const float f1 = fmaxf(__uint_as_float(v[q * 8 + 2 * e + 1]) + bias[q * 8 + 2 * e + 1] + __high2float(h2[e]), 0.f);
-            o2[e] = __floats2bfloat162_rn(f0, f1);
+            const float f0 = __uint_as_float(v[q * 8 + 2 * e]) + bias[q * 8 + 2 * e] + __low2float(h2[e]);
+            const float f1 = __uint_as_float(v[q * 8 + 2 * e + 1]) + bias[q * 8 + 2 * e + 1] + __high2float(h2[e]);
+            const uint32_t pk = pack_bf16x2_relu(f0, f1);
+            o2[e] = *reinterpret_cast<const __nv_bfloat162*>(&pk);
           }
           if (kPoolT) {
             if (hold_phase) {

@@ -87,14 +87,16 @@ __device__ __forceinline__ void rows_epilogue_tile(const RowsParams& p, const CU
   for (int q = 0; q < 8; ++q) {
     float f[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      f[e] = __uint_as_float(v[q * 8 + e]) + p.bias_v[q * 8 + e];
-      if (p.relu) f[e] = fmaxf(f[e], 0.f);
-    }
+    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + p.bias_v[q * 8 + e];
     uint4 o;
-    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+    uint32_t* o2 = reinterpret_cast<uint32_t*>(&o);
+    if (p.relu) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+      for (int e = 0; e < 4; ++e) o2[e] = pack_bf16x2_relu(f[2 * e], f[2 * e + 1]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o2[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+    }
     *reinterpret_cast<uint4*>(sout + row * 128 + ((q ^ (row & 7)) << 4)) = o;
   }
   rows_store_or_pool(p, tm_y_ptr, sout, eg, et, xt, yt, r);

@@ -13,6 +13,7 @@
 // (altfreezing/slowfast/models/resnet_helper.py:268-281,313-316).  Warp roles / issue discipline as in
 // conv_umma.cu and conv_rows.cu.
 #include <cuda.h>
+#include <string.h>
 
 #include "../../include/afb200.h"
 #include "common.cuh"
@@ -30,7 +31,7 @@ constexpr int TS_OUT_BYTES = 128 * 64 * 2;
 constexpr int TS_MAX_STAGES = 8;
 
 struct TsParams {
-  const float* bias;
+  float bias_v[64];    // launch-parameter copy of the bias (constant bank operands in the epilogue)
   int cblocks;          // Cin / 64 (1..4)
   int B, T, HW;
   int ptiles;           // ceil(HW / 128)
@@ -89,7 +90,6 @@ conv_tsweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + TS_N) bias_s[threadIdx.x - 64] = __ldg(p.bias + threadIdx.x - 64);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -192,14 +192,16 @@ conv_tsweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         for (int q = 0; q < 8; ++q) {
           float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            f[e] = __uint_as_float(v[q * 8 + e]) + bias_s[q * 8 + e];
-            if (p.relu) f[e] = fmaxf(f[e], 0.f);
-          }
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + p.bias_v[q * 8 + e];
           uint4 o;
-          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+          uint32_t* o2 = reinterpret_cast<uint32_t*>(&o);
+          if (p.relu) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+            for (int e = 0; e < 4; ++e) o2[e] = pack_bf16x2_relu(f[2 * e], f[2 * e + 1]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o2[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+          }
           *reinterpret_cast<uint4*>(sout + row * 128 + ((q ^ (row & 7)) << 4)) = o;
         }
         fence_proxy_async_smem();
@@ -265,7 +267,7 @@ bool conv_tsweep_supported(const ConvProblem& p) {
   if (!g_ts_encode) return false;
   static const bool off = getenv("AFB200_NO_TSWEEP") != nullptr;
   if (off) return false;
-  if (p.Cout != TS_N || p.Cin % 64 != 0 || p.Cin > 256 || p.res != nullptr || p.pool_t || p.pool_hw) return false;
+  if (p.Cout != TS_N || p.Cin % 64 != 0 || p.Cin > 256 || p.res != nullptr || p.pool_t || p.pool_hw || !p.bias_host) return false;
   if (p.kt != 3 || p.kh != 1 || p.kw != 1 || p.st != 1 || p.sh != 1 || p.sw != 1 || p.pt != 1 || p.ph != 0 || p.pw != 0) return false;
   if (p.Ti % TS_G != 0 || p.To != p.Ti) return false;
   if (p.xsW != p.Cin || p.xsH != (long long)p.Wi * p.Cin || p.xsT != (long long)p.Hi * p.Wi * p.Cin ||
@@ -276,7 +278,7 @@ bool conv_tsweep_supported(const ConvProblem& p) {
 
 int conv_tsweep_launch(const ConvProblem& p, cudaStream_t s) {
   TsParams tp;
-  tp.bias = p.bias; tp.cblocks = p.Cin / 64; tp.B = p.B; tp.T = p.Ti; tp.HW = p.Hi * p.Wi;
+  memcpy(tp.bias_v, p.bias_host, sizeof(tp.bias_v)); tp.cblocks = p.Cin / 64; tp.B = p.B; tp.T = p.Ti; tp.HW = p.Hi * p.Wi;
   tp.ptiles = (tp.HW + 127) / 128;
   tp.num_units = p.B * (p.Ti / TS_G) * tp.ptiles;
   tp.relu = p.relu;

@@ -427,14 +427,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             f[2 * e + 1] += __high2float(h2[e]);
           }
         }
-        if (p.relu) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-        }
         uint4 o;
-        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+        uint32_t* o2 = reinterpret_cast<uint32_t*>(&o);
+        if (p.relu) {                              // ReLU inside the conversion (F2FP...RELU): no FMNMX per element
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+          for (int e = 0; e < 4; ++e) o2[e] = pack_bf16x2_relu(f[2 * e], f[2 * e + 1]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o2[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+        }
         *reinterpret_cast<uint4*>(sout + off) = o;
       }
       if (p.pool_t) {
