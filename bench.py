@@ -358,8 +358,8 @@ def run_ours(args):
         dt, h2d, d2h = legs.e2e_crop_leg(eng, B, n_e2e, 2, rank, dev)
         e2e = {"value": n_total * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "steps": n_e2e, "boundary": "crop",
-               "api": "afb200.live.FrameRing.put_rows (af_ring_put_rows) + af_crop_infer: per step every one of the %d streams "
-                      "uploads its 8 new decoded 720p frames (the rows under the face box) from pinned host memory into the "
+               "api": "afb200.live.FrameRing.put_boxes (af_ring_put_boxes) + af_crop_infer: per step every one of the %d streams "
+                      "uploads its 8 new decoded 720p frames (the pixels under the enlarged face box, af_ring_put_boxes) from pinned host memory into the "
                       "device ring, the host computes crop boxes + the similarity fit and the descriptors of the 32-frame "
                       "windows (stride 8), af_crop_infer warps/normalises/classifies, scores are read back; two steps in "
                       "flight" % B}

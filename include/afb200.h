@@ -224,6 +224,14 @@ af_status af_crop_u8(const af_frame_desc* frames_dev, const af_clip_geom* geom_d
 af_status af_ring_put_rows(uint8_t* ring_dev, int64_t slot_stride, int64_t pitch, int32_t n, const int32_t* slots,
                            const uint8_t* const* frames_host, const int32_t* row0, const int32_t* row1, void* stream);
 
+/* The same feed restricted to the face box: item i copies the pixels [x0,x1) x [y0,y1) of boxes_xyxy[4i..4i+3] (the
+ * enlarged crop box get_crop_box returns, altfreezing/test_tools/utils.py:13-24; byte columns widened to 16-byte
+ * multiples) with one strided host->device copy.  K1 never reads a pixel outside a frame's box (the reference pastes the
+ * crop onto a zero canvas, faster_crop_align_xray.py:60-75), so nothing else of the frame has to reach the device:
+ * about a third of the bytes of whole rows for a 720p call frame. */
+af_status af_ring_put_boxes(uint8_t* ring_dev, int64_t slot_stride, int64_t pitch, int32_t n, const int32_t* slots,
+                            const uint8_t* const* frames_host, const int32_t* boxes_xyxy, void* stream);
+
 /* K1 on its own (SURVEY.md 8b `crop_pack`): the same warp followed by the callers' pack step
  *   x = (float(u8) - 255*mean_c) / (255*std_c), NTHWC -> NCTHW   (demo.py:84-87,317-319; TEST2.py:147-158)
  * written straight into a caller tensor viewed as [B,3,T,S,S] with ELEMENT strides `out_strides`

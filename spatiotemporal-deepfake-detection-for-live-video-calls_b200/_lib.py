@@ -60,7 +60,7 @@ class AfClipGeom(C.Structure):
 EXPORTS = ("af_last_error", "af_version", "af_launch_count", "af_create", "af_destroy", "af_set_option",
            "af_forward", "af_forward_frames", "af_infer_u8", "af_infer_u8_host", "af_submit_u8_host", "af_wait", "af_crop_u8", "af_crop_infer",
            "af_conv_ndhwc", "af_conv_shortcut_ndhwc", "af_get_stage", "af_get_stat", "af_crop_pack", "af_stem_pool_ndhwc4", "af_set_global_option", "af_ring_put_rows", "af_conv_bc_fused_ndhwc",
-           "af_conv_bc_fused_tpool_ndhwc")
+           "af_conv_bc_fused_tpool_ndhwc", "af_ring_put_boxes")
 
 _lib = None
 
@@ -120,6 +120,8 @@ def lib():
     L.af_set_global_option.argtypes = [C.c_char_p, i64]
     L.af_ring_put_rows.restype = i32
     L.af_ring_put_rows.argtypes = [vp, i64, i64, i32, vp, vp, vp, vp, vp]
+    L.af_ring_put_boxes.restype = i32
+    L.af_ring_put_boxes.argtypes = [vp, i64, i64, i32, vp, vp, vp, vp]
     L.af_conv_bc_fused_ndhwc.restype = i32
     L.af_conv_bc_fused_ndhwc.argtypes = [vp, C.POINTER(AfConvDesc), C.POINTER(AfConvDesc), vp, vp, C.POINTER(AfConvDesc), vp, i32, i32, i32,
                                          i32, vp]

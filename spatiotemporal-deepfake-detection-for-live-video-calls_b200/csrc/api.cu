@@ -1244,6 +1244,30 @@ af_status af_ring_put_rows(uint8_t* ring_dev, int64_t slot_stride, int64_t pitch
   return AF_OK;
 }
 
+af_status af_ring_put_boxes(uint8_t* ring_dev, int64_t slot_stride, int64_t pitch, int32_t n, const int32_t* slots,
+                            const uint8_t* const* frames_host, const int32_t* boxes_xyxy, void* stream) {
+  if (!ring_dev || n < 0 || (n > 0 && (!slots || !frames_host || !boxes_xyxy)) || pitch <= 0 || slot_stride < pitch) {
+    set_error("af_ring_put_boxes: invalid arguments");
+    return AF_ERR_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int i = 0; i < n; ++i) {
+    const int32_t* b = boxes_xyxy + 4 * (size_t)i;
+    if (b[2] <= b[0] || b[3] <= b[1]) continue;
+    // byte columns of the box, widened to 16-byte multiples (K1's interior path fetches aligned 16-byte words)
+    int64_t c0 = (int64_t)b[0] * 3 / 16 * 16, c1 = ((int64_t)b[2] * 3 + 15) / 16 * 16;
+    if (c1 > pitch) c1 = pitch;
+    if (b[0] < 0 || b[1] < 0 || c0 >= c1 || (int64_t)b[3] * pitch > slot_stride || slots[i] < 0 || !frames_host[i]) {
+      set_error("af_ring_put_boxes: item %d out of range (slot %d, box %d,%d..%d,%d)", i, slots[i], b[0], b[1], b[2], b[3]);
+      return AF_ERR_INVALID;
+    }
+    const int64_t off = (int64_t)b[1] * pitch + c0;
+    AFB_CUDA(cudaMemcpy2DAsync(ring_dev + (int64_t)slots[i] * slot_stride + off, (size_t)pitch, frames_host[i] + off, (size_t)pitch,
+                               (size_t)(c1 - c0), (size_t)(b[3] - b[1]), cudaMemcpyHostToDevice, s));
+  }
+  return AF_OK;
+}
+
 af_status af_crop_pack(const af_frame_desc* frames_dev, const af_clip_geom* geom_dev, int32_t batch,
                        int32_t frames_per_clip, int32_t size, int32_t bgr, const float mean255[3], const float std255[3],
                        void* clip_out_dev, int32_t out_dtype, const int64_t out_strides[5], void* stream) {

@@ -202,6 +202,23 @@ class FrameRing:
                                          C.c_void_p(r1.ctypes.data), C.c_void_p(st.cuda_stream)), "af_ring_put_rows")
 
 
+    def put_boxes(self, slots, host_ptrs, boxes_xyxy, stream=None):
+        """Batched feed of the face boxes only (af_ring_put_boxes): pixels boxes_xyxy[i] = (x0, y0, x1, y1) of the
+        pinned host frame at address host_ptrs[i] -> the same pixels of ring slot slots[i], one strided copy each."""
+        import ctypes as C
+        import torch
+        from ._lib import check, lib
+        sl = np.ascontiguousarray(slots, np.int32)
+        hp = np.ascontiguousarray(host_ptrs, np.uint64)
+        bx = np.ascontiguousarray(boxes_xyxy, np.int32).reshape(-1, 4)
+        assert len(sl) == len(hp) == len(bx)
+        st = stream if stream is not None else torch.cuda.current_stream(self.buf.device)
+        with torch.cuda.device(self.buf.device):
+            check(lib().af_ring_put_boxes(C.c_void_p(self.buf.data_ptr()), self.buf.stride(0), self.buf.stride(1), len(sl),
+                                          C.c_void_p(sl.ctypes.data), C.c_void_p(hp.ctypes.data), C.c_void_p(bx.ctypes.data),
+                                          C.c_void_p(st.cuda_stream)), "af_ring_put_boxes")
+
+
 def ring_descriptors(ring: FrameRing, clips: List[list], size: int = 224):
     """Descriptors (device arrays) for windows whose frames all live in `ring`."""
     from .crop import pack_descriptors_ring

@@ -388,3 +388,31 @@ def test_fused_bc_kernel_with_projection_shortcut(dev, case):
     diff = (got - want).abs()
     assert diff.max().item() <= tol, (diff.max().item(), tol)
     assert (diff > 2.0 ** -7 * want.abs().clamp_min(1.0)).float().mean().item() < 2e-3
+
+
+# ------------------------------------------------------------------ ring feed restricted to the face boxes
+def test_ring_put_boxes_crops_bit_exactly_like_whole_frames(dev, state_dict):
+    """af_ring_put_boxes uploads only the enlarged face box of each frame; the rest of the ring slot holds stale bytes
+    (0xAB here).  K1 never reads outside a frame's box (faster_crop_align_xray.py:60-83: the crop is pasted on a zero
+    canvas), so the aligned clip must equal the one cropped from whole frames, which equals the oracle."""
+    from afb200 import live
+    from oracle import crop_oracle
+    H, W = 720, 1280
+    eng = afb200.Engine(state_dict, max_batch=1, precision="bf16")
+    ring = live.FrameRing(eng, 32, H, W)
+    ring.buf.fill_(0xAB)
+    track = synthetic.synthetic_track(3)
+    frames = [synthetic.synthetic_frame_u8(300 + f) for f in range(32)]
+    host = torch.from_numpy(np.stack(frames)).pin_memory()
+    bigs = np.stack([afb200.get_crop_box((H, W), b, 0.5) for b, _ in track])
+    ptrs = np.uint64(host.data_ptr()) + np.arange(32, dtype=np.uint64) * np.uint64(host.stride(0))
+    ring.put_boxes(np.arange(32), ptrs, bigs)
+    torch.cuda.synchronize()
+    # bytes far outside every box stay stale
+    assert int(ring.buf[0, 0, 0, 0]) == 0xAB
+    lm5_rel = [lm - big[:2][None] for (_, lm), big in zip(track, bigs)]
+    lt, wh, diff, tfm, trans = afb200.clip_geometry(bigs, lm5_rel, 224)
+    got = afb200.crop.crop_u8([ring.buf[i] for i in range(32)], bigs, [(tfm, lt, wh)], 32, 224)[0].cpu().numpy()
+    want = crop_oracle.crop_align_from_frames(frames, bigs, tfm, lt, wh, 224)
+    assert np.array_equal(got, want)
+    eng.close()

@@ -38,7 +38,7 @@ def _barrier():
 # --------------------------------------------------------------------------------------------- e2e, crop boundary
 class StreamFeeder:
     """`n_streams` face tracks over pinned host frames.  step(i) uploads the 8 new frames of every stream (only the
-    rows its face box covers) into the device ring and returns the descriptors of the stream's current 32-frame
+    pixels its enlarged face box covers) into the device ring and returns the descriptors of the stream's current 32-frame
     window: what a live caller does per stride (af_realtime.py:450-479), batched over the streams of one GPU."""
     SLOTS = 48
 
@@ -59,7 +59,7 @@ class StreamFeeder:
         self.put(0, 32)                                                                 # the first window's frames
 
     def put(self, f0, f1, stream=None):
-        """Upload frames [f0,f1) of every stream (rows of the enlarged face box only)."""
+        """Upload frames [f0,f1) of every stream (the enlarged face box only)."""
         nf = f1 - f0
         new = afb200.get_crop_boxes((H720, W1280), self.det[:, f0:f1].reshape(-1, 4), 0.5).reshape(self.n, nf, 4)
         self.bigs[:, f0:f1] = new
@@ -68,9 +68,10 @@ class StreamFeeder:
         slots = s_idx * self.SLOTS + f_idx % self.SLOTS
         src = (s_idx * 5 + f_idx) % self.host.shape[0]
         ptrs = np.uint64(self._base) + src.astype(np.uint64) * np.uint64(self._frame_bytes)
-        r0, r1 = new[:, :, 1].reshape(-1), new[:, :, 3].reshape(-1)
-        self.ring.put_rows(slots, ptrs, r0, r1, stream)
-        self.h2d_bytes += int(((r1 - r0) * self.host.stride(1)).sum())
+        bx = new.reshape(-1, 4)
+        self.ring.put_boxes(slots, ptrs, bx, stream)
+        c0, c1 = bx[:, 0] * 3 // 16 * 16, np.minimum((bx[:, 2] * 3 + 15) // 16 * 16, self.host.stride(1))
+        self.h2d_bytes += int(((bx[:, 3] - bx[:, 1]) * (c1 - c0)).sum())
 
     def window(self, i):
         """Descriptors of every stream's window [stride*i, stride*i+32)."""
@@ -88,7 +89,7 @@ class StreamFeeder:
 
 def e2e_crop_leg(eng, B, steps, warmup, rank, dev):
     """clips/s through the crop boundary with HOST inputs: every step uploads the 8 new decoded frames of each of the
-    B streams from pinned memory (rows under the face box), builds the window descriptors on the host (crop boxes +
+    B streams from pinned memory (the pixels under the face box), builds the window descriptors on the host (crop boxes +
     similarity fit, A1/A2), runs af_crop_infer and reads the B scores back; two steps in flight."""
     feeder = StreamFeeder(eng, B, steps + warmup, seed0=1000 * rank)
     main = torch.cuda.current_stream(dev)
