@@ -113,7 +113,7 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   constexpr int N_SLOTS = kShortcut ? 2 : 4;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* smem_wb = smem;
   uint8_t* smem_wc = smem_wb + F_WB_BYTES;
   uint8_t* smem_a = smem_wc + WC_BYTES;

@@ -171,7 +171,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   constexpr uint32_t LAYOUT = kDirect ? 4u : 2u;
   constexpr uint32_t A_TAP_BYTES = RB_X * ROW_BYTES, W_TILE_BYTES = RB_N * ROW_BYTES, SBO_B = 8 * ROW_BYTES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   // carve-up: [A ring][W double buffer][out ring x2][bias][barriers][tmem ptr]
   uint8_t* smem_a = smem;
   uint8_t* smem_w = smem_a + p.stages * p.a_stage_bytes;
@@ -377,7 +377,7 @@ stem_sweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   pdl_launch_dependents();
   constexpr uint32_t LAYOUT = 4u, A_TAP_BYTES = RB_X * 64, W_TILE_BYTES = RB_N * 64, SBO_B = 512;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* smem_w = smem;                                        // [35][64][32] bf16, SWIZZLE_64B
   uint8_t* smem_a = smem_w + SW_W_BYTES;                         // [2] boxes
   uint8_t* smem_out = smem_a + SW_A_STAGES * p.a_stage_bytes;    // [2] x 16 KB
@@ -576,7 +576,7 @@ ftcn_stem_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const bf16* __re
                       int frames_padded) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem_w + FT_W_BYTES;
   uint8_t* smem_out = smem_a + FT_STAGES * FT_STAGE_BYTES;

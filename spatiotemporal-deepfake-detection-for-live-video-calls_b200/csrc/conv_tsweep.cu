@@ -59,7 +59,7 @@ conv_tsweep_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                    const __grid_constant__ CUtensorMap tm_y, const TsParams p) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   const int w_bytes = 3 * p.cblocks * TS_W_TILE;
   uint8_t* smem_w = smem;                                   // [3 taps][cblocks][64 x 64] bf16, SWIZZLE_128B
   uint8_t* smem_a = smem_w + w_bytes;                       // [stages] x 16 KB

@@ -115,7 +115,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   pdl_launch_dependents();
   if (threadIdx.x == 0) stamp(p, 0);
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   const bool has_res = p.res != nullptr;
   // carve-up: [operand ring][out slots: 2 groups x out_per_group][residual slots: 2 groups x 2][bias x2][barriers]
   uint8_t* smem_out = smem + p.stages * STAGE_BYTES;

@@ -11,6 +11,13 @@ constexpr int UMMA_BLOCK_M = 128;
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Dynamic shared memory rounded up to 1024 bytes (SWIZZLE_128B atoms) WITHOUT a round trip through an integer: the
+// result stays a pointer the compiler can prove to be in the shared window, so the epilogues' loads / stores compile
+// to LDS / STS (32-bit addresses, short scoreboard) instead of generic LD / ST (64-bit address arithmetic, long scoreboard).
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
+  return raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(raw) & 1023u)) & 1023u);
+}
+
 // One lane of a fully converged warp (PTX elect.sync): lets ptxas emit the warp-level tcgen05/TMA
 // instructions once instead of a per-active-thread waterfall loop.
 __device__ __forceinline__ bool elect_one() {
