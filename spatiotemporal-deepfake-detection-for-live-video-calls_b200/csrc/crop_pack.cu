@@ -71,7 +71,7 @@ __device__ __forceinline__ uint2 load6(const uint8_t* p) {
 // window are zeroed, and when clamping moved the position by one pixel / row the fetched data is shifted back under
 // the taps (a 24-bit funnel shift / a row select).  Pixels whose taps are all outside get four zero weights.  One code
 // path for interior, edge and outside pixels means no warp divergence along the rotated crop's borders.
-constexpr int CROP_ROWS = 32;      // output rows per block (8 thread rows x 4)
+constexpr int CROP_ROWS = 112;     // output rows per block (8 thread rows x 14): amortises the per-block prologue (fp64 geometry, descriptor, LUT fill: a quarter of the time with 32-row blocks; measured 0.351 -> 0.334 (56 rows) -> 0.300 ms (112 rows) per 32 clips)
 template <typename T, bool kToClip>
 __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__ frames,
                                                    const ClipGeom* __restrict__ geom, int T_, int S,
