@@ -207,11 +207,12 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       __syncwarp();
     };
     int j = 0;
-    prefetch_l2(0);
+    const int pf_dist = p.prefetch;                       // tiles ahead (0 = off)
+    for (int q = 0; q < pf_dist; ++q) prefetch_l2(q);
     for (; tiles.valid(j); ++j) {
       int xt, yt, r;                                      // r = frame index b*T + t
       tiles.coords(j, xt, yt, r);
-      prefetch_l2(j + 1);
+      prefetch_l2(j + pf_dist);
       for (int dx = 0; dx < 3; ++dx) {
         mbar_wait(&a_empty[stage], phase ^ 1);
         if (elect_one()) {

@@ -58,7 +58,8 @@ struct UmmaParams {
   int relu;
   int im2col;
   int stages;          // depth of the A/B operand ring
-  int out_per_group;   // output staging slots per epilogue group (1 or 2)
+  int out_per_group;   // output staging slots per epilogue group (1 or 2; 0 for residual layers: in place)
+  int res_slots;       // residual layers: slots per epilogue group (3 or 4); the output is computed in place in them
   int pool_t;          // fused temporal max-pool: tile = 64 pixels x 2 consecutive frames (rows r, r+64)
   int hw;              // pixels per frame (pool_t only)
   // second operand source (fused projection shortcut): a pointwise conv of stride [1,sh2,sw2] over another
@@ -117,16 +118,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   const bool has_res = p.res != nullptr;
-  // carve-up: [operand ring][out slots: 2 groups x out_per_group][residual slots: 2 groups x 2][bias x2][barriers]
+  // carve-up: [operand ring][out slots: 2 groups x out_per_group | residual/output slots: 2 groups x res_slots][bias x2][barriers]
   uint8_t* smem_out = smem + p.stages * STAGE_BYTES;
   uint8_t* smem_res = smem_out + 2 * p.out_per_group * OUT_STAGE_BYTES;
-  float* bias_s = reinterpret_cast<float*>(smem_res + (has_res ? 4 : 0) * OUT_STAGE_BYTES);
+  float* bias_s = reinterpret_cast<float*>(smem_res + (has_res ? 2 * p.res_slots : 0) * OUT_STAGE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + 2 * BLOCK_N);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_full = tmem_empty + 2;                 // [4]
-  uint64_t* tmem_empty_peer = res_full + 4;            // [2] leader only: the peer CTA's epilogue has drained the accumulator
+  uint64_t* res_full = tmem_empty + 2;                 // [8]
+  uint64_t* tmem_empty_peer = res_full + 8;            // [2] leader only: the peer CTA's epilogue has drained the accumulator
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_peer + 2);
 
   // warp index through a shuffle so the compiler knows it is warp-uniform (keeps the role loops'
@@ -151,7 +152,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (p.cblocks2) { tma_prefetch_desc(&tm_a2); tma_prefetch_desc(&tm_b2); }
     for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], (CHUNKS >= 2 ? 2 : 1) * EPI_THREADS); }
-    for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&res_full[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&tmem_empty_peer[i], 1);
     fence_barrier_init();
   } else if (warp == 1) {
@@ -354,8 +355,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int row = quad * 32 + lane;              // accumulator row == output pixel within the tile
     float* bias_g = bias_s + eg * BLOCK_N;
     uint8_t* out_g = smem_out + eg * p.out_per_group * OUT_STAGE_BYTES;
-    uint8_t* res_g = smem_res + eg * 2 * OUT_STAGE_BYTES;
-    uint64_t* res_bar = res_full + eg * 2;
+    const int R = p.res_slots;
+    uint8_t* res_g = smem_res + eg * R * OUT_STAGE_BYTES;
+    uint64_t* res_bar = res_full + eg * 4;
 
     EpiIter<CHUNKS> cur, pre;
     cur.init(first_tile, tile_stride, num_tiles, eg);
@@ -374,18 +376,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         tma_load_2d(dst, &tm_r, &res_bar[slot], n_tile * BLOCK_N + w.chunk * 64, m_tile * BLOCK_M);
       }
     };
+    // Residual layers work IN PLACE: the residual tile of a chunk is TMA-prefetched into one of R slots (R - 1 chunks
+    // ahead), the epilogue adds the accumulator into it, the TMA store leaves from the same slot and the slot is refilled
+    // once that store has read it.  No separate output staging: the smem buys a third / fourth tile in flight, and a
+    // chunk never waits for the previous chunk's store.
     if (has_res && et == 0) {
-      for (int j = 0; j < 2; ++j)
+      for (int j = 0; j < R; ++j)
         if (pre.valid()) { issue_res(pre, j); pre.next(); }
     }
     int n0 = 0;
     long long m0 = 0;
     int as = 0;
+    int rslot = 0, prev_rslot = 0;
+    uint32_t rphase = 0;
 #pragma unroll 1
     for (uint32_t k = 0; cur.valid(); cur.next(), ++k) {
       const int slot = k & 1;
-      uint8_t* sout = out_g + (p.out_per_group == 2 ? slot : 0) * OUT_STAGE_BYTES;
-      const uint8_t* sres = res_g + slot * OUT_STAGE_BYTES;
+      uint8_t* sout = has_res ? res_g + rslot * OUT_STAGE_BYTES : out_g + (p.out_per_group == 2 ? slot : 0) * OUT_STAGE_BYTES;
+      const uint8_t* sres = sout;
       if (cur.first_in_tile()) {
         const int mp = cur.tile / p.num_n_tiles, n_tile = cur.tile - mp * p.num_n_tiles;
         const int m_tile = kPair ? 2 * mp + (int)cta_rank : mp;
@@ -397,7 +405,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         mbar_wait(&tmem_full[as], (cur.it >> 1) & 1);
         tc_fence_after();
       }
-      if (et == 0) {                               // the store that last read this out slot has drained it
+      if (!has_res && et == 0) {                   // the store that last read this out slot has drained it
         if (p.out_per_group == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
       }
       epi_bar_sync(eg);                            // (also publishes bias_g)
@@ -405,7 +413,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BLOCK_N + cur.chunk * 64;
       TMEM_LD_32x32b_x32(taddr, v);
       TMEM_LD_32x32b_x32(taddr + 32, (v + 32));
-      if (has_res) mbar_wait(&res_bar[slot], (k >> 1) & 1u);
+      if (has_res) mbar_wait(&res_bar[rslot], rphase);
       tmem_ld_wait();
       if (cur.last_in_tile()) {                    // this group's last TMEM read of the accumulator
         tc_fence_before();
@@ -459,7 +467,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       if (et == 0) {
         tma_store_2d(&tm_y, sout, n0 + cbase, (int)m0);
         tma_store_commit();
-        if (has_res && pre.valid()) { issue_res(pre, slot); pre.next(); }   // refill the slot just drained
+        if (has_res && k >= 1) {                   // the PREVIOUS chunk's store has read its slot: refill that one
+          tma_store_wait_read<1>();
+          if (pre.valid()) { issue_res(pre, prev_rslot); pre.next(); }
+        }
+      }
+      if (has_res) {
+        prev_rslot = rslot;
+        if (++rslot == R) { rslot = 0; rphase ^= 1; }
       }
     }
     if (et == 0 && eg == 0) stamp(p, 5);
@@ -511,12 +526,13 @@ int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty
     AFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  // shared-memory budget: residual layers trade operand stages for 4 residual + 4 output slots
+  // shared-memory budget: residual layers trade operand stages for 2 x (3 or 4) residual slots that double as output staging
   const int stage_bytes = A_STAGE_BYTES + (kPair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
   const bool has_res = up.res != nullptr;
-  up.out_per_group = BLOCK_N <= 128 ? 2 : 1;
-  const int fixed = (2 * up.out_per_group + (has_res ? 4 : 0)) * OUT_STAGE_BYTES + 2 * BLOCK_N * 4 +
-                    (2 * MAX_STAGES + 10) * 8 + 16 + 1024;
+  up.out_per_group = has_res ? 0 : (BLOCK_N <= 128 ? 2 : 1);
+  up.res_slots = has_res ? (BLOCK_N <= 128 ? 4 : 3) : 0;
+  const int fixed = (2 * up.out_per_group + 2 * up.res_slots) * OUT_STAGE_BYTES + 2 * BLOCK_N * 4 +
+                    (2 * MAX_STAGES + 14) * 8 + 16 + 1024;
   int stages = (g_max_smem - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) { set_error("conv_umma: shared memory budget too small"); return AF_ERR_INVALID; }
