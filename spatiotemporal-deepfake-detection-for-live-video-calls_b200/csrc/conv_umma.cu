@@ -526,11 +526,21 @@ int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty
     AFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  // shared-memory budget: residual layers trade operand stages for 2 x (3 or 4) residual slots that double as output staging
+  // pair mode: tiles are 256 rows tall, one 2-CTA cluster (the two SMs of a TPC) per tile
+  const int tiles = (kPair ? (up.num_m_tiles + 1) / 2 : up.num_m_tiles) * up.num_n_tiles;
+  const int grid = kPair ? 2 * limit_grid(tiles, g_num_sms / 2) : limit_grid(tiles, g_num_sms);
+  // shared-memory budget: residual layers trade operand stages for 2 x (3 or 4) residual slots that double as output
+  // staging.  Small launches (batch 1-2: one or two tiles per CTA) never cycle through that many slots, and their K
+  // loops run at "ring depth per L2 round trip" (measured 160 ns per 64-channel block with 6 slots of operands in
+  // flight), so there the staging shrinks to what a CTA's few chunks can use and the ring takes the rest.
   const int stage_bytes = A_STAGE_BYTES + (kPair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
   const bool has_res = up.res != nullptr;
-  up.out_per_group = has_res ? 0 : (BLOCK_N <= 128 ? 2 : 1);
-  up.res_slots = has_res ? (BLOCK_N <= 128 ? 4 : 3) : 0;
+  const int ctas = kPair ? grid / 2 : grid;
+  const int tiles_per_cta = (tiles + ctas - 1) / ctas;
+  const int chunks_per_group = (tiles_per_cta * (BLOCK_N / 64) + 1) / 2;
+  up.out_per_group = has_res ? 0 : ((BLOCK_N <= 128 && chunks_per_group >= 2) ? 2 : 1);
+  const int res_default = BLOCK_N <= 128 ? 4 : 3;
+  up.res_slots = has_res ? (chunks_per_group < 2 ? 2 : chunks_per_group < res_default ? chunks_per_group : res_default) : 0;
   const int fixed = (2 * up.out_per_group + 2 * up.res_slots) * OUT_STAGE_BYTES + 2 * BLOCK_N * 4 +
                     (2 * MAX_STAGES + 14) * 8 + 16 + 1024;
   int stages = (g_max_smem - fixed) / stage_bytes;
@@ -538,9 +548,6 @@ int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty
   if (stages < 2) { set_error("conv_umma: shared memory budget too small"); return AF_ERR_INVALID; }
   up.stages = stages;
   const int dyn = fixed + stages * stage_bytes;
-  // pair mode: tiles are 256 rows tall, one 2-CTA cluster (the two SMs of a TPC) per tile
-  const int tiles = (kPair ? (up.num_m_tiles + 1) / 2 : up.num_m_tiles) * up.num_n_tiles;
-  const int grid = kPair ? 2 * limit_grid(tiles, g_num_sms / 2) : limit_grid(tiles, g_num_sms);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
   cudaLaunchAttribute attr[2];
