@@ -9,8 +9,10 @@ A "step" is one pass of the hot path over one batch of synthetic input:
   workload = BASELINE.json configs[1]: bf16, batch 32 clips per GPU, crop/warp/normalise kernel
   (from decoded 720p frames + face boxes already resident in HBM) followed by the I3D ResNet-50
   trunk and the head.  `value` is device-timed (CUDA events, max over ranks) with inputs in
-  HBM; `e2e` is the same metric through the host-buffer C-ABI call (ClassifierSvc.infer_scores
-  boundary: pinned u8 aligned clips in, scores out, H2D/D2H inside the timed region).
+  HBM; `e2e` is the same metric through the host-buffer C-ABI calls at the CROP boundary (pinned
+  decoded frames -> af_ring_put_boxes -> af_crop_infer -> scores on the host, H2D/D2H inside the
+  timed region: the work the reference arm does); `e2e_aligned` is the ClassifierSvc.infer_scores
+  boundary (pinned u8 aligned clips in, scores out).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -349,6 +351,22 @@ def run_ours(args):
     k1_ms, k1_n = eng.get_stat("feed_ms"), eng.get_stat("feed_launches")
     value = n_total * args.steps / (ms / 1e3)
 
+    # p50 batch-1 latency (crop + trunk + score on host), rank 0 only; measured right behind the timed region (the
+    # host-fed legs below leave the GPU in a lower clock state for a while, which adds ~0.09 ms to a batch-1 pass)
+    p50 = p99 = None
+    if rank == 0:
+        lat = []
+        fd1, cg1 = fd[: 32 * 40].contiguous(), cg[:64].contiguous()
+        for i in range(55):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            lg, sc = eng.crop_infer(fd1, cg1, 1)
+            float(sc[0])
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = sorted(lat[5:])
+        p50 = lat[len(lat) // 2]
+        p99 = lat[min(len(lat) - 1, int(round(0.99 * (len(lat) - 1))))]
+
     # end to end with HOST inputs, two boundaries, both at --steps:
     #  e2e          crop boundary (matches the reference arm's work: crop/align + pack + classify)
     #  e2e_aligned  ClassifierSvc.infer_scores boundary (pre-aligned u8 clips)
@@ -370,21 +388,6 @@ def run_ours(args):
                        "api": "af_submit_u8_host + af_wait (ClassifierSvc.infer_scores_stream: pinned u8 [B,32,224,224,3] -> "
                               "scores on the host, two batches in flight); no crop kernel on this boundary",
                        "blocking_call_value": n_total * n_e2e / dt_b}
-
-    # p50 batch-1 latency (crop + trunk + score on host), rank 0 only
-    p50 = p99 = None
-    if rank == 0:
-        lat = []
-        fd1, cg1 = fd[: 32 * 40].contiguous(), cg[:64].contiguous()
-        for i in range(55):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            lg, sc = eng.crop_infer(fd1, cg1, 1)
-            float(sc[0])
-            lat.append((time.perf_counter() - t0) * 1e3)
-        lat = sorted(lat[5:])
-        p50 = lat[len(lat) // 2]
-        p99 = lat[min(len(lat) - 1, int(round(0.99 * (len(lat) - 1))))]
 
     # parity of the very batch that was timed (rank 0): 4 clips back through af_crop_u8 -> CPU oracle
     parity = None
