@@ -17,8 +17,11 @@
 //               column): the c MMA takes its A operand from TMEM, so the intermediate costs neither 16 KB of shared
 //               memory (which buys the third halo-ring slot: two slots could not cover a box's load latency) nor any
 //               shared-memory bandwidth
-//   warps 6-13  epilogue 2 (two warpgroups on alternate 64-channel chunks): acc_c -> +bias_c +residual -> ReLU -> bf16,
-//               IN PLACE in the slot the residual tile was TMA-loaded into, then a TMA store from that slot
+//   warps 6-13  epilogue 2 (two warpgroups, one per 128-channel HALF of acc_c): acc_c -> +bias_c +residual -> ReLU -> bf16,
+//               IN PLACE in the slot the residual tile was TMA-loaded into, then a TMA store from that slot.  The c GEMM
+//               is issued as two N = 128 halves at different points of the next tile's b MMAs (after its first and its
+//               last halo box), each with its own full / empty barriers: the two groups work out of phase instead of
+//               bursting on the same issue slots, and a half's MMAs only wait for that half to be drained
 // TMEM: acc_b (64 columns) + Yb x2 (2 x 32) + acc_c (256) [+ 128 held output, kPoolT].  Shared memory: 72 + 32 KB weights,
 // 3 x 18 KB halo ring, 4 x 16 KB residual/output slots = 223 KB.
 //
@@ -125,9 +128,9 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   uint64_t* accb_empty = accb_full + 1;
   uint64_t* yb_full = accb_empty + 1;     // [2]
   uint64_t* yb_empty = yb_full + 2;       // [2]
-  uint64_t* accc_full = yb_empty + 2;
-  uint64_t* accc_empty = accc_full + 1;
-  uint64_t* res_full = accc_empty + 1;    // [2 groups][2 slots]
+  uint64_t* accc_full = yb_empty + 2;     // [2 halves]
+  uint64_t* accc_empty = accc_full + 2;   // [2 halves]
+  uint64_t* res_full = accc_empty + 2;    // [2 groups][2 slots]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 4);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -150,8 +153,7 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     mbar_init(accb_full, 1);
     mbar_init(accb_empty, 128);
     for (int i = 0; i < 2; ++i) { mbar_init(&yb_full[i], 128); mbar_init(&yb_empty[i], 1); }
-    mbar_init(accc_full, 1);
-    mbar_init(accc_empty, 256);
+    for (int i = 0; i < 2; ++i) { mbar_init(&accc_full[i], 1); mbar_init(&accc_empty[i], 128); }
     for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
   } else if (warp == 1) {
@@ -177,8 +179,8 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     int stage = 0;
     uint32_t phase = 0;
     // kShortcut: the block input under a tile (no halo; operand of the shortcut's K block) travels through the ring
-    // BEHIND the halo boxes of the CTA's next tile, because that is where the MMA warp consumes it (c of a tile is
-    // issued after b of the next one)
+    // BEHIND the halo boxes of the CTA's next tile, because that is where the MMA warp consumes it (both halves of c of a
+    // tile are issued after b of the next one; holding the slot across b's boxes would stall the ring)
     auto load_x = [&](int j) {
       int xt, yt, r;
       tiles.coords(j, xt, yt, r);
@@ -228,43 +230,65 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     if (kShortcut && j >= 1) load_x(j - 1);
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    constexpr uint32_t idesc_b = make_idesc(F_MID), idesc_c = make_idesc(F_OUT);
+    constexpr uint32_t idesc_b = make_idesc(F_MID), idesc_c = make_idesc(F_OUT / 2);
     mbar_wait(w_full, 0);
     tc_fence_after();
     const uint32_t wb_addr = smem_u32(smem_wb), wc_addr = smem_u32(smem_wc);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    auto issue_c = [&](int j) {                   // c of this CTA's j-th tile: Yb x W_c^T (+ X x W_s^T) -> acc_c
+    int x_stage = 0;
+    // kShortcut: the block-input tile of the tile whose c is about to be issued is the next box of the ring
+    auto take_x = [&]() {
+      mbar_wait(&a_full[stage], phase);
+      tc_fence_after();
+      x_stage = stage;
+      if (++stage == F_A_STAGES) { stage = 0; phase ^= 1; }
+    };
+    // half h (output channels [128h, 128h + 128)) of c of this CTA's j-th tile: Yb x W_c^T -> acc_c
+    auto issue_c_half = [&](int j, int h) {
       const int ys = j & 1;
-      mbar_wait(&yb_full[ys], (j >> 1) & 1);
-      mbar_wait(accc_empty, (j & 1) ^ 1);
+      if (h == 0) mbar_wait(&yb_full[ys], (j >> 1) & 1);
+      mbar_wait(&accc_empty[h], (j & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_tmem = tmem_base + YB_COL + ys * (F_MID / 2);
-        const uint64_t bdesc = make_smem_desc(wc_addr);
+        const uint32_t d_c = tmem_base + ACCC_COL + h * (F_OUT / 2);
+        const uint64_t bdesc = make_smem_desc(wc_addr + h * (F_WC_BYTES / 2));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_base + ACCC_COL, a_tmem + 8 * k, bdesc + 2 * k, idesc_c, k != 0 ? 1u : 0u);
-        umma_commit(&yb_empty[ys]);               // this Yb buffer may be overwritten once these have read it
-        if (!kShortcut) umma_commit(accc_full);
+        for (int k = 0; k < 4; ++k) umma_bf16_ts(d_c, a_tmem + 8 * k, bdesc + 2 * k, idesc_c, k != 0 ? 1u : 0u);
+        if (h == 1) umma_commit(&yb_empty[ys]);   // this Yb buffer may be overwritten once both halves have read it
+        umma_commit(&accc_full[h]);
       }
       __syncwarp();
-      if (kShortcut) {                            // second K block: the block-input tile (4th ring box) x shortcut weights
-        mbar_wait(&a_full[stage], phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * F_A_BYTES)), bdesc = make_smem_desc(wc_addr + F_WC_BYTES);
+    };
+    // shortcut form: c and the shortcut's K block at full width (N = 256: the block-input tile is read from shared memory
+    // once per k-step; two N = 128 halves measured slower here), both halves' barriers signalled together
+    auto issue_c_shortcut = [&](int j) {
+      const int ys = j & 1;
+      mbar_wait(&yb_full[ys], (j >> 1) & 1);
+      mbar_wait(&accc_empty[0], (j & 1) ^ 1);
+      mbar_wait(&accc_empty[1], (j & 1) ^ 1);
+      take_x();
+      if (elect_one()) {
+        constexpr uint32_t idesc_full = make_idesc(F_OUT);
+        const uint32_t a_tmem = tmem_base + YB_COL + ys * (F_MID / 2);
+        const uint64_t bdesc = make_smem_desc(wc_addr);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + ACCC_COL, adesc + 2 * k, bdesc + 2 * k, idesc_c, 1u);
-          umma_commit(&a_empty[stage]);
-          umma_commit(accc_full);
-        }
-        __syncwarp();
-        if (++stage == F_A_STAGES) { stage = 0; phase ^= 1; }
+        for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_base + ACCC_COL, a_tmem + 8 * k, bdesc + 2 * k, idesc_full, k != 0 ? 1u : 0u);
+        umma_commit(&yb_empty[ys]);
+        const uint64_t adesc = make_smem_desc(smem_u32(smem_a + x_stage * F_A_BYTES));
+        const uint64_t bdesc2 = make_smem_desc(wc_addr + F_WC_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + ACCC_COL, adesc + 2 * k, bdesc2 + 2 * k, idesc_full, 1u);
+        umma_commit(&a_empty[x_stage]);
+        umma_commit(&accc_full[0]);
+        umma_commit(&accc_full[1]);
       }
+      __syncwarp();
     };
     for (; tiles.valid(it); ++it) {
-      // acc_b is single-buffered: c of the previous tile is queued between two b's, which is all the time the first
+      // acc_b is single-buffered: c of the previous tile is queued inside this b, which is all the time the first
       // epilogue needs to read it out
       mbar_wait(accb_empty, (it & 1) ^ 1);
       tc_fence_after();
@@ -286,13 +310,25 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         }
         __syncwarp();
         if (++stage == F_A_STAGES) { stage = 0; phase ^= 1; }
+        // c of the previous tile rides inside this b (epilogue 1 has had a whole tile to produce its Yb): the first half
+        // behind the first halo box, the second half behind the last one (shortcut form: both behind the last one, where
+        // the block-input tile arrives)
+        if (!kShortcut && dx == 0 && it >= 1) issue_c_half(it - 1, 0);
       }
       if (elect_one()) umma_commit(accb_full);
       __syncwarp();
-      // c of a tile is issued after b of the NEXT tile, so epilogue 1 (acc_b -> Yb) hides behind those MMAs
-      if (it >= 1) issue_c(it - 1);
+      if (it >= 1) {
+        if (kShortcut) issue_c_shortcut(it - 1); else issue_c_half(it - 1, 1);
+      }
     }
-    if (it >= 1) issue_c(it - 1);
+    if (it >= 1) {
+      if (kShortcut) {
+        issue_c_shortcut(it - 1);
+      } else {
+        issue_c_half(it - 1, 0);
+        issue_c_half(it - 1, 1);
+      }
+    }
   } else if (warp < 6) {
     // ===================================================== epilogue 1 (warps 2-5): acc_b -> Yb
     pdl_wait_prior_grid();
@@ -326,20 +362,20 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   } else {
     // ===================================================== epilogue 2 (warps 6-13): acc_c + residual -> y
     pdl_wait_prior_grid();
-    const int eg = (warp - 6) >> 2;               // group 0: chunks 0, 2; group 1: chunks 1, 3
+    const int eg = (warp - 6) >> 2;               // group 0: chunks 0, 1 (half 0 of acc_c); group 1: chunks 2, 3
     const int et = (threadIdx.x - 192) & 127;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     uint8_t* slot_g = smem_slot + eg * (N_SLOTS / 2) * F_TILE_BYTES;
     uint64_t* res_bar = res_full + eg * 2;
-    // chunk sequence of this group: (tile it, chunk eg), (it, eg + 2), (it + 1, eg), ...
-    int pre_j = 0, pre_chunk = eg;
+    // chunk sequence of this group: (tile it, chunk 2eg), (it, 2eg + 1), (it + 1, 2eg), ...
+    int pre_j = 0, pre_chunk = 2 * eg;
     auto issue_res = [&](int slot) {
       int xt, yt, r;
       tiles.coords(pre_j, xt, yt, r);
       mbar_expect_tx(&res_bar[slot], F_TILE_BYTES);
       f_tma_load_4d(slot_g + slot * F_TILE_BYTES, &tm_r, &res_bar[slot], pre_chunk * 64, xt * FX, yt * FR, r);
-      if (pre_chunk + 2 < 4) pre_chunk += 2; else { pre_chunk = eg; ++pre_j; }
+      if (pre_chunk == 2 * eg) ++pre_chunk; else { pre_chunk = 2 * eg; ++pre_j; }
     };
     if (!kShortcut && et == 0)
       for (int j = 0; j < 2; ++j)
@@ -353,19 +389,19 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       for (; tiles.valid(it); ++it) {
         int xt, yt, r;
         tiles.coords(it, xt, yt, r);
-        mbar_wait(accc_full, it & 1);
+        mbar_wait(&accc_full[eg], it & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int half = 2 * eg; half < 8; half += (half & 1) ? 3 : 1, ++k) {      // halves (2eg, 2eg+1, 2eg+4, 2eg+5) of 8
+        for (int half = 4 * eg; half < 4 * eg + 4; ++half, ++k) {      // 32-channel pieces 4eg .. 4eg+3 of 8
           uint8_t* s_io = slot_g + (k & 1) * (F_TILE_BYTES / 2);
           uint32_t v[32];
           TMEM_LD_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + ACCC_COL + half * 32, v);
           if (et == 0) tma_store_wait_read<1>();  // the store that last read this sub-slot (two halves ago) has drained it
           wg_bar_sync(2 + eg);
           tmem_ld_wait();
-          if (half == 2 * eg + 5) {               // this group's last read of acc_c for the tile
+          if (half == 4 * eg + 3) {               // this group's last read of its half of acc_c for the tile
             tc_fence_before();
-            mbar_arrive(accc_empty);
+            mbar_arrive(&accc_empty[eg]);
           }
           const float* bias = p.bias_c + half * 32;
 #pragma unroll
@@ -392,10 +428,10 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       tiles.coords(it, xt, yt, r);
       const bool hold_phase = kPoolT && !(it & 1);      // even frame of a pair: the output waits in TMEM
       const bool max_phase = kPoolT && (it & 1);        // odd frame: max with the held output, store the pooled tile
-      mbar_wait(accc_full, it & 1);
+      mbar_wait(&accc_full[eg], it & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int chunk = eg; chunk < 4; chunk += 2, ++k) {
+      for (int chunk = 2 * eg; chunk < 2 * eg + 2; ++chunk, ++k) {
         const int slot = kShortcut ? 0 : (int)(k & 1);
         uint8_t* s_io = slot_g + slot * F_TILE_BYTES;
         uint32_t v[64];
@@ -414,9 +450,9 @@ conv_bc_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           mbar_wait(&res_bar[slot], (k >> 1) & 1u);
         }
         tmem_ld_wait();
-        if (chunk + 2 >= 4) {                     // this group's last read of acc_c for the tile
+        if (chunk == 2 * eg + 1) {                // this group's last read of its half of acc_c for the tile
           tc_fence_before();
-          mbar_arrive(accc_empty);
+          mbar_arrive(&accc_empty[eg]);
         }
         const float* bias = p.bias_c + chunk * 64;
 #pragma unroll
