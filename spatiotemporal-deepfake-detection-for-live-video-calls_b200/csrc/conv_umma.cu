@@ -761,8 +761,10 @@ int build_plan(const ConvProblem& p, UmmaPlan& plan) {
   // them two output slots per epilogue group and a deeper operand ring (measured on B200, 32 clips: K=64 5.4 -> 6.5 TB/s
   // at BLOCK_N 64, K=128 5.45 -> 5.7 TB/s at BLOCK_N 128; wider K is better off at 256)
   if (p.res && !p.x2 && pointwise) {
+    static const char* rk = getenv("AFB200_RES_BN128_MAXK");
+    const int maxk128 = rk ? atoi(rk) : 128;
     if (p.Cin <= 64) bn = 64;
-    else if (p.Cin <= 128 && bn > 128) bn = 128;
+    else if (p.Cin <= maxk128 && bn > 128) bn = 128;
   }
   static const char* fbn = getenv("AFB200_BLOCK_N");
   int force_bn = g_force_block_n ? g_force_block_n : (fbn ? atoi(fbn) : 0);
