@@ -147,8 +147,12 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
       interior = interior && qx - 1 >= xlo && qx + 2 < xhi && qy - 1 >= ylo && qy + 2 < yhi;
     }
   }
+  // destination of this thread's first row; every further row is 8 image rows down (64-bit address maths out of the loop)
+  T* q_row = kToClip ? dst + b * sB + t * sT + (long long)(blockIdx.y * CROP_ROWS + threadIdx.y) * sH + x * sW : nullptr;
+  uint8_t* q8_row = kToClip ? nullptr : out_u8 + (((long long)bt * S + blockIdx.y * CROP_ROWS + threadIdx.y) * S + x) * 3;
+  const long long q_step = 8 * sH;
 #pragma unroll 1
-  for (int ry = threadIdx.y; ry < CROP_ROWS; ry += 8) {
+  for (int ry = threadIdx.y; ry < CROP_ROWS; ry += 8, q_row += q_step, q8_row += 8 * S * 3) {
   const int y = blockIdx.y * CROP_ROWS + ry;
   if (y >= S) break;
   const int2 row = s_row[ry];
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
   if (bgr) { const int t0 = o[0]; o[0] = o[2]; o[2] = t0; }
 
   if (kToClip) {
-    T* q = dst + b * sB + t * sT + y * sH + x * sW;
+    T* q = q_row;
     if (sC == 0) {
       store_px4<T>(q, s_lut[o[0]], s_lut[256 + o[1]], s_lut[512 + o[2]]);
     } else {      // caller tensor viewed as [B,3,T,S,S] with its own strides (af_crop_pack)
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(256) crop_kernel(const FrameDesc* __restrict__
       store_1<T>(q + 2 * sC, s_lut[512 + o[2]]);
     }
   } else {
-    uint8_t* q = out_u8 + (((long long)bt * S + y) * S + x) * 3;
+    uint8_t* q = q8_row;
     q[0] = (uint8_t)o[0]; q[1] = (uint8_t)o[1]; q[2] = (uint8_t)o[2];
   }
   }
