@@ -18,3 +18,7 @@ rm -f gpurun_out/step_b32.ncu-rep        # ~100 MB: over gpurun's 64 MiB return 
 ls -la gpurun_out
 AFB200_TRACE=1 python tools/trace_layers.py 32 2> gpurun_out/layer_trace_b32.raw > /dev/null
 python tools/trace_summary.py gpurun_out/layer_trace_b32.raw 32 60 > gpurun_out/layer_trace_b32.txt
+# K1 on its own: crop_kernel (af_crop_infer's feeder) and pack_u8_kernel (af_infer_u8's feeder), second iteration
+ncu --set full --clock-control none -k regex:"crop_kernel|pack_u8_kernel" -s 2 -c 2 -f -o gpurun_out/k1 python tools/ncu_target_k1.py 32 > gpurun_out/ncu_k1.log 2>&1
+ncu -i gpurun_out/k1.ncu-rep --page raw --csv > gpurun_out/k1_raw.csv
+rm -f gpurun_out/k1.ncu-rep
