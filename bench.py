@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short offline / live / rgb workloads")
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU per step")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "tf32"])
     ap.add_argument("--variant", default="i3d", choices=["i3d", "ftcn_tt"],
                     help="i3d: the AltFreezing I3D (BASELINE.json's metric); ftcn_tt: the reference's second classifier "
                          "plugin (SURVEY 8f row 4) through the same pipeline")
@@ -490,7 +490,7 @@ def run_torch_gpu(args):
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
     sd = synthetic.synthetic_state_dict(0, args.variant)
-    mode = {"bf16": "amp_bf16", "fp32": "tf32"}[args.precision]
+    mode = {"bf16": "amp_bf16", "fp32": "tf32", "tf32": "tf32"}[args.precision]
     res = legs.torch_gpu_leg(sd, args.variant, args.batch, dev, mode, steps=max(1, args.steps), warmup=max(2, args.warmup))
     _emit(json.dumps({"metric": METRIC, "value": res.get("value"), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": res.get("ms_per_step"), "higher_is_better": True, "scaling": "weak",

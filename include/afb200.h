@@ -41,7 +41,9 @@ typedef enum { AF_F32 = 0, AF_BF16 = 1, AF_F16 = 2, AF_U8 = 3 } af_dtype;
 /* Arithmetic of the trunk. FP32: fp32 activations/weights/accumulate (parity gate
  * 1e-3 on logits). BF16: bf16 activations/weights, fp32 accumulate on tcgen05
  * tensor cores (parity gate 2e-2 and same decision at logit 0). */
-typedef enum { AF_PREC_FP32 = 0, AF_PREC_BF16 = 1 } af_precision;
+/* AF_PREC_TF32: fp32 storage and fp32 accumulation like AF_PREC_FP32, trunk convolutions on the tensor cores with TF32
+ * operands (what cuDNN does for the reference's fp32 model under torch's default allow_tf32). */
+typedef enum { AF_PREC_FP32 = 0, AF_PREC_BF16 = 1, AF_PREC_TF32 = 2 } af_precision;
 
 /* One Conv3d with its eval-mode BatchNorm3d already folded by the host
  * (W' = W*gamma/sqrt(var+eps), b' = beta - mean*gamma/sqrt(var+eps)).

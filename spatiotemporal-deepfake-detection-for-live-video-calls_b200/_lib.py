@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libafb200.so")
 
 AF_OK = 0
 AF_F32, AF_BF16, AF_F16, AF_U8 = 0, 1, 2, 3
-AF_PREC_FP32, AF_PREC_BF16 = 0, 1
+AF_PREC_FP32, AF_PREC_BF16, AF_PREC_TF32 = 0, 1, 2
 
 
 class AfConvDesc(C.Structure):

@@ -54,6 +54,7 @@ struct ConvLayer {
   int kt, kh, kw, st, sh, sw, pt, ph, pw;
   float* w_simt = nullptr;  // [taps][cin_p][cout] fp32 (bf16-rounded values in bf16 precision)
   bf16* w_umma = nullptr;   // [taps][cout][cin_p] bf16 (bf16 precision only)
+  float* w_tf32 = nullptr;  // [taps][cout][cin_p] fp32 (tf32 precision only: the tensor-core kernel's B operand)
   float* bias = nullptr;    // [cout]
   std::vector<float> bias_h;  // host copy of bias
 };
@@ -61,12 +62,24 @@ struct ConvLayer {
 static void free_layer(ConvLayer& L) {
   if (L.w_simt) cudaFree(L.w_simt);
   if (L.w_umma) cudaFree(L.w_umma);
+  if (L.w_tf32) cudaFree(L.w_tf32);
   if (L.bias) cudaFree(L.bias);
-  L.w_simt = nullptr; L.w_umma = nullptr; L.bias = nullptr;
+  L.w_simt = nullptr; L.w_umma = nullptr; L.w_tf32 = nullptr; L.bias = nullptr;
+}
+
+// fp32 -> nearest value with 10 mantissa bits (round half away from zero, like cvt.rna.tf32.f32): the tensor core
+// truncates its TF32 operands, rounding here keeps the weights' error unbiased
+static float tf32_round(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return v;      // inf / nan
+  u = (u + 0x1000u) & ~0x1FFFu;
+  memcpy(&v, &u, 4);
+  return v;
 }
 
 // Re-lay-out one folded conv for the kernels and upload it.
-static int upload_layer(const af_conv_desc& d, bool is_bf16, ConvLayer& L) {
+static int upload_layer(const af_conv_desc& d, bool is_bf16, ConvLayer& L, bool tf32 = false) {
   L.cin = d.cin; L.cout = d.cout; L.cin_p = (d.cin + 3) / 4 * 4;
   L.kt = d.kt; L.kh = d.kh; L.kw = d.kw; L.st = d.st; L.sh = d.sh; L.sw = d.sw;
   L.pt = d.pt; L.ph = d.ph; L.pw = d.pw;
@@ -90,6 +103,15 @@ static int upload_layer(const af_conv_desc& d, bool is_bf16, ConvLayer& L) {
   if (is_bf16) {
     AFB_CUDA(cudaMalloc(&L.w_umma, n * sizeof(bf16)));
     AFB_CUDA(cudaMemcpy(L.w_umma, wu.data(), n * sizeof(bf16), cudaMemcpyHostToDevice));
+  }
+  if (tf32 && !is_bf16 && L.cin_p % 32 == 0) {      // K-major per tap for the tensor-core kernel (conv_tf32.cu)
+    std::vector<float> wt(n, 0.f);
+    for (int co = 0; co < d.cout; ++co)
+      for (int ci = 0; ci < d.cin; ++ci)
+        for (int tp = 0; tp < taps; ++tp)
+          wt[((size_t)tp * d.cout + co) * L.cin_p + ci] = tf32_round(d.weight[((size_t)co * d.cin + ci) * taps + tp]);
+    AFB_CUDA(cudaMalloc(&L.w_tf32, n * sizeof(float)));
+    AFB_CUDA(cudaMemcpy(L.w_tf32, wt.data(), n * sizeof(float), cudaMemcpyHostToDevice));
   }
   AFB_CUDA(cudaMalloc(&L.bias, d.cout * sizeof(float)));
   AFB_CUDA(cudaMemcpy(L.bias, d.bias, d.cout * sizeof(float), cudaMemcpyHostToDevice));
@@ -182,12 +204,14 @@ using namespace afb;
 struct af_engine {
   int device = 0;
   bool is_bf16 = false;
+  bool tf32 = false;        // fp32 storage, trunk convs on the tensor cores with TF32 operands (conv_tf32.cu)
   int T = 32, S = 224, max_batch = 1;
   std::vector<ConvLayer> convs;
   ConvLayer stem_u;          // unfolded stem (bf16 engine), valid if has_stem_u
   bool has_stem_u = false;
   bf16* ftcn_w2 = nullptr;   // FTCN-TT tensor-core stem weights [6][128][8] bf16 (upload_ftcn_stem_w2)
   bf16* stem_w35 = nullptr;  // direct stem weights [35 (dt,dy)][cout][32 (dx*4+c)] bf16
+  float* stem_w35_tf32 = nullptr;   // the same layout in fp32 (tf32 precision: conv_tf32_stem_launch)
   int stem_direct = 0;       // 1 usable, 0 not tried / disabled, -1 tensor-map encode refused
   int stem = 0;
   std::vector<af_block_desc> blocks;
@@ -384,6 +408,10 @@ static int run_conv(af_engine* e, const ConvLayer& L, const void* x, Dims in, lo
   } else if (is_bf16 && impl >= 2) {
     set_error("tcgen05 conv kernel (impl %d) does not take this shape", impl);
     return AF_ERR_INVALID;
+  } else if (!is_bf16 && L.w_tf32 && (e ? e->tf32 : true) && impl != 1 && !pool_hw && !pool_t && !sc && conv_tf32_supported(p)) {
+    p.w = L.w_tf32;
+    rc = conv_tf32_launch(p, s);
+    which = "utf32";
   } else {
     p.w = L.w_simt;
     rc = conv_simt_launch(p, is_bf16, s);
@@ -634,6 +662,16 @@ static int run_trunk(af_engine* e, int B, const Feeder& feed, float* logits, flo
         } else {
           rc = run_conv(e, e->stem_u, e->fbuf[2], du, sB, sT, sH, sW, fB, nullptr, e->fbuf[0], true, s);
         }
+      } else if (e->stem_w35_tf32 && e->conv_impl != 1) {
+        // tf32 precision: the stem on the tensor cores straight from the padded fp32 clip (conv_tf32.cu, stem form)
+        OpTrace tr(s);
+        ProfRec prec(e, s);
+        const char* phys = (const char*)e->clip_raw + (long long)f0 * e->clip.sB * (long long)e->esz;
+        rc = conv_tf32_stem_launch(phys, fB, e->T, e->S, e->stem_w35_tf32, stem.bias, e->fbuf[0], s);
+        prec.done(0, 2.0 * (double)fB * dpre.elems() * 735.0,
+                  (double)fB * ((double)(e->T + 4) * (e->S + 6) * (e->S + 8) * 4 + dpre.elems()) * 4.0);
+        tr.done("stem tf32 k5x7x7 s2", 2.0 * (double)fB * dpre.elems() * 1120.0,
+                (double)fB * ((double)(e->T + 4) * (e->S + 6) * (e->S + 8) * 4 + dpre.elems()) * 4.0);
       } else {
         rc = run_conv(e, stem, xin, din, e->clip.sB, e->clip.sT, e->clip.sH, e->clip.sW, fB, nullptr, e->fbuf[0], true, s);
       }
@@ -769,6 +807,7 @@ af_status af_destroy(af_handle h) {
   for (auto& L : h->convs) free_layer(L);
   free_layer(h->stem_u);
   if (h->stem_w35) cudaFree(h->stem_w35);
+  if (h->stem_w35_tf32) cudaFree(h->stem_w35_tf32);
   if (h->ftcn_w2) cudaFree(h->ftcn_w2);
   for (float* fb : h->fused_bias)
     if (fb) cudaFree(fb);
@@ -858,9 +897,13 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
     if (!rc) rc = conv_bc_fused_init();
     if (rc) return (af_status)rc;
   }
+  if (e->tf32) {
+    int rc = conv_tf32_init();
+    if (rc) return (af_status)rc;
+  }
   e->convs.resize(w->n_convs);
   for (int i = 0; i < w->n_convs; ++i) {
-    int rc = upload_layer(w->convs[i], e->is_bf16, e->convs[i]);
+    int rc = upload_layer(w->convs[i], e->is_bf16, e->convs[i], e->tf32);
     if (rc) return (af_status)rc;
   }
   e->stem_pool2 = w->stem_pool2 != 0;
@@ -889,6 +932,22 @@ static af_status create_impl(af_engine* e, const af_weights* w) {
       rc = upload_stem_direct(w->convs[w->stem], &e->stem_w35);
       if (rc) return (af_status)rc;
       e->stem_direct = 1;
+    }
+  }
+  if (e->tf32 && !e->stem_pool2 && (e->S % 32 == 0) && getenv("AFB200_NO_TF32_STEM") == nullptr) {
+    const af_conv_desc& d = w->convs[w->stem];
+    if (d.kt == 5 && d.kh == 7 && d.kw == 7 && d.cin == 3 && d.cout == 64 && d.st == 1 && d.sh == 2 && d.sw == 2 && d.pt == 2 &&
+        d.ph == 3 && d.pw == 3) {
+      std::vector<float> w35((size_t)35 * 64 * 32, 0.f);
+      for (int co = 0; co < 64; ++co)
+        for (int c = 0; c < 3; ++c)
+          for (int dt = 0; dt < 5; ++dt)
+            for (int dy = 0; dy < 7; ++dy)
+              for (int dx = 0; dx < 7; ++dx)
+                w35[((size_t)(dt * 7 + dy) * 64 + co) * 32 + dx * 4 + c] =
+                    tf32_round(d.weight[((((size_t)co * 3 + c) * 5 + dt) * 7 + dy) * 7 + dx]);
+      AFB_CUDA(cudaMalloc(&e->stem_w35_tf32, w35.size() * sizeof(float)));
+      AFB_CUDA(cudaMemcpy(e->stem_w35_tf32, w35.data(), w35.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
   }
   e->blocks.assign(w->blocks, w->blocks + w->n_blocks);
@@ -941,7 +1000,7 @@ af_status af_create(af_handle* out, int32_t device, const af_weights* w, int32_t
     set_error("af_create: invalid arguments");
     return AF_ERR_INVALID;
   }
-  if (precision != AF_PREC_FP32 && precision != AF_PREC_BF16) {
+  if (precision != AF_PREC_FP32 && precision != AF_PREC_BF16 && precision != AF_PREC_TF32) {
     set_error("af_create: unknown precision %d", precision);
     return AF_ERR_INVALID;
   }
@@ -955,6 +1014,7 @@ af_status af_create(af_handle* out, int32_t device, const af_weights* w, int32_t
   af_engine* e = new af_engine();
   e->device = device;
   e->is_bf16 = precision == AF_PREC_BF16;
+  e->tf32 = precision == AF_PREC_TF32;
   e->esz = e->is_bf16 ? 2 : 4;
   e->T = w->clip_t; e->S = w->clip_s; e->max_batch = max_batch;
   e->stem = w->stem; e->fc_b = w->fc_bias; e->feat_dim = w->feature_dim;
@@ -1315,8 +1375,9 @@ af_status af_conv_ndhwc(const void* x_dev, const af_conv_desc* conv_host, const 
   }
   const bool is_bf16 = precision == AF_PREC_BF16;
   if (is_bf16) { int rc = conv_umma_init(); if (!rc) rc = conv_rows_init(); if (!rc) rc = conv_tsweep_init(); if (rc) return (af_status)rc; }
+  if (precision == AF_PREC_TF32) { int rc = conv_tf32_init(); if (rc) return (af_status)rc; }
   ConvLayer L;
-  int rc = upload_layer(*conv_host, is_bf16, L);
+  int rc = upload_layer(*conv_host, is_bf16, L, precision == AF_PREC_TF32);
   if (!rc) {
     Dims in = {t, hgt, wid, L.cin_p};
     const long long sW = in.C, sH = (long long)in.W * in.C, sT = sH * in.H, sB = sT * in.T;

@@ -81,6 +81,11 @@ int conv_rows_init();
 bool conv_tsweep_supported(const ConvProblem& p);
 int conv_tsweep_launch(const ConvProblem& p, cudaStream_t s);
 int conv_tsweep_init();
+// conv_tf32.cu: fp32 NDHWC activations, fp32 weights [taps][Cout][Cin], tcgen05.mma kind::tf32
+int conv_tf32_init();
+bool conv_tf32_supported(const ConvProblem& p);
+int conv_tf32_launch(const ConvProblem& p, cudaStream_t s);
+int conv_tf32_stem_launch(const void* clip_phys, int B, int T, int S, const void* w35, const float* bias, void* y, cudaStream_t s);
 int conv_stem_direct_launch(const void* clip_phys, int B, int T, int S, const void* w35, const float* bias_host, void* y,
                             int pool, cudaStream_t s, int force_per_frame = 0);
 // conv_bc_fused.cu (s2 bottleneck tail: 1x3x3 64->64 + ReLU, then 1x1x1 64->256 + residual + ReLU, one kernel)

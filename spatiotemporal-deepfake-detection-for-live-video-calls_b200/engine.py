@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib, synthetic
-from ._lib import AF_BF16, AF_F16, AF_F32, AF_PREC_BF16, AF_PREC_FP32, check, lib
+from ._lib import AF_BF16, AF_F16, AF_F32, AF_PREC_BF16, AF_PREC_FP32, AF_PREC_TF32, check, lib
 from .weights import FoldedWeights
 
 _DTYPES = {torch.float32: AF_F32, torch.bfloat16: AF_BF16, torch.float16: AF_F16}
@@ -45,7 +45,8 @@ class Engine:
         self.variant = variant
         fw = FoldedWeights(state_dict, clip_t, clip_s, variant)
         self.feature_dim = int(fw.struct.feature_dim)
-        prec = {"bf16": AF_PREC_BF16, "fp32": AF_PREC_FP32}[precision]
+        # "tf32": fp32 storage / accumulation, trunk convs on the tensor cores with TF32 operands (conv_tf32.cu)
+        prec = {"bf16": AF_PREC_BF16, "fp32": AF_PREC_FP32, "tf32": AF_PREC_TF32}[precision]
         torch.cuda.init()
         with torch.cuda.device(self.device):
             check(self._L.af_create(C.byref(self._h), device, C.byref(fw.struct), max_batch, prec), "af_create")
@@ -207,9 +208,10 @@ class Engine:
 
 
 def conv_ndhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride, pad, relu: bool,
-               residual: Optional[torch.Tensor] = None, impl: int = 0) -> torch.Tensor:
+               residual: Optional[torch.Tensor] = None, impl: int = 0, tf32: bool = False) -> torch.Tensor:
     """One folded conv on an NDHWC device tensor [B,T,H,W,C] (fp32 or bf16) through the
-    engine's kernels (test/diagnostic entry af_conv_ndhwc). weight: [cout,cin,kt,kh,kw] fp32."""
+    engine's kernels (test/diagnostic entry af_conv_ndhwc). weight: [cout,cin,kt,kh,kw] fp32.
+    tf32 (fp32 tensors only): the tensor-core kernel with TF32 operands instead of the exact FFMA kernel."""
     L = lib()
     assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
     B, T, H, W, Cin = x.shape
@@ -230,7 +232,7 @@ def conv_ndhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride
     y = torch.empty((B, To, Ho, Wo, cout), dtype=x.dtype, device=x.device)
     if residual is not None:
         assert residual.dtype == x.dtype and residual.is_contiguous()
-    prec = AF_PREC_BF16 if x.dtype == torch.bfloat16 else AF_PREC_FP32
+    prec = AF_PREC_BF16 if x.dtype == torch.bfloat16 else (AF_PREC_TF32 if tf32 else AF_PREC_FP32)
     with torch.cuda.device(x.device):
         check(L.af_conv_ndhwc(C.c_void_p(x.data_ptr()), C.byref(d),
                               C.c_void_p(residual.data_ptr()) if residual is not None else None,
