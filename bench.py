@@ -392,7 +392,7 @@ def run_ours(args):
     # parity of the very batch that was timed (rank 0): 4 clips back through af_crop_u8 -> CPU oracle
     parity = None
     if rank == 0 and not args.no_parity:
-        parity = legs.parity_leg(sd, args.variant, last_logits.cpu().numpy(), clip_sources, [0, B // 3, (2 * B) // 3, B - 1] if B >= 4 else list(range(B)), cores)
+        parity = legs.parity_leg(sd, args.variant, last_logits.cpu().numpy(), clip_sources, [0, B // 3, (2 * B) // 3, B - 1] if B >= 4 else list(range(B)), cores, args.precision)
 
     # the stock PyTorch (cuDNN) path on the same GPU, N=1 only
     gpu_baseline = None
