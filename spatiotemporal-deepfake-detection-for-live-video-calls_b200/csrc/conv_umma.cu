@@ -539,7 +539,8 @@ int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty
   const int tiles_per_cta = (tiles + ctas - 1) / ctas;
   const int chunks_per_group = (tiles_per_cta * (BLOCK_N / 64) + 1) / 2;
   up.out_per_group = has_res ? 0 : ((BLOCK_N <= 128 && chunks_per_group >= 2) ? 2 : 1);
-  const int res_default = BLOCK_N <= 128 ? 4 : 3;
+  static const char* rs256 = getenv("AFB200_RES_SLOTS_256");
+  const int res_default = BLOCK_N <= 128 ? 4 : (rs256 ? atoi(rs256) : 3);
   up.res_slots = has_res ? (chunks_per_group < 2 ? 2 : chunks_per_group < res_default ? chunks_per_group : res_default) : 0;
   const int fixed = (2 * up.out_per_group + 2 * up.res_slots) * OUT_STAGE_BYTES + 2 * BLOCK_N * 4 +
                     (2 * MAX_STAGES + 14) * 8 + 16 + 1024;
