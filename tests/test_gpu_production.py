@@ -416,3 +416,27 @@ def test_ring_put_boxes_crops_bit_exactly_like_whole_frames(dev, state_dict):
     want = crop_oracle.crop_align_from_frames(frames, bigs, tfm, lt, wh, 224)
     assert np.array_equal(got, want)
     eng.close()
+
+
+def test_new_entry_points_reject_bad_arguments(dev, state_dict):
+    """Error behaviour of the round-2 entries: bad boxes / slots for the ring feed, an odd frame count or a shortcut for
+    the pooled fused kernel.  Every failure is an Afb200Error with a message, nothing is launched."""
+    from afb200 import live
+    eng = afb200.Engine(state_dict, max_batch=1, precision="bf16")
+    ring = live.FrameRing(eng, 2, 64, 96)
+    host = torch.zeros((64, 96, 3), dtype=torch.uint8).pin_memory()
+    ring.put_boxes([0], [host.data_ptr()], np.array([[8, 8, 8, 40]]))            # empty box: skipped, not an error
+    with pytest.raises(afb200.Afb200Error, match="out of range"):
+        ring.put_boxes([0], [host.data_ptr()], np.array([[8, 8, 40, 65]]))       # rows past the slot
+    with pytest.raises(afb200.Afb200Error, match="out of range"):
+        ring.put_boxes([-1], [host.data_ptr()], np.array([[8, 8, 40, 40]]))
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 3, 16, 8, 64, generator=g).to(dev, torch.bfloat16)        # T = 3: no frame pairs
+    res = torch.randn(1, 3, 16, 8, 256, generator=g).to(dev, torch.bfloat16)
+    wb, bb = torch.randn(64, 64, 1, 3, 3) * 0.05, torch.zeros(64)
+    wc, bc = torch.randn(256, 64, 1, 1, 1) * 0.1, torch.zeros(256)
+    with pytest.raises(AssertionError):
+        afb200.conv_bc_fused_ndhwc(x, wb, bb, wc, bc, res, pool_t=True)
+    with pytest.raises(afb200.Afb200Error):
+        afb200.conv_bc_fused_ndhwc(x, torch.randn(64, 64, 1, 1, 1), bb, wc, bc, res)      # b must be 1x3x3
+    eng.close()
