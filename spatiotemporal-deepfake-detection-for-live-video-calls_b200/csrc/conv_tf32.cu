@@ -421,7 +421,13 @@ int conv_tf32_launch(const ConvProblem& p, cudaStream_t s) {
   const bool pointwise = p.kt == 1 && p.kh == 1 && p.kw == 1 && p.st == 1 && p.sh == 1 && p.sw == 1;
   tp.im2col = pointwise ? 0 : 1;
   tp.num_m_tiles = (int)((p.M + T_M - 1) / T_M);
-  const int bn = (p.Cout % 128 == 0 && (long long)tp.num_m_tiles * (p.Cout / 128) >= 2LL * g_t_sms) ? 128 : 64;
+  // tile width: the widest of 256 / 128 / 64 that still gives every SM ~2 tiles (an N = 64 TF32 MMA reads 6 KB of operands
+  // per 32 clocks and is shared-memory bound like its bf16 counterpart; N = 256 needs 12 KB per 128 clocks)
+  int bn = 64;
+  for (int cand : {256, 128})
+    if (p.Cout % cand == 0 && (long long)tp.num_m_tiles * (p.Cout / cand) >= 2LL * g_t_sms) { bn = cand; break; }
+  static const char* fbn = getenv("AFB200_TF32_BLOCK_N");
+  if (fbn && (atoi(fbn) == 64 || atoi(fbn) == 128 || atoi(fbn) == 256) && p.Cout % atoi(fbn) == 0) bn = atoi(fbn);
   tp.num_n_tiles = p.Cout / bn;
   alignas(64) CUtensorMap ta, tb, ty, tr;
   int rc = tp.im2col ? t_encode_im2col(&ta, p) : t_encode_2d(&ta, p.x, (uint64_t)p.M, (uint64_t)p.Cin, T_M, "A");
@@ -433,7 +439,8 @@ int conv_tf32_launch(const ConvProblem& p, cudaStream_t s) {
   if (rc) return rc;
   rc = t_encode_2d(&tr, p.res ? p.res : p.y, (uint64_t)p.M, (uint64_t)p.Cout, T_M, "R");
   if (rc) return rc;
-  return bn == 128 ? t_launch<128, false>(ta, tb, ty, tr, tp, s) : t_launch<64, false>(ta, tb, ty, tr, tp, s);
+  return bn == 256 ? t_launch<256, false>(ta, tb, ty, tr, tp, s)
+                   : bn == 128 ? t_launch<128, false>(ta, tb, ty, tr, tp, s) : t_launch<64, false>(ta, tb, ty, tr, tp, s);
 }
 
 // The stem on the tensor cores with TF32 operands.  clip_phys: the engine's padded fp32 NDHWC4 clip
