@@ -11,12 +11,11 @@
 // Work unit: one 8-wide x 16-tall output tile (128 pixels) of one frame.
 //   warp 0      TMA producer: the three dx-shifted 18-row halo boxes of the tile (the kh = 3 vertical taps are views of
 //               one box, as in conv_rows.cu); W_b (9 x 64 x 64) and W_c (256 x 64) are loaded once and stay resident
-//   warp 1      MMA issuer: b(i) -> acc_b (128 x 64 fp32, TMEM), then c(i-1): Yb(i-1) [128 x 64 bf16, TMEM] x W_c^T
-//               -> acc_c (128 x 256): c of a tile is issued AFTER b of the next one so the first epilogue hides behind it
+//   warp 1      MMA issuer: b(i) -> acc_b (128 x 64 fp32, TMEM), and c(i-1): Yb(i-1) [128 x 64 bf16, TMEM] x W_c^T
+//               -> acc_c (128 x 256): c of a tile rides inside b of the NEXT one so the first epilogue hides behind it
 //   warps 2-5   epilogue 1: acc_b -> +bias_b, ReLU, bf16 -> Yb written back to TENSOR MEMORY (tcgen05.st, two channels per
 //               column): the c MMA takes its A operand from TMEM, so the intermediate costs neither 16 KB of shared
-//               memory (which buys the third halo-ring slot: two slots could not cover a box's load latency) nor any
-//               shared-memory bandwidth
+//               memory (spent on a third halo-ring slot instead) nor any shared-memory bandwidth
 //   warps 6-13  epilogue 2 (two warpgroups, one per 128-channel HALF of acc_c): acc_c -> +bias_c +residual -> ReLU -> bf16,
 //               IN PLACE in the slot the residual tile was TMA-loaded into, then a TMA store from that slot.  The c GEMM
 //               is issued as two N = 128 halves at different points of the next tile's b MMAs (after its first and its
@@ -63,7 +62,7 @@ struct FusedParams {
   float bias_c[F_OUT];
   int x_tiles, y_tiles, frames;     // tiles per row / column of a frame, B*T frames
   int num_tiles;                    // work items per grid: tiles, or (kPoolT) frame-pair units of two tiles each
-  int prefetch;                     // L2-prefetch the next tile's inputs (AFB200_NO_L2_PREFETCH=1 turns it off)
+  int prefetch;                     // L2-prefetch the inputs of the tile this many tiles ahead (0 = off; AFB200_L2_PREFETCH)
 };
 
 // The j-th tile of this CTA.  Plain: tile = blockIdx.x + j * gridDim.x over (x tile, y tile, frame).  kPoolT: unit
