@@ -367,7 +367,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 // FOUR consecutive output frames (4 accumulators).  The 35 (dt,dy) weight tiles (140 KB) stay resident in shared
 // memory for the CTA's lifetime, and each of the unit's 8 input-frame boxes is loaded ONCE and used by every
 // (output frame, dt) pair it participates in (input frame f feeds output g with dt = f - g): 2 boxes per output
-// tile instead of 5 boxes + 5 weight groups, which takes the stem off the L2->SM bandwidth limit.
+// tile instead of 5 boxes + 5 weight groups, which takes the stem off the L2->SM bandwidth limit.  All n <= 4 output
+// frames a box feeds are issued as ONE 128 x 64n x 16 MMA (adjacent weight tiles, adjacent accumulators).
 constexpr int SW_W_BYTES = 35 * RB_N * 64;        // 143360
 constexpr int SW_A_STAGES = 2;
 

@@ -20,10 +20,11 @@
 //              (both walk their loops with all 32 lanes and issue through elect.sync, so descriptors and
 //               coordinates live in uniform registers and UTCHMMA/UTMALDG go out back to back)
 //   warps 2-9: two epilogue warpgroups on alternate 64-column chunks: tcgen05.ld -> +bias (+residual tile,
-//              TMA-prefetched two chunks ahead) -> ReLU -> bf16 -> swizzled smem -> TMA store; optional fused
-//              temporal max-pool (tile = 64 pixels x 2 frames).  Double-buffered against the next tile's main
-//              loop through the tmem_full/tmem_empty barriers.
-// Shared memory is carved at launch: residual layers trade operand stages for residual/output slots.
+//              TMA-prefetched into one of 3-4 slots and updated IN PLACE) -> ReLU inside the bf16x2 conversion ->
+//              swizzled smem -> TMA store; optional fused temporal max-pool (tile = 64 pixels x 2 frames).
+//              Double-buffered against the next tile's main loop through the tmem_full/tmem_empty barriers.
+// Shared memory is carved at launch: residual layers trade operand stages for residual/output slots; small launches
+// (batch 1-2) shrink the staging and deepen the operand ring.  kPair: 2-CTA clusters with cta_group::2 MMAs.
 // Programmatic dependent launch overlaps each kernel's prologue with its predecessor's tail.
 #include <cuda.h>
 
